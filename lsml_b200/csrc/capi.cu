@@ -1,0 +1,202 @@
+// capi.cu -- the C ABI of liblsml_b200.so (declared in include/lsml_b200.h).
+//
+// (1) the six drop-in symbols of lsml/util/_cutil/masked_gradient.c operating on HOST pointers
+//     (stage to the device, run the sm_100a kernel, copy back) and
+// (2) the lsml_* device-pointer entry points used by the Python host layer.
+//
+// There is no CPU fallback anywhere: if no CUDA device is usable the drop-in symbols print the
+// error and abort() (they have no error channel, like the reference's MI_CHECK_INDEX build,
+// helpers.c:18-33) and the lsml_* functions return a non-zero status.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include "lsml_internal.h"
+#include "../../include/lsml_b200.h"
+
+namespace lsml {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace lsml
+
+using namespace lsml;
+
+namespace {
+
+[[noreturn]] void die(const char* fn) {
+    fprintf(stderr, "liblsml_b200: %s failed: %s\n", fn, lsml_last_error());
+    fflush(stderr);
+    abort();
+}
+
+// RAII device buffer for the host-pointer drop-in path
+struct DevBuf {
+    void* p = nullptr;
+    int alloc(size_t bytes) { return check_cuda(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc"); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+// Host-pointer implementation shared by gmag_os{1,2,3}d.  Output buffers are copied IN first
+// so that voxels outside the mask keep whatever the caller had there (the reference only
+// writes masked voxels; masked_gradient.py:219 zero-fills before the call).
+int host_gmag_os(int ndim, const int* shape, double* A, bool* mask, double* nu, double* gmag,
+                 const double* dx) {
+    Geom g;
+    if (make_geom(g, ndim, shape, 1, dx)) return 1;
+    const size_t n = (size_t)g.voxels, nb = n * sizeof(double);
+    DevBuf dA, dM, dNu, dG;
+    if (dA.alloc(nb) || dM.alloc(n) || dNu.alloc(nb) || dG.alloc(nb)) return 2;
+    cudaStream_t s = 0;
+    LSML_CUDA(cudaMemcpyAsync(dA.p, A, nb, cudaMemcpyHostToDevice, s));
+    LSML_CUDA(cudaMemcpyAsync(dM.p, mask, n, cudaMemcpyHostToDevice, s));
+    LSML_CUDA(cudaMemcpyAsync(dNu.p, nu, nb, cudaMemcpyHostToDevice, s));
+    LSML_CUDA(cudaMemcpyAsync(dG.p, gmag, nb, cudaMemcpyHostToDevice, s));
+    int st = gmag_os_dense<double>(g, (const double*)dA.p, (const u8*)dM.p, (const double*)dNu.p,
+                                   (double*)dG.p, s);
+    if (st) return st;
+    LSML_CUDA(cudaMemcpyAsync(gmag, dG.p, nb, cudaMemcpyDeviceToHost, s));
+    LSML_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int host_gradient_centered(int ndim, const int* shape, double* A, bool* mask, double** d,
+                           double* gmag, const double* dx, int normalize) {
+    Geom g;
+    if (make_geom(g, ndim, shape, 1, dx)) return 1;
+    const size_t n = (size_t)g.voxels, nb = n * sizeof(double);
+    DevBuf dA, dM, dD, dG;
+    if (dA.alloc(nb) || dM.alloc(n) || dD.alloc(nb * ndim) || dG.alloc(nb)) return 2;
+    cudaStream_t s = 0;
+    LSML_CUDA(cudaMemcpyAsync(dA.p, A, nb, cudaMemcpyHostToDevice, s));
+    LSML_CUDA(cudaMemcpyAsync(dM.p, mask, n, cudaMemcpyHostToDevice, s));
+    for (int a = 0; a < ndim; ++a)
+        LSML_CUDA(cudaMemcpyAsync((char*)dD.p + a * nb, d[a], nb, cudaMemcpyHostToDevice, s));
+    LSML_CUDA(cudaMemcpyAsync(dG.p, gmag, nb, cudaMemcpyHostToDevice, s));
+    int st = gradient_centered_dense<double>(g, (const double*)dA.p, (const u8*)dM.p,
+                                             (double*)dD.p, (double*)dG.p, normalize, s);
+    if (st) return st;
+    for (int a = 0; a < ndim; ++a)
+        LSML_CUDA(cudaMemcpyAsync(d[a], (char*)dD.p + a * nb, nb, cudaMemcpyDeviceToHost, s));
+    LSML_CUDA(cudaMemcpyAsync(gmag, dG.p, nb, cudaMemcpyDeviceToHost, s));
+    LSML_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// (1) drop-in symbols
+// ---------------------------------------------------------------------------------------------
+void gmag_os3d(int m, int n, int p, double* A, bool* mask, double* nu, double* gmag,
+               double deli, double delj, double delk) {
+    const int shape[3] = {m, n, p};
+    const double dx[3] = {deli, delj, delk};
+    if (host_gmag_os(3, shape, A, mask, nu, gmag, dx)) die("gmag_os3d");
+}
+void gmag_os2d(int m, int n, double* A, bool* mask, double* nu, double* gmag, double deli,
+               double delj) {
+    const int shape[2] = {m, n};
+    const double dx[2] = {deli, delj};
+    if (host_gmag_os(2, shape, A, mask, nu, gmag, dx)) die("gmag_os2d");
+}
+void gmag_os1d(int m, double* A, bool* mask, double* nu, double* gmag, double deli) {
+    if (host_gmag_os(1, &m, A, mask, nu, gmag, &deli)) die("gmag_os1d");
+}
+void gradient_centered3d(int m, int n, int p, double* A, bool* mask, double* di, double* dj,
+                         double* dk, double* gmag, double deli, double delj, double delk,
+                         int normalize) {
+    const int shape[3] = {m, n, p};
+    const double dx[3] = {deli, delj, delk};
+    double* d[3] = {di, dj, dk};
+    if (host_gradient_centered(3, shape, A, mask, d, gmag, dx, normalize)) die("gradient_centered3d");
+}
+void gradient_centered2d(int m, int n, double* A, bool* mask, double* di, double* dj,
+                         double* gmag, double deli, double delj, int normalize) {
+    const int shape[2] = {m, n};
+    const double dx[2] = {deli, delj};
+    double* d[2] = {di, dj};
+    if (host_gradient_centered(2, shape, A, mask, d, gmag, dx, normalize)) die("gradient_centered2d");
+}
+void gradient_centered1d(int m, double* A, bool* mask, double* di, double* gmag, double deli,
+                         int normalize) {
+    double* d[1] = {di};
+    if (host_gradient_centered(1, &m, A, mask, d, gmag, &deli, normalize)) die("gradient_centered1d");
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) device entry points
+// ---------------------------------------------------------------------------------------------
+int lsml_version(void) { return 100; }
+const char* lsml_last_error(void) { return lsml::g_err; }
+long long lsml_launch_count(void) { return lsml::g_launches.load(); }
+
+int lsml_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { check_cuda(e, "cudaGetDeviceCount"); return -(int)e; }
+    return n;
+}
+
+int lsml_gmag_os_f64(int ndim, const int* shape, long long batch, const double* A,
+                     const uint8_t* mask, const double* nu, double* gmag, const double* dx,
+                     void* stream) {
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return 1;
+    return gmag_os_dense<double>(g, A, mask, nu, gmag, (cudaStream_t)stream);
+}
+int lsml_gmag_os_f32(int ndim, const int* shape, long long batch, const float* A,
+                     const uint8_t* mask, const float* nu, float* gmag, const double* dx,
+                     void* stream) {
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return 1;
+    return gmag_os_dense<float>(g, A, mask, nu, gmag, (cudaStream_t)stream);
+}
+int lsml_gradient_centered_f64(int ndim, const int* shape, long long batch, const double* A,
+                               const uint8_t* mask, double* grads, double* gmag,
+                               const double* dx, int normalize, void* stream) {
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return 1;
+    return gradient_centered_dense<double>(g, A, mask, grads, gmag, normalize, (cudaStream_t)stream);
+}
+int lsml_gradient_centered_f32(int ndim, const int* shape, long long batch, const float* A,
+                               const uint8_t* mask, float* grads, float* gmag,
+                               const double* dx, int normalize, void* stream) {
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return 1;
+    return gradient_centered_dense<float>(g, A, mask, grads, gmag, normalize, (cudaStream_t)stream);
+}
+
+long long lsml_compact_workspace_bytes(long long total) { return compact_workspace_bytes(total); }
+
+int lsml_compact_mask(long long total, long long voxels_per_item, const uint8_t* mask,
+                      long long* band_idx, long long* n_band, long long* item_offsets_out,
+                      void* workspace, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int st = compact_mask(total, mask, band_idx, n_band, workspace, s);
+    if (st) return st;
+    if (item_offsets_out != nullptr && voxels_per_item > 0)
+        return item_offsets(band_idx, n_band, voxels_per_item, total / voxels_per_item,
+                            item_offsets_out, s);
+    return 0;
+}
+
+}  // extern "C"
