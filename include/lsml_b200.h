@@ -73,12 +73,99 @@ int lsml_gradient_centered_f32(int ndim, const int *shape, long long batch, cons
 /* Band compaction (numpy boolean indexing `X[mask]`, lsml/core/model.py:388,394):
  * writes the ascending row-major flat indices of the non-zero mask bytes of the whole
  * batch (index = item*voxels + local) to band_idx (capacity total) and the count to *n_band
- * (device int64).  item_counts (device int64[batch], may be NULL) receives per-item counts.
+ * (device int64).  item_offsets (device int64[batch+1], may be NULL) receives the CSR offsets
+ * of the items inside band_idx.
  * workspace: lsml_compact_workspace_bytes(total) bytes of device memory. */
 long long lsml_compact_workspace_bytes(long long total);
 int lsml_compact_mask(long long total, long long voxels_per_item, const uint8_t *mask,
-                      long long *band_idx, long long *n_band, long long *item_counts,
+                      long long *band_idx, long long *n_band, long long *item_offsets,
                       void *workspace, void *stream);
+
+
+/* ---- image planes: one-time, u-independent (lsml/feature/provided/image.py) ---------------- */
+/* scipy.ndimage.gaussian_filter1d along `axis` (0..ndim-1), mode='reflect', evaluated in
+ * scipy's own summation order (bit-identical planes).  weights: DEVICE array of 2*radius+1
+ * doubles, already reversed as gaussian_filter1d does (image.py:28-29, 52-56); antisym=1 for
+ * order-1 kernels.  mode: 0 out=t, 1 out=t*t, 2 out+=t*t, 3 out=sqrt(out+t*t), 4 out=sqrt(t*t)
+ * (modes 1-4 build ImageEdgeSample's magnitude without temporaries, image.py:59-61). */
+int lsml_gauss1d_f64(int ndim, const int *shape, long long batch, const double *in, double *out,
+                     const double *weights, int radius, int antisym, int axis, int mode,
+                     void *stream);
+/* |numpy.gradient(img, *dx)| (ImageEdgeSample with sigma == 0, image.py:48-49) */
+int lsml_np_gradient_mag_f64(int ndim, const int *shape, long long batch, const double *in,
+                             double *out, const double *dx, void *stream);
+/* (img - img.mean()) / img.std() per item (lsml/core/model.py:328-329) */
+long long lsml_normalize_workspace_bytes(long long voxels, long long batch);
+int lsml_normalize_f64(long long voxels, long long batch, const double *img, double *out,
+                       void *workspace, void *stream);
+
+/* ---- per-iteration feature extraction ------------------------------------------------------- */
+/* Exact integer statistics of {u > 0} per item (Size / Moments / centre of mass, shape.py:28,
+ * 201-230): stats[item*8 + {0: count, 1..3: sum of index per padded axis, 4..6: sum of index^2,
+ * 7: number of exact zeros}] as uint64. */
+int lsml_global_stats(int ndim, const int *shape, long long batch, const double *u,
+                      unsigned long long *stats, void *stream);
+/* mean and population std of `nplanes` image planes over each item's band
+ * (InteriorImageAverage / InteriorImageVariation, image.py:78-121): out arrays [batch][nplanes] */
+long long lsml_band_stats_workspace_bytes(long long voxels, long long batch, int nplanes);
+int lsml_band_stats(long long voxels, long long batch, const double *planes,
+                    long long plane_stride, int nplanes, const long long *band_idx,
+                    const long long *item_offsets, double *mean, double *stdv, void *workspace,
+                    void *stream);
+/* BoundarySize for 2-D items: marching-squares length of {u = 0} (shape.py:70-85) */
+long long lsml_contour_workspace_bytes(int m, int n, long long batch);
+int lsml_contour_length(int ndim, const int *shape, long long batch, const double *u,
+                        const double *dx, double *boundary, void *workspace, void *stream);
+/* Feature program: column f has kind[f] in {0 plane sample (a=plane), 1 distance to centre of
+ * mass, 2 band mean (a=plane), 3 band std (a=plane), 4 size, 5 boundary size, 6 isoperimetric
+ * ratio, 7 moment (a=axis, b=order)}.  kind/a/b are HOST int arrays of length nfeat (<= 64). */
+int lsml_item_features(int nfeat, const int *kind, const int *a, const int *b, int ndim,
+                       const int *shape, long long batch, const double *dx, int nplanes,
+                       const unsigned long long *stats, const double *band_mean,
+                       const double *band_std, const double *boundary, double *item_feat,
+                       double *com, void *stream);
+/* FeatureMap.__call__(...)[mask] (feature_map.py:53-80): X is (n_band, nfeat) row-major */
+int lsml_assemble_features(int nfeat, const int *kind, const int *a, const int *b, int ndim,
+                           const int *shape, long long batch, const double *dx,
+                           const long long *band_idx, const long long *n_band,
+                           const double *planes, long long plane_stride,
+                           const double *item_feat, const double *com, double *X, void *stream);
+
+/* ---- regressor inference (model.py:388; parameters exported from scikit-learn) -------------- */
+/* mean/scale: StandardScaler parameters or NULL. */
+int lsml_linear_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
+                        const double *scale, const double *coef, double intercept, double *out,
+                        void *stream);
+/* nodes: 8-byte packed nodes (see regress.cu); divisor = n_estimators */
+int lsml_forest_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
+                        const double *scale, const void *nodes, const int *tree_base,
+                        const uint8_t *root_is_leaf, int n_trees, double divisor, double *out,
+                        void *stream);
+/* sizes: HOST int[n_layers+1]; W, b: HOST arrays of n_layers DEVICE pointers;
+ * act: 0 identity, 1 relu, 2 tanh, 3 logistic */
+int lsml_mlp_predict(const double *X, const long long *n_band, const double *mean,
+                     const double *scale, int n_layers, const int *sizes,
+                     const double *const *W, const double *const *b, int act, double *out,
+                     void *stream);
+
+/* ---- banded update u[mask] += step*v*|Du|_upwind (model.py:390-394) ------------------------- */
+/* new_u[b] receives the updated value of band voxel b; with apply != 0 it is also scattered
+ * into u.  gmag_out (may be NULL) receives the upwind gradient magnitude per band voxel. */
+int lsml_band_update(int ndim, const int *shape, long long batch, const double *dx, double *u,
+                     const double *vel, const long long *band_idx, const long long *n_band,
+                     double step, double *new_u, double *gmag_out, int apply, void *stream);
+
+/* ---- band rebuild: distance_transform(u, band, dx) (lsml/util/distance_transform.py:5-59) --- */
+long long lsml_fmm_workspace_bytes(long long total);
+int lsml_fmm_workspace_init(long long total, void *workspace, void *stream);
+/* mask (uint8, zero on first use) and workspace persist between calls; stats = lsml_global_stats
+ * of the same u; dist_out may be NULL (0 outside the band otherwise). */
+int lsml_fmm_rebuild(int ndim, const int *shape, long long batch, const double *dx,
+                     const double *u, double band, const unsigned long long *stats,
+                     uint8_t *mask, double *dist_out, void *workspace, void *stream);
+/* synchronous: copies the 8 int64 counters of the last rebuild to HOST out
+ * {n_init, n_cand, changed, sweeps, converged, prev_init, prev_cand, -} */
+int lsml_fmm_counters(long long total, void *workspace, long long *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,389 @@
+"""Device-resident level-set evolution engine: the hot path of lsml on one B200.
+
+One :class:`BandEngine` holds a *batch* of independent items (images or volumes of identical
+shape) entirely in HBM and advances all of them one iteration per :meth:`step`:
+
+    features = FeatureMap(u, img, dist, mask, dx)          lsml/feature/feature_map.py:53-80
+    v[mask]  = regressor.predict(features[mask])           lsml/core/model.py:388
+    gmag     = gmag_os(u, v, mask, dx)                     lsml/core/model.py:390
+    u[mask] += step * v[mask] * gmag[mask]                 lsml/core/model.py:394
+    dist, mask = distance_transform(u, band, dx)           lsml/core/model.py:397
+
+Data layout in HBM (all float64, C order):
+    u        (batch, *shape)            level sets, updated in place on the band
+    planes   (P, batch, *shape)         u-independent image planes, computed ONCE per image:
+                                        smoothed image / edge magnitude per sigma
+    mask     (batch, *shape) uint8      band mask (= the reference's ``mask``)
+    band_idx (B,) int64                 ascending flat indices item*voxels+local (numpy order)
+    X        (B, F)                     feature matrix, row order = band order
+    vel, new_u (B,)                     velocity and updated level-set value per band voxel
+
+All numerical work is done by the CUDA kernels behind ``liblsml_b200.so``; this class only
+owns buffers (torch tensors) and sequences launches on the current stream.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .regressors import export_regressor
+
+FK_PLANE, FK_DIST_COM, FK_BAND_MEAN, FK_BAND_STD = 0, 1, 2, 3
+FK_SIZE, FK_BOUNDARY, FK_ISOPERIMETRIC, FK_MOMENT = 4, 5, 6, 7
+
+
+def gaussian_kernel1d(sigma, order, radius):
+    """scipy.ndimage._filters._gaussian_kernel1d restated (same numpy operations, so the
+    weights are bit-identical to the ones scipy's gaussian_filter1d uses)."""
+    if order < 0:
+        raise ValueError("order must be non-negative")
+    exponent_range = np.arange(order + 1)
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi_x = np.exp(-0.5 / sigma2 * x ** 2)
+    phi_x = phi_x / phi_x.sum()
+    if order == 0:
+        return phi_x
+    q = np.zeros(order + 1)
+    q[0] = 1
+    D = np.diag(exponent_range[1:], 1)
+    P = np.diag(np.ones(order) / -sigma2, -1)
+    Q_deriv = D + P
+    for _ in range(order):
+        q = Q_deriv.dot(q)
+    q = (x[:, None] ** exponent_range).dot(q)
+    return q * phi_x
+
+
+def gaussian_weights(sigma, order, truncate=4.0):
+    """(reversed weights, radius) exactly as scipy.ndimage.gaussian_filter1d builds them."""
+    sd = float(sigma)
+    lw = int(truncate * sd + 0.5)
+    return np.ascontiguousarray(gaussian_kernel1d(sd, order, lw)[::-1]), lw
+
+
+class FeatureProgram:
+    """Feature specs (see oracle/oracle.py for the tuple vocabulary) compiled to the column
+    program of ``lsml_assemble_features`` plus the list of image planes it samples."""
+
+    def __init__(self, specs, ndim):
+        self.specs = [tuple(s) for s in specs]
+        self.ndim = ndim
+        self.planes = []          # ("sample" | "edge", sigma)
+        kind, a, b = [], [], []
+        self.needs_boundary = False
+        self.needs_band_stats = False
+        for spec in self.specs:
+            k = spec[0]
+            if k == "image_sample":
+                kind.append(FK_PLANE); a.append(self._plane("sample", spec[1])); b.append(0)
+            elif k == "image_edge":
+                kind.append(FK_PLANE); a.append(self._plane("edge", spec[1])); b.append(0)
+            elif k == "band_mean":
+                kind.append(FK_BAND_MEAN); a.append(self._plane("sample", spec[1])); b.append(0)
+                self.needs_band_stats = True
+            elif k == "band_std":
+                kind.append(FK_BAND_STD); a.append(self._plane("sample", spec[1])); b.append(0)
+                self.needs_band_stats = True
+            elif k == "size":
+                kind.append(FK_SIZE); a.append(0); b.append(0)
+            elif k == "boundary_size":
+                kind.append(FK_BOUNDARY); a.append(0); b.append(0)
+                self.needs_boundary = True
+            elif k == "isoperimetric":
+                kind.append(FK_ISOPERIMETRIC); a.append(0); b.append(0)
+                self.needs_boundary = True
+            elif k == "moments":
+                for axis in spec[1]:
+                    for order in spec[2]:
+                        if order not in (1, 2):
+                            raise NotImplementedError(
+                                "Moments of order %r: only orders 1 and 2 have a device kernel"
+                                % (order,))
+                        kind.append(FK_MOMENT); a.append(int(axis)); b.append(int(order))
+            elif k == "dist_to_com":
+                kind.append(FK_DIST_COM); a.append(0); b.append(0)
+            else:
+                raise NotImplementedError(
+                    "no device kernel registered for feature spec %r (there is no CPU "
+                    "fallback)" % (spec,))
+        if self.needs_boundary and ndim != 2:
+            raise NotImplementedError(
+                "BoundarySize / IsoperimetricRatio: only the 2-D (marching squares) kernel "
+                "exists; the 3-D Lewiner marching-cubes area is not implemented")
+        self.nfeat = len(kind)
+        if self.nfeat > 64:
+            raise ValueError("at most 64 feature columns")
+        self.kind = _lib.int_array(kind)
+        self.a = _lib.int_array(a)
+        self.b = _lib.int_array(b)
+
+    def _plane(self, what, sigma):
+        key = (what, float(sigma))
+        if key not in self.planes:
+            self.planes.append(key)
+        return self.planes.index(key)
+
+
+class BandEngine:
+    def __init__(self, shape, batch, dx=None, band=3.0, specs=(), device="cuda"):
+        _lib.require_cuda()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("BandEngine runs on CUDA devices only")
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        assert 1 <= self.ndim <= 3, "Only dimensions 1-3 supported."
+        self.batch = int(batch)
+        self.voxels = int(np.prod(self.shape))
+        self.total = self.voxels * self.batch
+        self.dx = (np.ones(self.ndim) if dx is None else np.asarray(dx, dtype=np.float64)).copy()
+        if self.dx.shape != (self.ndim,):
+            raise ValueError("`dx` has incorrect number of elements.")
+        self.band = float(band)
+        self.program = FeatureProgram(specs, self.ndim)
+        self._shape_c = _lib.int_array(self.shape)
+        self._dx_c = _lib.double_array(self.dx)
+        d, f64, i64 = self.device, torch.float64, torch.int64
+        full = (self.batch,) + self.shape
+        with torch.cuda.device(d):
+            self.u = torch.zeros(full, dtype=f64, device=d)
+            self.mask = torch.zeros(full, dtype=torch.uint8, device=d)
+            self.planes = torch.zeros((max(len(self.program.planes), 1),) + full, dtype=f64, device=d)
+            self.stats = torch.zeros((self.batch, 8), dtype=torch.int64, device=d)
+            self.n_band_dev = torch.zeros(1, dtype=i64, device=d)
+            self.item_offsets = torch.zeros(self.batch + 1, dtype=i64, device=d)
+            self.band_idx = torch.zeros(1, dtype=i64, device=d)
+            npl = max(len(self.program.planes), 1)
+            self.band_mean = torch.zeros((self.batch, npl), dtype=f64, device=d)
+            self.band_std = torch.zeros((self.batch, npl), dtype=f64, device=d)
+            self.boundary = torch.zeros(self.batch, dtype=f64, device=d)
+            self.item_feat = torch.zeros((self.batch, max(self.program.nfeat, 1)), dtype=f64, device=d)
+            self.com = torch.zeros((self.batch, 3), dtype=f64, device=d)
+            self._ws_compact = torch.empty(
+                int(_lib.lib.lsml_compact_workspace_bytes(_lib.c_i64(self.total))),
+                dtype=torch.uint8, device=d)
+            _lib.lib.lsml_band_stats_workspace_bytes.restype = _lib.c_i64
+            self._ws_band = torch.empty(max(8, int(_lib.lib.lsml_band_stats_workspace_bytes(
+                _lib.c_i64(self.voxels), _lib.c_i64(self.batch), ctypes.c_int(npl)))),
+                dtype=torch.uint8, device=d)
+            if self.program.needs_boundary:
+                _lib.lib.lsml_contour_workspace_bytes.restype = _lib.c_i64
+                self._ws_contour = torch.empty(int(_lib.lib.lsml_contour_workspace_bytes(
+                    ctypes.c_int(self.shape[0]), ctypes.c_int(self.shape[1]),
+                    _lib.c_i64(self.batch))), dtype=torch.uint8, device=d)
+            _lib.lib.lsml_fmm_workspace_bytes.restype = _lib.c_i64
+            self._ws_fmm = None       # allocated on the first band rebuild
+        self.n_band = 0
+        self._cap = 0
+        self.X = self.vel = self.new_u = None
+        self.band_voxel_iterations = 0
+        self.history = None           # list of (band_idx, new_u) per iteration when recording
+        self.last_fmm_counters = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return _lib.current_stream()
+
+    def _ensure_capacity(self, n):
+        if n <= self._cap:
+            return
+        cap = min(self.total, max(int(n * 1.5) + 1024, 4096))
+        cap = max(cap, n)
+        d, f64 = self.device, torch.float64
+        self.X = torch.empty((cap, max(self.program.nfeat, 1)), dtype=f64, device=d)
+        self.vel = torch.zeros(cap, dtype=f64, device=d)
+        self.new_u = torch.empty(cap, dtype=f64, device=d)
+        self._cap = cap
+
+    # ------------------------------------------------------------------ images
+    def load_images(self, imgs, normalize=True):
+        """imgs: (batch, *shape) float64 numpy array or CUDA tensor.  Computes every image plane
+        the feature program samples (one-time, u-independent)."""
+        with torch.cuda.device(self.device):
+            t = imgs if torch.is_tensor(imgs) else torch.from_numpy(np.ascontiguousarray(imgs))
+            t = t.to(self.device, dtype=torch.float64, non_blocking=True).contiguous()
+            if tuple(t.shape) != (self.batch,) + self.shape:
+                raise ValueError("`imgs` has shape {} but must be shape {}".format(
+                    tuple(t.shape), (self.batch,) + self.shape))
+            if normalize:
+                out = torch.empty_like(t)
+                _lib.lib.lsml_normalize_workspace_bytes.restype = _lib.c_i64
+                ws = torch.empty(int(_lib.lib.lsml_normalize_workspace_bytes(
+                    _lib.c_i64(self.voxels), _lib.c_i64(self.batch))), dtype=torch.uint8,
+                    device=self.device)
+                _lib.check(_lib.lib.lsml_normalize_f64(
+                    _lib.c_i64(self.voxels), _lib.c_i64(self.batch), _lib.ptr(t), _lib.ptr(out),
+                    _lib.ptr(ws), self._stream()), "normalize")
+                t = out
+            self.img = t
+            self._compute_planes()
+
+    def _gauss(self, src, dst, sigma, order, axis, mode):
+        w, radius = gaussian_weights(sigma, order)
+        wd = torch.from_numpy(w).to(self.device)
+        self._keep.append(wd)
+        _lib.check(_lib.lib.lsml_gauss1d_f64(
+            ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(src),
+            _lib.ptr(dst), _lib.ptr(wd), ctypes.c_int(radius), ctypes.c_int(1 if order else 0),
+            ctypes.c_int(axis), ctypes.c_int(mode), self._stream()), "gauss1d")
+
+    def _compute_planes(self):
+        self._keep = []
+        tmp = None
+        for p, (what, sigma) in enumerate(self.program.planes):
+            dst = self.planes[p]
+            if what == "sample":
+                if sigma == 0:
+                    dst.copy_(self.img)                              # image.py:22-23
+                else:                                                # image.py:25-31
+                    if tmp is None:
+                        tmp = torch.empty_like(self.img)
+                    src = self.img
+                    bufs = [tmp, dst] if self.ndim % 2 == 0 else [dst, tmp]
+                    for i in range(self.ndim):
+                        out = bufs[i % 2]
+                        self._gauss(src, out, sigma / self.dx[i], 0, i, 0)
+                        src = out
+                    assert src.data_ptr() == dst.data_ptr()
+            else:
+                if sigma == 0:                                       # image.py:48-49
+                    _lib.check(_lib.lib.lsml_np_gradient_mag_f64(
+                        ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch),
+                        _lib.ptr(self.img), _lib.ptr(dst), self._dx_c, self._stream()),
+                        "np_gradient_mag")
+                else:                                                # image.py:51-61
+                    for a in range(self.ndim):
+                        if self.ndim == 1:
+                            mode = 4
+                        elif a == 0:
+                            mode = 1
+                        elif a == self.ndim - 1:
+                            mode = 3
+                        else:
+                            mode = 2
+                        self._gauss(self.img, dst, sigma / self.dx[a], 1, a, mode)
+        torch.cuda.current_stream().synchronize()
+        self._keep = []
+
+    # ------------------------------------------------------------------ level sets / band
+    def set_level_sets(self, u0, mask=None):
+        """u0: (batch, *shape).  With ``mask`` None the band is rebuilt from u0
+        (InitializerBase.__call__, initializer_base.py:56-61); otherwise the given band mask is
+        used as is (for feature / update calls with a caller-supplied mask)."""
+        with torch.cuda.device(self.device):
+            t = u0 if torch.is_tensor(u0) else torch.from_numpy(np.ascontiguousarray(u0))
+            self.u.copy_(t.to(self.device, dtype=torch.float64).reshape(self.u.shape))
+            self._global_stats()
+            if mask is None:
+                self._rebuild_band()
+            else:
+                m = mask if torch.is_tensor(mask) else torch.from_numpy(np.ascontiguousarray(mask))
+                self.mask.copy_(m.to(self.device).reshape(self.mask.shape).to(torch.uint8))
+                self._ws_fmm = None   # the marcher's sparse state no longer matches `mask`
+                self._compact()
+
+    def _global_stats(self):
+        _lib.check(_lib.lib.lsml_global_stats(
+            ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(self.u),
+            _lib.ptr(self.stats), self._stream()), "global_stats")
+
+    def _rebuild_band(self, dist_out=None):
+        if self._ws_fmm is None:
+            nbytes = int(_lib.lib.lsml_fmm_workspace_bytes(_lib.c_i64(self.total)))
+            self._ws_fmm = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.mask.zero_()
+            _lib.check(_lib.lib.lsml_fmm_workspace_init(
+                _lib.c_i64(self.total), _lib.ptr(self._ws_fmm), self._stream()), "fmm_init")
+        _lib.check(_lib.lib.lsml_fmm_rebuild(
+            ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
+            _lib.ptr(self.u), ctypes.c_double(self.band), _lib.ptr(self.stats),
+            _lib.ptr(self.mask), _lib.ptr(dist_out), _lib.ptr(self._ws_fmm), self._stream()),
+            "fmm_rebuild")
+        self._compact()
+
+    def fmm_counters(self):
+        out = (ctypes.c_longlong * 8)()
+        _lib.check(_lib.lib.lsml_fmm_counters(_lib.c_i64(self.total), _lib.ptr(self._ws_fmm), out,
+                                              self._stream()), "fmm_counters")
+        return dict(n_init=out[0], n_cand=out[1], sweeps=out[3], converged=bool(out[4]))
+
+    def distance(self):
+        """The reference's ``dist`` (signed distance inside the band, 0 elsewhere)."""
+        dist = torch.empty_like(self.u)
+        with torch.cuda.device(self.device):
+            self._rebuild_band(dist_out=dist)
+        return dist
+
+    def _compact(self):
+        if self.band_idx.numel() < self.total:
+            # capacity: the band can be the whole grid (band == 0 or u == 0 everywhere)
+            self.band_idx = torch.empty(self.total, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib.lsml_compact_mask(
+            _lib.c_i64(self.total), _lib.c_i64(self.voxels), _lib.ptr(self.mask),
+            _lib.ptr(self.band_idx), _lib.ptr(self.n_band_dev), _lib.ptr(self.item_offsets),
+            _lib.ptr(self._ws_compact), self._stream()), "compact_mask")
+        self.n_band = int(self.n_band_dev.item())      # one host sync per iteration (capacity)
+        self._ensure_capacity(self.n_band)
+
+    # ------------------------------------------------------------------ features
+    def compute_features(self):
+        """FeatureMap on the current band -> X[:n_band] (band order)."""
+        pr = self.program
+        if self.n_band == 0 or pr.nfeat == 0:
+            return self.X[:0] if self.X is not None else None
+        npl = len(pr.planes)
+        stride = self.total
+        if pr.needs_band_stats:
+            _lib.check(_lib.lib.lsml_band_stats(
+                _lib.c_i64(self.voxels), _lib.c_i64(self.batch), _lib.ptr(self.planes),
+                _lib.c_i64(stride), ctypes.c_int(npl), _lib.ptr(self.band_idx),
+                _lib.ptr(self.item_offsets), _lib.ptr(self.band_mean), _lib.ptr(self.band_std),
+                _lib.ptr(self._ws_band), self._stream()), "band_stats")
+        if pr.needs_boundary:
+            _lib.check(_lib.lib.lsml_contour_length(
+                ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(self.u),
+                self._dx_c, _lib.ptr(self.boundary), _lib.ptr(self._ws_contour), self._stream()),
+                "contour_length")
+        _lib.check(_lib.lib.lsml_item_features(
+            ctypes.c_int(pr.nfeat), pr.kind, pr.a, pr.b, ctypes.c_int(self.ndim), self._shape_c,
+            _lib.c_i64(self.batch), self._dx_c, ctypes.c_int(max(npl, 1)), _lib.ptr(self.stats),
+            _lib.ptr(self.band_mean), _lib.ptr(self.band_std), _lib.ptr(self.boundary),
+            _lib.ptr(self.item_feat), _lib.ptr(self.com), self._stream()), "item_features")
+        _lib.check(_lib.lib.lsml_assemble_features(
+            ctypes.c_int(pr.nfeat), pr.kind, pr.a, pr.b, ctypes.c_int(self.ndim), self._shape_c,
+            _lib.c_i64(self.batch), self._dx_c, _lib.ptr(self.band_idx), _lib.ptr(self.n_band_dev),
+            _lib.ptr(self.planes), _lib.c_i64(stride), _lib.ptr(self.item_feat),
+            _lib.ptr(self.com), _lib.ptr(self.X), self._stream()), "assemble_features")
+        return self.X[:self.n_band]
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, regressor, step, rebuild=True, record=False):
+        """One evolution iteration of every item.  Returns the number of band voxels updated."""
+        with torch.cuda.device(self.device):
+            nb = self.n_band
+            if nb == 0:                       # `if mask.any()` (model.py:381): nothing to do
+                if record and self.history is not None:
+                    self.history.append(None)
+                return 0
+            reg = export_regressor(regressor, self.device)
+            if reg.n_features != self.program.nfeat:
+                raise ValueError("regressor expects {} features, feature map has {}".format(
+                    reg.n_features, self.program.nfeat))
+            self.compute_features()
+            reg.predict_into(self.X, self.n_band_dev, self.vel)
+            _lib.check(_lib.lib.lsml_band_update(
+                ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
+                _lib.ptr(self.u), _lib.ptr(self.vel), _lib.ptr(self.band_idx),
+                _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)), _lib.ptr(self.new_u),
+                _lib.c_p(0), ctypes.c_int(1), self._stream()), "band_update")
+            if record:
+                if self.history is None:
+                    self.history = []
+                self.history.append((self.band_idx[:nb].clone(), self.new_u[:nb].clone()))
+            self.band_voxel_iterations += nb
+            self._global_stats()
+            if rebuild:
+                self._rebuild_band()
+            return nb

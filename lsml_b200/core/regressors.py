@@ -1,0 +1,200 @@
+"""Export host-trained scikit-learn regressors to flat device arrays.
+
+The reference calls ``regression_model.predict(features[mask])`` with whatever class the user
+passed to ``fit`` (lsml/core/model.py:388, fit_job_handler.py:412-428, 504); the shipped examples
+use ``Pipeline(StandardScaler, LinearRegression)`` (examples/hamburger2d/main.py:35-41) and
+``Pipeline(StandardScaler, RandomForestRegressor)`` (examples/gestalt2d/main.py:46-55).
+Training stays on the host; only ``predict`` runs on the GPU, with scikit-learn's arithmetic
+(see lsml_b200/csrc/regress.cu).  Unknown model classes raise ``TypeError``: there is no
+host-callback fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _dev(a, device, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a if dtype is None else np.asarray(a, dtype=dtype)))
+    return t.to(device)
+
+
+class DeviceRegressor:
+    """Base: optional StandardScaler parameters + ``predict_into``."""
+
+    def __init__(self, n_features, scaler, device):
+        self.n_features = int(n_features)
+        self.device = device
+        if scaler is not None:
+            mean, scale = scaler
+            self.mean = _dev(mean, device, np.float64)
+            self.scale = _dev(scale, device, np.float64)
+        else:
+            self.mean = self.scale = None
+
+    def predict_into(self, X, n_band, out):
+        raise NotImplementedError
+
+    def predict(self, X):
+        """Convenience: X CUDA tensor (B, F) -> CUDA tensor (B,)."""
+        X = X.contiguous()
+        n_band = torch.tensor([X.shape[0]], dtype=torch.int64, device=X.device)
+        out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+        with torch.cuda.device(X.device):
+            self.predict_into(X, n_band, out)
+        return out
+
+
+class LinearDeviceRegressor(DeviceRegressor):
+    def __init__(self, coef, intercept, scaler, device):
+        coef = np.asarray(coef, dtype=np.float64).ravel()
+        super().__init__(coef.size, scaler, device)
+        self.coef = _dev(coef, device)
+        self.intercept = float(np.asarray(intercept).ravel()[0]) if np.ndim(intercept) else float(intercept)
+
+    def predict_into(self, X, n_band, out):
+        _lib.check(_lib.lib.lsml_linear_predict(
+            _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
+            _lib.ptr(self.scale), _lib.ptr(self.coef), ctypes.c_double(self.intercept),
+            _lib.ptr(out), _lib.current_stream()), "linear_predict")
+
+
+def _round_down_to_f32(thr):
+    """Largest float32 <= thr, so that `x_f32 <= thr_f64` <=> `x_f32 <= thr_f32`."""
+    t32 = thr.astype(np.float32)
+    too_big = t32.astype(np.float64) > thr
+    t32[too_big] = np.nextafter(t32[too_big], np.float32(-np.inf))
+    return t32
+
+
+def pack_trees(trees, n_features):
+    """sklearn ``Tree`` objects -> (nodes uint32[n,2], tree_base int32[T], root_is_leaf uint8[T]).
+
+    Nodes are renumbered breadth-first per tree so that the two children of an internal node are
+    adjacent; see regress.cu for the 8-byte layout.
+    """
+    all_nodes, bases, root_leaf = [], [], []
+    base = 0
+    for tree in trees:
+        left, right = tree.children_left, tree.children_right
+        feat, thr = tree.feature, tree.threshold
+        val = tree.value.reshape(tree.node_count, -1)[:, 0].astype(np.float64)
+        n = tree.node_count
+        if n >= (1 << 22):
+            raise ValueError("tree with %d nodes exceeds the 22-bit child index" % n)
+        new_id = np.full(n, -1, dtype=np.int64)
+        order = [0]
+        new_id[0] = 0
+        head = 0
+        while head < len(order):
+            o = order[head]
+            head += 1
+            if left[o] != -1:
+                new_id[left[o]] = len(order)
+                order.append(left[o])
+                new_id[right[o]] = len(order)
+                order.append(right[o])
+        order = np.asarray(order)
+        is_leaf = left[order] == -1
+        nodes = np.zeros((n, 2), dtype=np.uint32)
+        # leaves: the float64 value as (lo, hi) words
+        nodes[is_leaf] = val[order[is_leaf]].view(np.uint32).reshape(-1, 2)
+        io = order[~is_leaf]
+        if (feat[io] >= n_features).any() or (feat[io] > 254).any():
+            raise ValueError("tree uses a feature index outside the feature map")
+        t32 = _round_down_to_f32(thr[io])
+        lnew = new_id[left[io]]
+        meta = ((feat[io].astype(np.uint32) << np.uint32(24)) |
+                ((left[left[io]] == -1).astype(np.uint32) << np.uint32(23)) |
+                ((left[right[io]] == -1).astype(np.uint32) << np.uint32(22)) |
+                lnew.astype(np.uint32))
+        nodes[~is_leaf, 0] = t32.view(np.uint32)
+        nodes[~is_leaf, 1] = meta
+        all_nodes.append(nodes)
+        bases.append(base)
+        root_leaf.append(1 if left[0] == -1 else 0)
+        base += n
+    return (np.concatenate(all_nodes, axis=0), np.asarray(bases, dtype=np.int32),
+            np.asarray(root_leaf, dtype=np.uint8))
+
+
+class ForestDeviceRegressor(DeviceRegressor):
+    def __init__(self, trees, n_features, divisor, scaler, device):
+        super().__init__(n_features, scaler, device)
+        nodes, bases, root_leaf = pack_trees(trees, n_features)
+        self.n_trees = len(bases)
+        self.n_nodes = int(nodes.shape[0])
+        self.nodes = _dev(nodes, device)
+        self.tree_base = _dev(bases, device)
+        self.root_is_leaf = _dev(root_leaf, device)
+        self.divisor = float(divisor)
+
+    def predict_into(self, X, n_band, out):
+        _lib.check(_lib.lib.lsml_forest_predict(
+            _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
+            _lib.ptr(self.scale), _lib.ptr(self.nodes), _lib.ptr(self.tree_base),
+            _lib.ptr(self.root_is_leaf), ctypes.c_int(self.n_trees),
+            ctypes.c_double(self.divisor), _lib.ptr(out), _lib.current_stream()),
+            "forest_predict")
+
+
+_ACT = {"identity": 0, "relu": 1, "tanh": 2, "logistic": 3}
+
+
+class MlpDeviceRegressor(DeviceRegressor):
+    def __init__(self, coefs, intercepts, activation, scaler, device):
+        super().__init__(coefs[0].shape[0], scaler, device)
+        if coefs[-1].shape[1] != 1:
+            raise ValueError("only single-output MLP regressors are supported")
+        self.W = [_dev(w, device, np.float64) for w in coefs]
+        self.b = [_dev(b, device, np.float64) for b in intercepts]
+        self.sizes = [coefs[0].shape[0]] + [w.shape[1] for w in coefs]
+        self.act = _ACT[activation]
+
+    def predict_into(self, X, n_band, out):
+        n = len(self.W)
+        Wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.W])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in self.b])
+        _lib.check(_lib.lib.lsml_mlp_predict(
+            _lib.ptr(X), _lib.ptr(n_band), _lib.ptr(self.mean), _lib.ptr(self.scale),
+            ctypes.c_int(n), _lib.int_array(self.sizes), Wp, bp, ctypes.c_int(self.act),
+            _lib.ptr(out), _lib.current_stream()), "mlp_predict")
+
+
+def export_regressor(model, device="cuda"):
+    """Turn a fitted scikit-learn regressor (optionally inside a Pipeline with a StandardScaler)
+    into a :class:`DeviceRegressor`."""
+    if isinstance(model, DeviceRegressor):
+        return model
+    device = torch.device(device)
+    scaler = None
+    final = model
+    cls = type(model).__name__
+    if cls == "Pipeline":
+        steps = [s for _, s in model.steps if s is not None and s != "passthrough"]
+        final = steps[-1]
+        pre = steps[:-1]
+        if len(pre) > 1 or (pre and type(pre[0]).__name__ != "StandardScaler"):
+            raise TypeError("only Pipeline([StandardScaler,] regressor) can be exported")
+        if pre:
+            sc = pre[0]
+            nfeat = sc.n_features_in_
+            mean = sc.mean_ if sc.with_mean and sc.mean_ is not None else np.zeros(nfeat)
+            scale = sc.scale_ if sc.with_std and sc.scale_ is not None else np.ones(nfeat)
+            scaler = (mean, scale)
+    name = type(final).__name__
+    if name in ("LinearRegression", "Ridge", "Lasso", "ElasticNet", "SGDRegressor",
+                "HuberRegressor", "BayesianRidge"):
+        return LinearDeviceRegressor(final.coef_, final.intercept_, scaler, device)
+    if name in ("RandomForestRegressor", "ExtraTreesRegressor"):
+        trees = [e.tree_ for e in final.estimators_]
+        return ForestDeviceRegressor(trees, final.n_features_in_, len(trees), scaler, device)
+    if name in ("DecisionTreeRegressor", "ExtraTreeRegressor"):
+        return ForestDeviceRegressor([final.tree_], final.n_features_in_, 1.0, scaler, device)
+    if name == "MLPRegressor":
+        return MlpDeviceRegressor(final.coefs_, final.intercepts_, final.activation, scaler, device)
+    raise TypeError("no device exporter for regressor class %r (supported: linear models, "
+                    "RandomForest/ExtraTrees/DecisionTree regressors, MLPRegressor, optionally "
+                    "behind a StandardScaler in a Pipeline); there is no CPU fallback" % name)

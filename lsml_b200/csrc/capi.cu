@@ -199,4 +199,110 @@ int lsml_compact_mask(long long total, long long voxels_per_item, const uint8_t*
     return 0;
 }
 
+#define GEOM(g) Geom g; if (make_geom(g, ndim, shape, batch, dx)) return 1
+
+int lsml_gauss1d_f64(int ndim, const int* shape, long long batch, const double* in, double* out,
+                     const double* weights, int radius, int antisym, int axis, int mode,
+                     void* stream) {
+    const double* dx = nullptr;
+    GEOM(g);
+    if (axis < 0 || axis >= ndim) { set_error("gauss1d: axis %d out of range", axis); return 1; }
+    return gauss1d(g, in, out, weights, radius, antisym, 3 - ndim + axis, mode, (cudaStream_t)stream);
+}
+int lsml_np_gradient_mag_f64(int ndim, const int* shape, long long batch, const double* in,
+                             double* out, const double* dx, void* stream) {
+    GEOM(g);
+    return np_gradient_mag(g, in, out, (cudaStream_t)stream);
+}
+long long lsml_normalize_workspace_bytes(long long voxels, long long batch) {
+    return normalize_workspace_bytes(voxels, batch);
+}
+int lsml_normalize_f64(long long voxels, long long batch, const double* img, double* out,
+                       void* workspace, void* stream) {
+    return normalize_images(voxels, batch, img, out, workspace, (cudaStream_t)stream);
+}
+int lsml_global_stats(int ndim, const int* shape, long long batch, const double* u,
+                      unsigned long long* stats, void* stream) {
+    const double* dx = nullptr;
+    GEOM(g);
+    return global_stats(g, u, stats, (cudaStream_t)stream);
+}
+long long lsml_band_stats_workspace_bytes(long long voxels, long long batch, int nplanes) {
+    return band_stats_workspace_bytes(voxels, batch, nplanes);
+}
+int lsml_band_stats(long long voxels, long long batch, const double* planes,
+                    long long plane_stride, int nplanes, const long long* band_idx,
+                    const long long* item_offsets, double* mean, double* stdv, void* workspace,
+                    void* stream) {
+    return band_stats(voxels, batch, planes, plane_stride, nplanes, band_idx, item_offsets, mean,
+                      stdv, workspace, (cudaStream_t)stream);
+}
+long long lsml_contour_workspace_bytes(int m, int n, long long batch) {
+    return contour_workspace_bytes(m, n, batch);
+}
+int lsml_contour_length(int ndim, const int* shape, long long batch, const double* u,
+                        const double* dx, double* boundary, void* workspace, void* stream) {
+    GEOM(g);
+    return contour_length(g, u, boundary, workspace, (cudaStream_t)stream);
+}
+int lsml_item_features(int nfeat, const int* kind, const int* a, const int* b, int ndim,
+                       const int* shape, long long batch, const double* dx, int nplanes,
+                       const unsigned long long* stats, const double* band_mean,
+                       const double* band_std, const double* boundary, double* item_feat,
+                       double* com, void* stream) {
+    GEOM(g);
+    return item_features_c(nfeat, kind, a, b, g, nplanes, stats, band_mean, band_std, boundary,
+                           item_feat, com, (cudaStream_t)stream);
+}
+int lsml_assemble_features(int nfeat, const int* kind, const int* a, const int* b, int ndim,
+                           const int* shape, long long batch, const double* dx,
+                           const long long* band_idx, const long long* n_band,
+                           const double* planes, long long plane_stride,
+                           const double* item_feat, const double* com, double* X, void* stream) {
+    GEOM(g);
+    return assemble_features_c(nfeat, kind, a, b, g, band_idx, n_band, planes, plane_stride,
+                               item_feat, com, X, (cudaStream_t)stream);
+}
+int lsml_linear_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
+                        const double* scale, const double* coef, double intercept, double* out,
+                        void* stream) {
+    return linear_predict(X, n_band, nfeat, mean, scale, coef, intercept, out, (cudaStream_t)stream);
+}
+int lsml_forest_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
+                        const double* scale, const void* nodes, const int* tree_base,
+                        const uint8_t* root_is_leaf, int n_trees, double divisor, double* out,
+                        void* stream) {
+    return forest_predict(X, n_band, nfeat, mean, scale, nodes, tree_base, root_is_leaf, n_trees,
+                          divisor, out, (cudaStream_t)stream);
+}
+int lsml_mlp_predict(const double* X, const long long* n_band, const double* mean,
+                     const double* scale, int n_layers, const int* sizes,
+                     const double* const* W, const double* const* b, int act, double* out,
+                     void* stream) {
+    return mlp_predict(X, n_band, mean, scale, n_layers, sizes, W, b, act, out, (cudaStream_t)stream);
+}
+int lsml_band_update(int ndim, const int* shape, long long batch, const double* dx, double* u,
+                     const double* vel, const long long* band_idx, const long long* n_band,
+                     double step, double* new_u, double* gmag_out, int apply, void* stream) {
+    GEOM(g);
+    return band_update(g, u, vel, band_idx, n_band, step, new_u, gmag_out, apply, (cudaStream_t)stream);
+}
+long long lsml_fmm_workspace_bytes(long long total) { return fmm_workspace_bytes(total); }
+int lsml_fmm_workspace_init(long long total, void* workspace, void* stream) {
+    return fmm_workspace_init(total, workspace, (cudaStream_t)stream);
+}
+int lsml_fmm_rebuild(int ndim, const int* shape, long long batch, const double* dx,
+                     const double* u, double band, const unsigned long long* stats,
+                     uint8_t* mask, double* dist_out, void* workspace, void* stream) {
+    GEOM(g);
+    return fmm_rebuild(g, u, band, stats, mask, dist_out, workspace, (cudaStream_t)stream);
+}
+int lsml_fmm_counters(long long total, void* workspace, long long* out, void* stream) {
+    const i64* dev = nullptr;
+    fmm_counters_ptr(total, workspace, &dev);
+    LSML_CUDA(cudaMemcpyAsync(out, dev, 8 * sizeof(i64), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LSML_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
 }  // extern "C"

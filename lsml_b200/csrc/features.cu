@@ -1,0 +1,604 @@
+// features.cu -- per-voxel feature extraction on the narrow band.
+//
+// One-time per image (u-independent, lsml/feature/provided/image.py):
+//   gauss1d_kernel        scipy.ndimage.gaussian_filter1d (order 0/1, mode='reflect'), evaluated
+//                         in scipy's NI_Correlate1D order so the planes are bit-identical:
+//                         tmp = x[0]*w[0]; for jj=-r..-1: tmp += (x[jj] +- x[-jj]) * w[jj]
+//   np_gradient_mag_kernel numpy.gradient(img, *dx) magnitude (ImageEdgeSample sigma=0)
+//   normalize_kernel      (img - mean) / std per item (lsml/core/model.py:328-329)
+// Every iteration:
+//   global_stats_kernel   {u>0}: count, sum idx, sum idx^2 per axis as EXACT int64 (Size,
+//                         Moments, centre of mass; shape.py:28, 214-230)
+//   band_sum_kernel       per-item band sums of the image planes (InteriorImageAverage /
+//                         Variation are band statistics, image.py:83-119) -- two-stage,
+//                         fixed-shape, deterministic
+//   contour_length_kernel marching squares total length (BoundarySize 2-D, shape.py:70-85)
+//   item_features_kernel  turns the raw sums into the per-item ("global") feature values
+//   assemble_kernel       writes the (B, F) feature matrix in band order (feature_map.py:53-80)
+#include "lsml_internal.h"
+
+namespace lsml {
+
+// ---------------------------------------------------------------------------------------------
+// separable Gaussian (order 0: symmetric, order 1: antisymmetric), scipy 'reflect' boundary
+// ---------------------------------------------------------------------------------------------
+enum GaussMode { GM_STORE = 0, GM_SQ_FIRST = 1, GM_SQ_ADD = 2, GM_SQ_ADD_SQRT = 3, GM_SQ_SQRT = 4 };
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    // (d c b a | a b c d | d c b a): period 2n
+    const int period = 2 * n;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < n ? m : period - 1 - m;
+}
+
+__global__ void __launch_bounds__(256)
+gauss1d_kernel(const double* __restrict__ in, double* __restrict__ out,
+               const double* __restrict__ w /* centre at w[r] */, int r, int antisym,
+               int n0, int n1, int n2, int axis, i64 rows, int mode) {
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
+    if (k >= n2 || row >= rows) return;
+    const i64 l = row * n2 + k;
+    int c, n; i64 st;
+    if (axis == 2) { c = k; n = n2; st = 1; }
+    else if (axis == 1) { c = (int)(row % n1); n = n1; st = n2; }
+    else { c = (int)((row / n1) % n0); n = n0; st = (i64)n1 * n2; }
+    const double* base = in + (l - (i64)c * st);
+    double tmp = __ldg(base + (i64)c * st) * __ldg(w + r);
+    const bool interior = (c - r >= 0) && (c + r < n);
+    for (int jj = -r; jj < 0; ++jj) {
+        const int ia = interior ? c + jj : reflect_index(c + jj, n);
+        const int ib = interior ? c - jj : reflect_index(c - jj, n);
+        const double a = __ldg(base + (i64)ia * st), b = __ldg(base + (i64)ib * st);
+        const double pair = antisym ? (a - b) : (a + b);
+        tmp = tmp + pair * __ldg(w + r + jj);
+    }
+    if (mode == GM_STORE) out[l] = tmp;
+    else if (mode == GM_SQ_FIRST) out[l] = tmp * tmp;
+    else if (mode == GM_SQ_ADD) out[l] = out[l] + tmp * tmp;
+    else if (mode == GM_SQ_ADD_SQRT) out[l] = sqrt(out[l] + tmp * tmp);
+    else out[l] = sqrt(tmp * tmp);
+}
+
+// numpy.gradient along one axis (edge_order=1): interior (f[+1]-f[-1])/(2 dx), ends (f1-f0)/dx
+__device__ __forceinline__ double np_grad_axis(const double* __restrict__ A, i64 l, i64 st, int c,
+                                               int n, double dx) {
+    if (n == 1) return 0.0;   // numpy raises for extent-1 axes; never reached from the host API
+    if (c == 0) return (__ldg(A + l + st) - __ldg(A + l)) / dx;
+    if (c == n - 1) return (__ldg(A + l) - __ldg(A + l - st)) / dx;
+    return (__ldg(A + l + st) - __ldg(A + l - st)) / (2. * dx);
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+np_gradient_mag_kernel(const double* __restrict__ A, double* __restrict__ out, int n0, int n1,
+                       int n2, i64 rows, double dx0, double dx1, double dx2) {
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
+    if (k >= n2 || row >= rows) return;
+    const i64 l = row * n2 + k;
+    double acc = 0.0;   // reduce(lambda a, b: a + b**2, gradients, zeros) ** 0.5  (image.py:59-61)
+    if (NDIM >= 3) {
+        const double g = np_grad_axis(A, l, (i64)n1 * n2, (int)((row / n1) % n0), n0, dx0);
+        acc = acc + g * g;
+    }
+    if (NDIM >= 2) {
+        const double g = np_grad_axis(A, l, (i64)n2, (int)(row % n1), n1, dx1);
+        acc = acc + g * g;
+    }
+    const double g = np_grad_axis(A, l, (i64)1, k, n2, dx2);
+    acc = acc + g * g;
+    out[l] = sqrt(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic per-item sums over a dense array: stage 1 (slices x items), stage 2 (one warp)
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+
+// mode 0: sum x ; mode 1: sum (x - mean[item])^2
+__global__ void __launch_bounds__(RS_THREADS)
+dense_sum_partial_kernel(const double* __restrict__ x, i64 voxels, int slices, int mode,
+                         const double* __restrict__ mean, double* __restrict__ partial) {
+    __shared__ double red[32];
+    const int item = blockIdx.y, s = blockIdx.x;
+    const i64 per = (voxels + slices - 1) / slices;
+    const i64 lo = min(voxels, (i64)s * per), hi = min(voxels, lo + per);
+    const double* p = x + (i64)item * voxels;
+    const double mu = mode ? mean[item] : 0.0;
+    double acc = 0.0;
+    for (i64 i = lo + threadIdx.x; i < hi; i += RS_THREADS) {
+        const double v = __ldg(p + i);
+        if (mode) { const double d = v - mu; acc += d * d; } else acc += v;
+    }
+    const double tot = block_sum<double>(acc, red);
+    if (threadIdx.x == 0) partial[(i64)item * slices + s] = tot;
+}
+
+// final: out[item] = f(sum partial) ; op 0: sum/count  op 1: sqrt(sum/count)
+__global__ void sum_final_kernel(const double* __restrict__ partial, int slices, i64 batch,
+                                 double count, int op, double* __restrict__ out) {
+    const i64 item = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= batch) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int s = lane; s < slices; s += 32) acc += partial[item * slices + s];
+    acc = warp_sum(acc);
+    if (lane == 0) out[item] = op == 0 ? acc / count : sqrt(acc / count);
+}
+
+__global__ void __launch_bounds__(256)
+normalize_kernel(const double* __restrict__ img, double* __restrict__ out, i64 voxels,
+                 const double* __restrict__ mean, const double* __restrict__ stdv) {
+    const int item = blockIdx.y;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= voxels) return;
+    const i64 l = (i64)item * voxels + i;
+    out[l] = (img[l] - mean[item]) / stdv[item];   // model.py:329
+}
+
+// ---------------------------------------------------------------------------------------------
+// {u > 0} statistics as exact integers: stats[item][0]=count, [1..3]=sum idx_a, [4..6]=sum idx_a^2
+// (padded axes), [7] = #(u == 0).  atomicAdd on integers is order-independent => deterministic.
+// ---------------------------------------------------------------------------------------------
+constexpr int GS_ROWS_PER_CTA = 32;
+
+__global__ void __launch_bounds__(256)
+global_stats_kernel(const double* __restrict__ u, int n0, int n1, int n2, u64* __restrict__ stats) {
+    __shared__ u64 red[32];
+    const int item = blockIdx.y;
+    const i64 rows_per_item = (i64)n0 * n1;
+    const i64 row0 = (i64)blockIdx.x * GS_ROWS_PER_CTA;
+    const int bx = blockDim.x, by = blockDim.y;
+    u64 cnt = 0, s0 = 0, s1 = 0, s2 = 0, q0 = 0, q1 = 0, q2 = 0, zeros = 0;
+    for (int rr = threadIdx.y; rr < GS_ROWS_PER_CTA; rr += by) {
+        const i64 row = row0 + rr;
+        if (row >= rows_per_item) break;
+        const u64 i = (u64)(row / n1), j = (u64)(row % n1);
+        const double* p = u + ((i64)item * rows_per_item + row) * n2;
+        for (int k = threadIdx.x; k < n2; k += bx) {
+            const double v = __ldg(p + k);
+            if (v > 0.0) {
+                cnt += 1; s0 += i; s1 += j; s2 += (u64)k;
+                q0 += i * i; q1 += j * j; q2 += (u64)k * (u64)k;
+            } else if (v == 0.0) {
+                zeros += 1;
+            }
+        }
+    }
+    u64 vals[8] = {cnt, s0, s1, s2, q0, q1, q2, zeros};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const u64 t = block_sum<u64>(vals[q], red);
+        if (threadIdx.x == 0 && threadIdx.y == 0 && t) atomicAdd(stats + (i64)item * 8 + q, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// band sums of P image planes, per item.  planes: (P, batch*voxels).  Deterministic two-stage:
+// slice s of item i covers band positions [off_i + s*L, off_i + (s+1)*L), L = ceil(n_i/slices).
+// mode 0: sum x -> partial ; mode 1: sum (x - mean[item][p])^2
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_PLANES = 16;
+
+__global__ void __launch_bounds__(RS_THREADS)
+band_sum_partial_kernel(const double* __restrict__ planes, i64 plane_stride, int nplanes,
+                        const i64* __restrict__ band_idx, const i64* __restrict__ item_offsets,
+                        int slices, int mode, const double* __restrict__ mean /* [item][P] */,
+                        double* __restrict__ partial /* [item][P][slices] */) {
+    __shared__ double red[32];
+    const int item = blockIdx.y, s = blockIdx.x;
+    const i64 off = item_offsets[item], n = item_offsets[item + 1] - off;
+    const i64 per = (n + slices - 1) / slices;
+    const i64 lo = min(n, (i64)s * per), hi = min(n, lo + per);
+    double acc[MAX_PLANES];
+#pragma unroll
+    for (int p = 0; p < MAX_PLANES; ++p) acc[p] = 0.0;
+    for (i64 b = lo + threadIdx.x; b < hi; b += RS_THREADS) {
+        const i64 g = __ldg(band_idx + off + b);
+#pragma unroll
+        for (int p = 0; p < MAX_PLANES; ++p) {
+            if (p < nplanes) {
+                const double v = __ldg(planes + (i64)p * plane_stride + g);
+                if (mode) { const double d = v - mean[(i64)item * nplanes + p]; acc[p] += d * d; }
+                else acc[p] += v;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < MAX_PLANES; ++p) {
+        if (p < nplanes) {
+            const double t = block_sum<double>(acc[p], red);
+            if (threadIdx.x == 0) partial[((i64)item * nplanes + p) * slices + s] = t;
+        }
+    }
+}
+
+// out[item][p] = op(sum_s partial / n_item) ; op 0 mean, op 1 sqrt (population std, ddof=0)
+__global__ void band_sum_final_kernel(const double* __restrict__ partial, int nplanes, int slices,
+                                      const i64* __restrict__ item_offsets, i64 batch, int op,
+                                      double* __restrict__ out) {
+    const i64 w = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= batch * nplanes) return;
+    const i64 item = w / nplanes;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int s = lane; s < slices; s += 32) acc += partial[w * slices + s];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const double n = (double)(item_offsets[item + 1] - item_offsets[item]);
+        out[w] = op == 0 ? acc / n : sqrt(acc / n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// marching squares (skimage find_contours level 0, fully_connected='low') total segment length,
+// scaled like lsml: row differences * dx[1], column differences * dx[0] (shape.py:80).
+// Closed contours only contribute their segments; the closing chord of OPEN contours
+// (shape.py:79) is added by contour_chord_kernel below.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ms_frac(double from, double to) {
+    return to == from ? 0.0 : (0.0 - from) / (to - from);
+}
+__device__ __forceinline__ double seg_len(double r0, double c0, double r1, double c1, double sr,
+                                          double sc) {
+    const double dr = (r1 - r0) * sr, dc = (c1 - c0) * sc;
+    return sqrt(dr * dr + dc * dc);
+}
+
+__global__ void __launch_bounds__(256)
+contour_length_kernel(const double* __restrict__ u, int m, int n, double sr, double sc,
+                      int cells_per_cta, double* __restrict__ partial) {
+    __shared__ double red[32];
+    const int item = blockIdx.y;
+    const double* p = u + (i64)item * m * n;
+    const i64 ncells = (i64)(m - 1) * (n - 1);
+    const i64 lo = (i64)blockIdx.x * cells_per_cta;
+    const i64 hi = min(ncells, lo + cells_per_cta);
+    double acc = 0.0;
+    for (i64 c = lo + threadIdx.x; c < hi; c += blockDim.x) {
+        const int r0 = (int)(c / (n - 1)), c0 = (int)(c % (n - 1));
+        const double ul = __ldg(p + (i64)r0 * n + c0), ur = __ldg(p + (i64)r0 * n + c0 + 1);
+        const double ll = __ldg(p + (i64)(r0 + 1) * n + c0), lr = __ldg(p + (i64)(r0 + 1) * n + c0 + 1);
+        if (ul != ul || ur != ur || ll != ll || lr != lr) continue;
+        const int sq = (ul > 0) + 2 * (ur > 0) + 4 * (ll > 0) + 8 * (lr > 0);
+        if (sq == 0 || sq == 15) continue;
+        const double tr = r0, tc = c0 + ms_frac(ul, ur);          // top
+        const double br = r0 + 1, bc = c0 + ms_frac(ll, lr);      // bottom
+        const double lr_ = r0 + ms_frac(ul, ll), lc = c0;         // left
+        const double rr = r0 + ms_frac(ur, lr), rc = c0 + 1;      // right
+        switch (sq) {
+            case 1: case 14: acc += seg_len(tr, tc, lr_, lc, sr, sc); break;
+            case 2: case 13: acc += seg_len(rr, rc, tr, tc, sr, sc); break;
+            case 3: case 12: acc += seg_len(rr, rc, lr_, lc, sr, sc); break;
+            case 4: case 11: acc += seg_len(lr_, lc, br, bc, sr, sc); break;
+            case 5: case 10: acc += seg_len(tr, tc, br, bc, sr, sc); break;
+            case 7: case 8: acc += seg_len(rr, rc, br, bc, sr, sc); break;
+            case 6: acc += seg_len(rr, rc, tr, tc, sr, sc); acc += seg_len(lr_, lc, br, bc, sr, sc); break;
+            case 9: acc += seg_len(tr, tc, lr_, lc, sr, sc); acc += seg_len(br, bc, rr, rc, sr, sc); break;
+        }
+    }
+    const double t = block_sum<double>(acc, red);
+    if (threadIdx.x == 0) partial[(i64)item * gridDim.x + blockIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-item ("global") feature values
+// ---------------------------------------------------------------------------------------------
+enum FeatKind {
+    FK_PLANE = 0,       // a = plane index (local)
+    FK_DIST_COM = 1,    // local
+    FK_BAND_MEAN = 2,   // a = plane index
+    FK_BAND_STD = 3,    // a = plane index
+    FK_SIZE = 4,
+    FK_BOUNDARY = 5,
+    FK_ISOPERIMETRIC = 6,
+    FK_MOMENT = 7,      // a = axis (0..ndim-1), b = order (1 or 2)
+};
+
+struct FeatProgram {
+    int nfeat;
+    int kind[64];
+    int a[64];
+    int b[64];
+};
+
+struct ItemGeom {
+    int ndim;
+    int pad;           // 3 - ndim
+    double dx[3];      // padded
+    double pdx;        // prod(dx) over real axes, multiplied left to right
+};
+
+// moment of `order` along padded axis ax from the exact integer sums
+__device__ double moment_from_stats(const u64* st, int ax, int order, double dx, double pdx) {
+    const double cnt = (double)st[0];
+    const double measure = cnt * pdx;                       // Size: (u>0).sum()*prod(dx)
+    if (order == 1) return ((double)st[1 + ax] * dx) * pdx / measure;   // shape.py:227-228
+    // order 2: sum (x - c)^2 with c the centroid = (N*Sxx - Sx^2)/N exactly (128-bit integers)
+    const unsigned __int128 N = st[0], Sx = st[1 + ax], Sxx = st[4 + ax];
+    const unsigned __int128 num = N * Sxx - Sx * Sx;
+    const double numd = (double)(u64)(num >> 64) * 18446744073709551616.0 + (double)(u64)num;
+    const double ssd = (numd / cnt) * (dx * dx);
+    return ssd * pdx / measure;
+}
+
+__global__ void item_features_kernel(FeatProgram prog, ItemGeom geo, i64 batch, int nplanes,
+                                     const u64* __restrict__ stats,
+                                     const double* __restrict__ band_mean,
+                                     const double* __restrict__ band_std,
+                                     const double* __restrict__ boundary,
+                                     double* __restrict__ item_feat /* [item][nfeat] */,
+                                     double* __restrict__ com /* [item][3] padded axes */) {
+    const i64 item = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= batch) return;
+    const u64* st = stats + item * 8;
+    for (int ax = 0; ax < 3; ++ax)
+        com[item * 3 + ax] = ax >= geo.pad ? moment_from_stats(st, ax, 1, geo.dx[ax], geo.pdx) : 0.0;
+    const double size = (double)st[0] * geo.pdx;
+    const double bsz = boundary ? boundary[item] : 0.0;
+    const double pi = 3.141592653589793;
+    for (int f = 0; f < prog.nfeat; ++f) {
+        double v = 0.0;
+        switch (prog.kind[f]) {
+            case FK_BAND_MEAN: v = band_mean[item * nplanes + prog.a[f]]; break;
+            case FK_BAND_STD: v = band_std[item * nplanes + prog.a[f]]; break;
+            case FK_SIZE: v = size; break;
+            case FK_BOUNDARY: v = bsz; break;
+            case FK_ISOPERIMETRIC:
+                v = geo.ndim == 2 ? 4 * pi * size / (bsz * bsz)                 // shape.py:136
+                                  : 36 * pi * (size * size) / (bsz * bsz * bsz); // shape.py:151
+                break;
+            case FK_MOMENT: {
+                const int ax = geo.pad + prog.a[f];
+                v = moment_from_stats(st, ax, prog.b[f], geo.dx[ax], geo.pdx);
+                break;
+            }
+            default: break;
+        }
+        item_feat[item * prog.nfeat + f] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (B, F) feature matrix in band order.  One thread per (band voxel, feature) pair with the
+// feature index fastest => fully coalesced 8-byte stores of the row-major matrix.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
+                const i64* __restrict__ band_idx, const i64* __restrict__ n_band,
+                const double* __restrict__ planes, i64 plane_stride,
+                const double* __restrict__ item_feat, const double* __restrict__ com,
+                double* __restrict__ X) {
+    const i64 nb = *n_band;
+    const i64 total = nb * prog.nfeat;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (i64)gridDim.x * blockDim.x) {
+        const i64 b = t / prog.nfeat;
+        const int f = (int)(t - b * prog.nfeat);
+        const i64 g = __ldg(band_idx + b);
+        const i64 item = g / voxels;
+        double v;
+        const int kind = prog.kind[f];
+        if (kind == FK_PLANE) {
+            v = __ldg(planes + (i64)prog.a[f] * plane_stride + g);
+        } else if (kind == FK_DIST_COM) {
+            const i64 loc = g - item * voxels;
+            const int k = (int)(loc % n2);
+            const i64 r = loc / n2;
+            const int j = (int)(r % n1), i = (int)(r / n1);
+            const double* c = com + item * 3;
+            // numpy.linalg.norm(mesh - com, axis=0): ((d0^2 + d1^2) + d2^2) over the real axes
+            double acc = 0.0;
+            if (geo.ndim == 3) { const double d = i * geo.dx[0] - c[0]; acc = d * d; }
+            if (geo.ndim >= 2) { const double d = j * geo.dx[1] - c[1]; acc = geo.ndim == 2 ? d * d : acc + d * d; }
+            { const double d = k * geo.dx[2] - c[2]; acc = geo.ndim == 1 ? d * d : acc + d * d; }
+            v = sqrt(acc);
+        } else {
+            v = item_feat[item * prog.nfeat + f];
+        }
+        X[t] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static void rows_launch(const Geom& g, dim3& grid, dim3& block, i64& rows) {
+    int bx = 32;
+    while (bx < 256 && bx < g.n[2]) bx <<= 1;
+    const int by = 256 / bx;
+    rows = g.batch * g.n[0] * g.n[1];
+    block = dim3(bx, by, 1);
+    grid = dim3((unsigned)((rows + by - 1) / by), (unsigned)((g.n[2] + bx - 1) / bx), 1);
+}
+
+int gauss1d(const Geom& g, const double* in, double* out, const double* w, int radius,
+            int antisym, int axis_padded, int mode, cudaStream_t s) {
+    dim3 grid, block; i64 rows;
+    rows_launch(g, grid, block, rows);
+    gauss1d_kernel<<<grid, block, 0, s>>>(in, out, w, radius, antisym, g.n[0], g.n[1], g.n[2],
+                                          axis_padded, rows, mode);
+    LSML_LAUNCH_CHECK("gauss1d_kernel");
+    return 0;
+}
+
+int np_gradient_mag(const Geom& g, const double* in, double* out, cudaStream_t s) {
+    dim3 grid, block; i64 rows;
+    rows_launch(g, grid, block, rows);
+    if (g.ndim == 3)
+        np_gradient_mag_kernel<3><<<grid, block, 0, s>>>(in, out, g.n[0], g.n[1], g.n[2], rows, g.dx[0], g.dx[1], g.dx[2]);
+    else if (g.ndim == 2)
+        np_gradient_mag_kernel<2><<<grid, block, 0, s>>>(in, out, g.n[0], g.n[1], g.n[2], rows, g.dx[0], g.dx[1], g.dx[2]);
+    else
+        np_gradient_mag_kernel<1><<<grid, block, 0, s>>>(in, out, g.n[0], g.n[1], g.n[2], rows, g.dx[0], g.dx[1], g.dx[2]);
+    LSML_LAUNCH_CHECK("np_gradient_mag_kernel");
+    return 0;
+}
+
+static int dense_slices(i64 voxels) {
+    i64 s = (voxels + 16383) / 16384;
+    return (int)(s < 1 ? 1 : (s > 1024 ? 1024 : s));
+}
+
+i64 normalize_workspace_bytes(i64 voxels, i64 batch) {
+    return (i64)sizeof(double) * (batch * dense_slices(voxels) + 2 * batch);
+}
+
+int normalize_images(i64 voxels, i64 batch, const double* img, double* out, void* workspace,
+                     cudaStream_t s) {
+    const int slices = dense_slices(voxels);
+    double* partial = static_cast<double*>(workspace);
+    double* mean = partial + batch * slices;
+    double* stdv = mean + batch;
+    const dim3 grid(slices, (unsigned)batch);
+    const int fin_blocks = (int)((batch + 7) / 8);
+    dense_sum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(img, voxels, slices, 0, nullptr, partial);
+    LSML_LAUNCH_CHECK("dense_sum_partial_kernel");
+    sum_final_kernel<<<fin_blocks, 256, 0, s>>>(partial, slices, batch, (double)voxels, 0, mean);
+    LSML_LAUNCH_CHECK("sum_final_kernel");
+    dense_sum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(img, voxels, slices, 1, mean, partial);
+    LSML_LAUNCH_CHECK("dense_sum_partial_kernel");
+    sum_final_kernel<<<fin_blocks, 256, 0, s>>>(partial, slices, batch, (double)voxels, 1, stdv);
+    LSML_LAUNCH_CHECK("sum_final_kernel");
+    const dim3 ngrid((unsigned)((voxels + 255) / 256), (unsigned)batch);
+    normalize_kernel<<<ngrid, 256, 0, s>>>(img, out, voxels, mean, stdv);
+    LSML_LAUNCH_CHECK("normalize_kernel");
+    return 0;
+}
+
+int global_stats(const Geom& g, const double* u, u64* stats, cudaStream_t s) {
+    LSML_CUDA(cudaMemsetAsync(stats, 0, sizeof(u64) * 8 * g.batch, s));
+    int bx = 32;
+    while (bx < 256 && bx < g.n[2]) bx <<= 1;
+    const dim3 block(bx, 256 / bx);
+    const i64 rows_per_item = (i64)g.n[0] * g.n[1];
+    const dim3 grid((unsigned)((rows_per_item + GS_ROWS_PER_CTA - 1) / GS_ROWS_PER_CTA), (unsigned)g.batch);
+    global_stats_kernel<<<grid, block, 0, s>>>(u, g.n[0], g.n[1], g.n[2], stats);
+    LSML_LAUNCH_CHECK("global_stats_kernel");
+    return 0;
+}
+
+int band_slices(i64 voxels) {
+    i64 s = (voxels + 32767) / 32768;
+    return (int)(s < 1 ? 1 : (s > 512 ? 512 : s));
+}
+
+i64 band_stats_workspace_bytes(i64 voxels, i64 batch, int nplanes) {
+    return (i64)sizeof(double) * batch * nplanes * band_slices(voxels);
+}
+
+// mean and population std of every plane over each item's band
+int band_stats(i64 voxels, i64 batch, const double* planes, i64 plane_stride, int nplanes,
+               const i64* band_idx, const i64* item_offsets, double* mean, double* stdv,
+               void* workspace, cudaStream_t s) {
+    if (nplanes > MAX_PLANES) { set_error("at most %d image planes", MAX_PLANES); return 1; }
+    if (nplanes == 0) return 0;
+    const int slices = band_slices(voxels);
+    double* partial = static_cast<double*>(workspace);
+    const dim3 grid(slices, (unsigned)batch);
+    const int fin_blocks = (int)((batch * nplanes + 7) / 8);
+    band_sum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(planes, plane_stride, nplanes, band_idx,
+                                                        item_offsets, slices, 0, nullptr, partial);
+    LSML_LAUNCH_CHECK("band_sum_partial_kernel");
+    band_sum_final_kernel<<<fin_blocks, 256, 0, s>>>(partial, nplanes, slices, item_offsets, batch, 0, mean);
+    LSML_LAUNCH_CHECK("band_sum_final_kernel");
+    band_sum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(planes, plane_stride, nplanes, band_idx,
+                                                        item_offsets, slices, 1, mean, partial);
+    LSML_LAUNCH_CHECK("band_sum_partial_kernel");
+    band_sum_final_kernel<<<fin_blocks, 256, 0, s>>>(partial, nplanes, slices, item_offsets, batch, 1, stdv);
+    LSML_LAUNCH_CHECK("band_sum_final_kernel");
+    return 0;
+}
+
+constexpr int CL_CELLS_PER_CTA = 8192;
+
+i64 contour_workspace_bytes(int m, int n, i64 batch) {
+    const i64 ncells = (i64)(m - 1) * (n - 1);
+    const i64 ctas = (ncells + CL_CELLS_PER_CTA - 1) / CL_CELLS_PER_CTA;
+    return (i64)sizeof(double) * batch * (ctas < 1 ? 1 : ctas);
+}
+
+// 2-D only: boundary[item] = total marching-squares length (closed contours)
+int contour_length(const Geom& g, const double* u, double* boundary, void* workspace,
+                   cudaStream_t s) {
+    if (g.ndim != 2) { set_error("contour_length: 2-D grids only"); return 1; }
+    const int m = g.n[1], n = g.n[2];
+    const i64 ncells = (i64)(m - 1) * (n - 1);
+    i64 ctas = (ncells + CL_CELLS_PER_CTA - 1) / CL_CELLS_PER_CTA;
+    if (ctas < 1) ctas = 1;
+    double* partial = static_cast<double*>(workspace);
+    // shape.py:80: (row, col) * dx[::-1]  => rows scale with dx[1], columns with dx[0]
+    contour_length_kernel<<<dim3((unsigned)ctas, (unsigned)g.batch), 256, 0, s>>>(
+        u, m, n, g.dx[2], g.dx[1], CL_CELLS_PER_CTA, partial);
+    LSML_LAUNCH_CHECK("contour_length_kernel");
+    sum_final_kernel<<<(int)((g.batch + 7) / 8), 256, 0, s>>>(partial, (int)ctas, g.batch, 1.0, 0, boundary);
+    LSML_LAUNCH_CHECK("sum_final_kernel");
+    return 0;
+}
+
+int item_features(const FeatProgram& prog, const Geom& g, int nplanes, const u64* stats,
+                  const double* band_mean, const double* band_std, const double* boundary,
+                  double* item_feat, double* com, cudaStream_t s) {
+    ItemGeom geo;
+    geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
+    double pdx = 1.0;
+    for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
+    for (int a = geo.pad; a < 3; ++a) pdx = (a == geo.pad) ? g.dx[a] : pdx * g.dx[a];
+    geo.pdx = pdx;
+    item_features_kernel<<<(unsigned)((g.batch + 127) / 128), 128, 0, s>>>(
+        prog, geo, g.batch, nplanes, stats, band_mean, band_std, boundary, item_feat, com);
+    LSML_LAUNCH_CHECK("item_features_kernel");
+    return 0;
+}
+
+int assemble_features(const FeatProgram& prog, const Geom& g, const i64* band_idx,
+                      const i64* n_band, const double* planes, i64 plane_stride,
+                      const double* item_feat, const double* com, double* X, cudaStream_t s) {
+    ItemGeom geo;
+    geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
+    for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
+    geo.pdx = 1.0;
+    assemble_kernel<<<LSML_SMS * 8, 256, 0, s>>>(prog, geo, g.n[1], g.n[2], g.voxels, band_idx,
+                                                  n_band, planes, plane_stride, item_feat, com, X);
+    LSML_LAUNCH_CHECK("assemble_kernel");
+    return 0;
+}
+
+}  // namespace lsml
+
+namespace lsml {
+
+static int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a, const int* b) {
+    if (nfeat < 0 || nfeat > 64) { set_error("feature program: 0..64 columns (got %d)", nfeat); return 1; }
+    p.nfeat = nfeat;
+    for (int f = 0; f < nfeat; ++f) {
+        p.kind[f] = kind[f]; p.a[f] = a[f]; p.b[f] = b[f];
+        if (kind[f] == FK_MOMENT && (b[f] < 1 || b[f] > 2)) {
+            set_error("Moments: only orders 1 and 2 are implemented on the device (got %d)", b[f]);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int item_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
+                    int nplanes, const u64* stats, const double* band_mean,
+                    const double* band_std, const double* boundary, double* item_feat,
+                    double* com, cudaStream_t s) {
+    FeatProgram p;
+    if (fill_program(p, nfeat, kind, a, b)) return 1;
+    return item_features(p, g, nplanes, stats, band_mean, band_std, boundary, item_feat, com, s);
+}
+
+int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
+                        const i64* band_idx, const i64* n_band, const double* planes,
+                        i64 plane_stride, const double* item_feat, const double* com, double* X,
+                        cudaStream_t s) {
+    FeatProgram p;
+    if (fill_program(p, nfeat, kind, a, b)) return 1;
+    return assemble_features(p, g, band_idx, n_band, planes, plane_stride, item_feat, com, X, s);
+}
+
+}  // namespace lsml

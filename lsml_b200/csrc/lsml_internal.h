@@ -19,3 +19,56 @@ int item_offsets(const i64* band_idx, const i64* n_band, i64 voxels, i64 batch, 
                  cudaStream_t s);
 
 }  // namespace lsml
+
+namespace lsml {
+
+// features.cu
+struct FeatProgram;
+int gauss1d(const Geom& g, const double* in, double* out, const double* w, int radius,
+            int antisym, int axis_padded, int mode, cudaStream_t s);
+int np_gradient_mag(const Geom& g, const double* in, double* out, cudaStream_t s);
+i64 normalize_workspace_bytes(i64 voxels, i64 batch);
+int normalize_images(i64 voxels, i64 batch, const double* img, double* out, void* workspace,
+                     cudaStream_t s);
+int global_stats(const Geom& g, const double* u, u64* stats, cudaStream_t s);
+i64 band_stats_workspace_bytes(i64 voxels, i64 batch, int nplanes);
+int band_stats(i64 voxels, i64 batch, const double* planes, i64 plane_stride, int nplanes,
+               const i64* band_idx, const i64* item_offsets, double* mean, double* stdv,
+               void* workspace, cudaStream_t s);
+i64 contour_workspace_bytes(int m, int n, i64 batch);
+int contour_length(const Geom& g, const double* u, double* boundary, void* workspace,
+                   cudaStream_t s);
+int item_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
+                    int nplanes, const u64* stats, const double* band_mean,
+                    const double* band_std, const double* boundary, double* item_feat,
+                    double* com, cudaStream_t s);
+int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
+                        const i64* band_idx, const i64* n_band, const double* planes,
+                        i64 plane_stride, const double* item_feat, const double* com, double* X,
+                        cudaStream_t s);
+
+// regress.cu
+int linear_predict(const double* X, const i64* n_band, int F, const double* mean,
+                   const double* scale, const double* coef, double intercept, double* out,
+                   cudaStream_t s);
+int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
+                   const double* scale, const void* nodes, const int* tree_base,
+                   const u8* root_is_leaf, int n_trees, double divisor, double* out,
+                   cudaStream_t s);
+int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
+                int n_layers, const int* sizes, const double* const* W, const double* const* b,
+                int act, double* out, cudaStream_t s);
+
+// update.cu
+int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx,
+                const i64* n_band, double step, double* new_u, double* gmag_out, int apply,
+                cudaStream_t s);
+
+// fmm.cu
+i64 fmm_workspace_bytes(i64 total);
+int fmm_workspace_init(i64 total, void* workspace, cudaStream_t s);
+int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u8* mask,
+                double* dist_out, void* workspace, cudaStream_t s);
+int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
+
+}  // namespace lsml

@@ -1,0 +1,100 @@
+// update.cu -- the banded level-set update (SURVEY.md section 8a rows a1 (banded) + a13).
+//
+//   gmag = gradient_magnitude_osher_sethian(u, velocity, mask, dx)     model.py:390
+//   u[mask] += step * velocity[mask] * gmag[mask]                      model.py:394
+//
+// fused per band voxel: the upwind |Du| is evaluated from the PRE-update u (quirk 1 of
+// SURVEY.md section 9), the product is (step*v)*gmag left to right (quirk 13).  Because band
+// voxels are neighbours of each other the new values go to a banded buffer first
+// (band_update_kernel) and are scattered into u by band_apply_kernel; the banded buffer is
+// also the sparse per-iteration record from which `segment` rebuilds the iterates `us`.
+//
+// Algorithmic bytes per band voxel (f64): 8 (index) + 8 (v) + 8*(1 + H/B) (u incl. one-ring
+// halo) + 8 (new value) + 8 + 8 (apply: read new value, write u) ~ 56-64 B.
+#include "lsml_internal.h"
+
+namespace lsml {
+
+__device__ __forceinline__ void fwd_bwd_b(const double* __restrict__ A, i64 l, i64 st, int c,
+                                          int n, double center, double& f, double& b) {
+    if (n == 1) { f = 0.0; b = 0.0; return; }
+    if (c == 0) { f = __ldg(A + l + st) - center; b = f; }
+    else if (c == n - 1) { b = center - __ldg(A + l - st); f = b; }
+    else { f = __ldg(A + l + st) - center; b = center - __ldg(A + l - st); }
+}
+
+__device__ __forceinline__ double os_acc(double b, double f, bool neg, double acc, bool first) {
+    double tb, tf;
+    if (neg) { tb = ref_max(b, 0.0); tf = ref_min(f, 0.0); }
+    else     { tb = ref_min(b, 0.0); tf = ref_max(f, 0.0); }
+    tb = tb * tb; tf = tf * tf;
+    return first ? (tb + tf) : ((acc + tb) + tf);
+}
+
+struct BandGeom {
+    int ndim, n0, n1, n2;
+    i64 voxels;
+    double dx0, dx1, dx2, r0, r1, r2;
+};
+
+__global__ void __launch_bounds__(256)
+band_update_kernel(const double* __restrict__ u, const double* __restrict__ vel,
+                   const i64* __restrict__ band_idx, const i64* __restrict__ n_band, BandGeom g,
+                   double step, double* __restrict__ new_u, double* __restrict__ gmag_out) {
+    const i64 nb = *n_band;
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+         b += (i64)gridDim.x * blockDim.x) {
+        const i64 l = __ldg(band_idx + b);
+        const i64 loc = l % g.voxels;
+        const int k = (int)(loc % g.n2);
+        const i64 r = loc / g.n2;
+        const int j = (int)(r % g.n1), i = (int)(r / g.n1);
+        const double c = __ldg(u + l), v = __ldg(vel + b);
+        const bool neg = v < 0.0;
+        double acc = 0.0, f, bk;
+        bool first = true;
+        if (g.ndim >= 3) {
+            fwd_bwd_b(u, l, (i64)g.n1 * g.n2, i, g.n0, c, f, bk);
+            f = div_dx(f, g.dx0, g.r0); bk = div_dx(bk, g.dx0, g.r0);
+            acc = os_acc(bk, f, neg, acc, first); first = false;
+        }
+        if (g.ndim >= 2) {
+            fwd_bwd_b(u, l, (i64)g.n2, j, g.n1, c, f, bk);
+            f = div_dx(f, g.dx1, g.r1); bk = div_dx(bk, g.dx1, g.r1);
+            acc = os_acc(bk, f, neg, acc, first); first = false;
+        }
+        fwd_bwd_b(u, l, (i64)1, k, g.n2, c, f, bk);
+        f = div_dx(f, g.dx2, g.r2); bk = div_dx(bk, g.dx2, g.r2);
+        acc = os_acc(bk, f, neg, acc, first);
+        const double gm = sqrt(acc);
+        if (gmag_out != nullptr) gmag_out[b] = gm;
+        new_u[b] = c + (step * v) * gm;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+band_apply_kernel(double* __restrict__ u, const double* __restrict__ new_u,
+                  const i64* __restrict__ band_idx, const i64* __restrict__ n_band) {
+    const i64 nb = *n_band;
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+         b += (i64)gridDim.x * blockDim.x)
+        u[__ldg(band_idx + b)] = __ldg(new_u + b);
+}
+
+int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx,
+                const i64* n_band, double step, double* new_u, double* gmag_out, int apply,
+                cudaStream_t s) {
+    BandGeom bg;
+    bg.ndim = g.ndim; bg.n0 = g.n[0]; bg.n1 = g.n[1]; bg.n2 = g.n[2]; bg.voxels = g.voxels;
+    bg.dx0 = g.dx[0]; bg.dx1 = g.dx[1]; bg.dx2 = g.dx[2];
+    bg.r0 = g.rdx[0]; bg.r1 = g.rdx[1]; bg.r2 = g.rdx[2];
+    band_update_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, vel, band_idx, n_band, bg, step, new_u, gmag_out);
+    LSML_LAUNCH_CHECK("band_update_kernel");
+    if (apply) {
+        band_apply_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, new_u, band_idx, n_band);
+        LSML_LAUNCH_CHECK("band_apply_kernel");
+    }
+    return 0;
+}
+
+}  // namespace lsml
