@@ -1,0 +1,228 @@
+"""GPU parity of the per-iteration pipeline against the CPU oracle (features, regressors,
+update, band rebuild).  Every comparison states its bar:
+
+* integer / index / mask results: bit-exact
+* image planes, local features, tree-ensemble velocities, updated level sets given identical
+  inputs: bit-exact (same float64 expressions in the same order)
+* global features that are reductions (band mean/std, 2nd moments, contour length):
+  relative 1e-12 (summation order differs from numpy's pairwise sum)
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+IMG_SPECS = [("image_sample", 0), ("image_sample", 2), ("image_edge", 0), ("image_edge", 2),
+             ("band_mean", 0), ("band_mean", 2), ("band_std", 0), ("band_std", 2)]
+
+
+def shape_specs(ndim, boundary):
+    if boundary:
+        return [("boundary_size",), ("dist_to_com",), ("isoperimetric",),
+                ("moments", (0, 1), (1, 2)), ("size",)]
+    return [("dist_to_com",), ("moments", (0, 1), (1, 2)), ("size",)]
+
+
+def make_item(rs, shape, radius_frac=0.3):
+    """A noisy blob image and a smooth, non-distance level set around it."""
+    ndim = len(shape)
+    grids = np.indices(shape).astype(float)
+    c = [s / 2 + rs.uniform(-2, 2) for s in shape]
+    r = np.sqrt(sum((grids[a] - c[a]) ** 2 for a in range(ndim)))
+    rad = radius_frac * min(shape)
+    img = (r < rad).astype(float) + 0.2 * rs.randn(*shape)
+    u = (rad * 0.8 - r) * (1.0 + 0.3 * np.sin(grids[0] / 3.0)) + 0.05 * rs.randn(*shape)
+    return img, u
+
+
+def build_engine(shape, batch, dx, specs, band=3.0, seed=0, normalize=True):
+    from lsml_b200.core.engine import BandEngine
+    rs = np.random.RandomState(seed)
+    imgs, us = zip(*[make_item(rs, shape) for _ in range(batch)])
+    imgs, us = np.stack(imgs), np.stack(us)
+    eng = BandEngine(shape, batch, dx=dx, band=band, specs=specs)
+    eng.load_images(imgs, normalize=normalize)
+    eng.set_level_sets(us)
+    return eng, imgs, us
+
+
+@pytest.mark.parametrize("shape,dx", [((41, 37), (1.0, 1.0)), ((41, 37), (0.7, 1.3)),
+                                      ((23, 30, 27), (1.0, 1.0, 1.0)),
+                                      ((23, 30, 27), (1.2, 0.8, 1.0)), ((64,), (0.5,))])
+def test_image_planes_bit_exact(oracle, shape, dx):
+    specs = [("image_sample", 0), ("image_sample", 1), ("image_sample", 2.5),
+             ("image_edge", 0), ("image_edge", 1), ("image_edge", 3)]
+    eng, imgs, us = build_engine(shape, 2, dx, specs, normalize=False)
+    dxa = np.asarray(dx)
+    for p, (what, sigma) in enumerate(eng.program.planes):
+        got = eng.planes[p].cpu().numpy()
+        for b in range(2):
+            want = (oracle.image_sample_plane(imgs[b], sigma, dxa) if what == "sample"
+                    else oracle.image_edge_plane(imgs[b], sigma, dxa))
+            assert np.array_equal(got[b], want), (what, sigma, np.abs(got[b] - want).max())
+
+
+def test_normalize_matches_numpy(oracle):
+    eng, imgs, us = build_engine((33, 45), 3, (1, 1), [("image_sample", 0)], normalize=True)
+    got = eng.img.cpu().numpy()
+    for b in range(3):
+        assert np.allclose(got[b], oracle.normalize_image(imgs[b]), rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("shape,dx,band", [((51, 51), (1.0, 1.0), 3.0),
+                                           ((40, 56), (0.8, 1.25), 2.5),
+                                           ((30, 33, 29), (1.0, 1.0, 1.0), 3.0),
+                                           ((30, 33, 29), (1.0, 0.75, 1.5), 2.0)])
+def test_band_rebuild_mask_bit_exact_and_distance(oracle, shape, dx, band):
+    """distance_transform(u, band, dx): mask bit-exact, distances bit-exact."""
+    eng, imgs, us = build_engine(shape, 3, dx, [("size",)], band=band, normalize=False)
+    dist = eng.distance().cpu().numpy()
+    mask = eng.mask.cpu().numpy().astype(bool)
+    ctr = eng.fmm_counters()
+    assert ctr["converged"], ctr
+    for b in range(3):
+        wd, wm = oracle.distance_transform(us[b], band, np.asarray(dx))
+        assert np.array_equal(mask[b], wm), (b, (mask[b] != wm).sum(), ctr)
+        assert np.array_equal(dist[b], wd), np.abs(dist[b] - wd).max()
+    idx = eng.band_idx[:eng.n_band].cpu().numpy()
+    assert np.array_equal(idx, np.flatnonzero(mask.ravel()))
+
+
+def test_band_rebuild_reference_known_answers(oracle):
+    """lsml/util/test/test_distance_transform.py:11-53 through the device path."""
+    from lsml_b200.core.engine import BandEngine
+
+    def run(arr, band, dx):
+        eng = BandEngine(arr.shape, 1, dx=dx, band=band, specs=[])
+        eng.set_level_sets(arr[None])
+        return eng.distance().cpu().numpy()[0], eng.mask.cpu().numpy()[0].astype(bool)
+
+    d, m = run(np.r_[-1, -1, 1, -1, -1.], 1, [1.])
+    assert (d == np.r_[0., -0.5, 0.5, -0.5, 0.]).all()
+    assert (m == np.r_[False, True, True, True, False]).all()
+    for sign in (1.0, -1.0):
+        d, m = run(sign * np.ones((4, 5, 6)), 0, [1, 1, 1.])
+        assert m.sum() == 0
+    arr = np.ones((4, 5, 6))
+    arr[2] = -1
+    d, m = run(arr, 0, [1, 1, 1.])
+    assert m.sum() == arr.size
+    wd, wm = oracle.distance_transform(arr, 0, [1, 1, 1.])
+    assert np.array_equal(d, wd)
+    d, m = run(np.zeros((4, 5, 6)), 0, [1, 1, 1.])
+    assert m.sum() == 120 and (d == 0).all()
+
+
+@pytest.mark.parametrize("shape,dx", [((51, 51), (1.0, 1.0)), ((40, 56), (0.8, 1.25)),
+                                      ((30, 33, 29), (1.0, 1.0, 1.0)),
+                                      ((30, 33, 29), (1.0, 0.75, 1.5))])
+def test_feature_matrix_against_oracle(oracle, shape, dx):
+    ndim = len(shape)
+    specs = IMG_SPECS + shape_specs(ndim, boundary=(ndim == 2))
+    eng, imgs, us = build_engine(shape, 3, dx, specs, normalize=False)
+    X = eng.compute_features().cpu().numpy()
+    mask = eng.mask.cpu().numpy().astype(bool)
+    off = eng.item_offsets.cpu().numpy()
+    dxa = np.asarray(dx)
+    cols = []
+    for s in specs:
+        cols += [s] * oracle.spec_width(s)
+    for b in range(3):
+        want = oracle.feature_matrix(specs, us[b], imgs[b], None, mask[b], dxa)
+        got = X[off[b]:off[b + 1]]
+        assert got.shape == want.shape
+        for f, s in enumerate(cols):
+            exact = s[0] in ("image_sample", "image_edge", "size") or \
+                (s[0] == "dist_to_com" and np.all(dxa == 1.0))
+            if exact:
+                assert np.array_equal(got[:, f], want[:, f]), \
+                    (s, np.abs(got[:, f] - want[:, f]).max())
+            else:
+                assert np.allclose(got[:, f], want[:, f], rtol=RTOL, atol=1e-13), \
+                    (s, np.abs(got[:, f] - want[:, f]).max())
+
+
+def _train_models(X, y, seed=0):
+    from sklearn.ensemble import ExtraTreesRegressor, RandomForestRegressor
+    from sklearn.linear_model import LinearRegression
+    from sklearn.neural_network import MLPRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from sklearn.tree import DecisionTreeRegressor
+    rs = np.random.RandomState(seed)
+    models = {
+        "linear": Pipeline([("s", StandardScaler()), ("r", LinearRegression())]),
+        "forest": Pipeline([("s", StandardScaler()),
+                            ("r", RandomForestRegressor(n_estimators=20, max_samples=300,
+                                                        random_state=rs))]),
+        "forest_noscale": RandomForestRegressor(n_estimators=7, max_depth=6, random_state=1),
+        "extra": ExtraTreesRegressor(n_estimators=5, random_state=2),
+        "tree": DecisionTreeRegressor(max_depth=1, random_state=0),
+        "mlp": Pipeline([("s", StandardScaler()),
+                         ("r", MLPRegressor(hidden_layer_sizes=(16, 8), max_iter=50,
+                                            random_state=0))]),
+    }
+    for m in models.values():
+        m.fit(X, y)
+    return models
+
+
+def test_regressors_against_sklearn():
+    import torch
+    from lsml_b200.core.regressors import export_regressor
+    rs = np.random.RandomState(5)
+    X = rs.randn(4000, 12) * rs.rand(12) * 5 + rs.randn(12)
+    y = np.sin(X[:, 0]) + 0.5 * X[:, 3] - (X[:, 5] > 0.3) + 0.1 * rs.randn(4000)
+    Xt = rs.randn(5000, 12) * rs.rand(12) * 5 + rs.randn(12)
+    Xt[:300] = X[:300]                      # training points sit exactly on split values
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        models = _train_models(X, y)
+    Xd = torch.from_numpy(Xt).cuda()
+    for name, m in models.items():
+        want = m.predict(Xt)
+        got = export_regressor(m).predict(Xd).cpu().numpy()
+        if name in ("forest", "forest_noscale", "extra", "tree"):
+            assert np.array_equal(got, want), (name, np.abs(got - want).max())
+        else:
+            assert np.allclose(got, want, rtol=1e-11, atol=1e-12), \
+                (name, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("shape,dx", [((51, 51), (1.0, 1.0)), ((30, 33, 29), (1.0, 0.75, 1.5))])
+def test_full_step_against_oracle(oracle, shape, dx):
+    """features -> forest velocity -> upwind update -> band rebuild, two iterations."""
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    ndim = len(shape)
+    specs = IMG_SPECS + shape_specs(ndim, boundary=False)
+    eng, imgs, us = build_engine(shape, 2, dx, specs, normalize=False, seed=3)
+    dxa = np.asarray(dx)
+    mask0 = eng.mask.cpu().numpy().astype(bool)
+    # train on the oracle's features of item 0 with a synthetic target
+    F0 = oracle.feature_matrix(specs, us[0], imgs[0], None, mask0[0], dxa)
+    rs = np.random.RandomState(0)
+    y = F0[:, 0] - F0[:, 1] + 0.1 * rs.randn(F0.shape[0])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        reg = Pipeline([("s", StandardScaler()),
+                        ("r", RandomForestRegressor(n_estimators=10, max_samples=200,
+                                                    random_state=rs))]).fit(F0, y)
+    step = 0.4
+    u_o = [us[b].copy() for b in range(2)]
+    m_o = [mask0[b] for b in range(2)]
+    for it in range(2):
+        eng.step(reg, step)
+        u_g = eng.u.cpu().numpy()
+        m_g = eng.mask.cpu().numpy().astype(bool)
+        for b in range(2):
+            u_o[b], _, m_o[b], vb = oracle.evolve_step(u_o[b], imgs[b], None, m_o[b], dxa, specs,
+                                                       reg, step, eng.band)
+            assert np.array_equal(m_g[b], m_o[b]), (it, b, (m_g[b] != m_o[b]).sum())
+            assert np.allclose(u_g[b], u_o[b], rtol=1e-12, atol=1e-12), \
+                np.abs(u_g[b] - u_o[b]).max()
