@@ -59,6 +59,11 @@ struct FmmCounters {      // device-resident, 8 x i64
     i64 pad;
 };
 
+// Ordering decisions are made on |d| rounded to float32 (see oracle/lsml_oracle.c:qmag): values
+// that tie in exact arithmetic but differ by float64 rounding noise tie exactly here and are
+// ordered by flat index.
+__device__ __forceinline__ float qmag(double d) { return __double2float_rn(fabs(d)); }
+
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 // claim voxel g (state 0 -> 2); returns true for the single winner.  The state is one byte of
@@ -164,7 +169,7 @@ __device__ __forceinline__ void push_neighbours(i64 l, const FmmGeom& g, double*
             const int cc = coord[ax] + j;
             if (cc < 0 || cc >= ext[ax]) continue;
             const i64 n = l + j * st[ax];
-            if (mask[n] == 0 && claim(mask, n)) {
+            if (__ldcg(mask + n) == 0 && claim(mask, n)) {
                 const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_cand), (u64)1);
                 list[cap - 1 - pos] = n;
             }
@@ -183,47 +188,89 @@ fmm_seed_kernel(double* T, u8* mask, i64* list, i64 cap, FmmGeom g, FmmCounters*
 
 // ---- the marcher's upwind update on a local stencil ------------------------------------------
 // t1/t2: values one / two cells away, index [ax][dir] with dir 0 = -1, 1 = +1;
-// f1/f2: "frozen now" predicates.  Same expressions as oracle fmm_update().
+// f1/f2: "frozen now" predicates.  Same expressions, in the same order, as the oracle's
+// fmm_update()/fmm_solve() (oracle/lsml_oracle.c), including the causality rule: a root that is
+// smaller in magnitude than a value it was computed from (or a non-positive discriminant)
+// removes the contributor with the largest magnitude and solves again.
 template <int NDIM>
 __device__ __forceinline__ double stencil_update(const double (&t1)[3][2], const double (&t2)[3][2],
                                                  const bool (&f1)[3][2], const bool (&f2)[3][2],
                                                  const FmmGeom& g, double phi) {
     const double aa = 9.0 / 4.0, one_third = 1.0 / 3.0;
-    double a = 0, b = 0, c = 0;
+    double v1[3], v2[3];
+    bool active[3];
+    int nactive = 0;
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
-        double v1 = DBL_MAX, v2 = DBL_MAX;
+        v1[ax] = DBL_MAX; v2[ax] = DBL_MAX;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-            if (f1[ax][d] && fabs(t1[ax][d]) < fabs(v1)) {
-                v1 = t1[ax][d];
-                v2 = DBL_MAX;
-                if (f2[ax][d] && ((t2[ax][d] <= v1 && v1 >= 0) || (t2[ax][d] >= v1 && v1 <= 0)))
-                    v2 = t2[ax][d];
+            if (f1[ax][d] && (v1[ax] == DBL_MAX || qmag(t1[ax][d]) < qmag(v1[ax]))) {
+                v1[ax] = t1[ax][d];
+                v2[ax] = DBL_MAX;
+                if (f2[ax][d] && (v1[ax] == 0.0 || t2[ax][d] * v1[ax] < 0 ||
+                                  qmag(t2[ax][d]) <= qmag(v1[ax])))
+                    v2[ax] = t2[ax][d];
             }
         }
-        if (v2 < DBL_MAX) {
-            const double tp = one_third * (4 * v1 - v2);
-            a += g.idx2[ax] * aa;
-            b -= g.idx2[ax] * 2 * aa * tp;
-            c += g.idx2[ax] * aa * (tp * tp);
-        } else if (v1 < DBL_MAX) {
-            a += g.idx2[ax];
-            b -= g.idx2[ax] * 2 * v1;
-            c += g.idx2[ax] * (v1 * v1);
-        }
+        active[ax] = v1[ax] < DBL_MAX;
+        nactive += active[ax] ? 1 : 0;
     }
-    c -= 1;
-    const double det = b * b - 4 * a * c;
-    if (det > 0) {
-        if (phi > DBL_EPSILON) return (-b + sqrt(det)) / 2.0 / a;
-        return (-b - sqrt(det)) / 2.0 / a;
+#pragma unroll 1
+    while (nactive > 0) {
+        double a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int ax = 3 - NDIM; ax < 3; ++ax) {
+            if (!active[ax]) continue;
+            if (v2[ax] < DBL_MAX) {
+                const double tp = one_third * (4 * v1[ax] - v2[ax]);
+                a += g.idx2[ax] * aa;
+                b -= g.idx2[ax] * 2 * aa * tp;
+                c += g.idx2[ax] * aa * (tp * tp);
+            } else {
+                a += g.idx2[ax];
+                b -= g.idx2[ax] * 2 * v1[ax];
+                c += g.idx2[ax] * (v1[ax] * v1[ax]);
+            }
+        }
+        c -= 1;
+        const double det = b * b - 4 * a * c;
+        if (det > 0) {
+            const double r = (phi > DBL_EPSILON) ? (-b + sqrt(det)) / 2.0 / a
+                                                 : (-b - sqrt(det)) / 2.0 / a;
+            bool causal = true;
+#pragma unroll
+            for (int ax = 3 - NDIM; ax < 3; ++ax) {
+                if (!active[ax]) continue;
+                if (qmag(r) <= qmag(v1[ax])) causal = false;
+                if (v2[ax] < DBL_MAX && qmag(r) <= qmag(v2[ax])) causal = false;
+            }
+            if (causal) return r;
+        }
+        // remove the contributor farthest from the interface (first maximum in the order
+        // ax0.v2, ax0.v1, ax1.v2, ...): a value2 demotes its axis, a value1 drops it
+        int worst = -1;
+        bool worst_is_v2 = false;
+        float wv = -1.0f;
+#pragma unroll
+        for (int ax = 3 - NDIM; ax < 3; ++ax) {
+            if (!active[ax]) continue;
+            if (v2[ax] < DBL_MAX && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = true; }
+            if (qmag(v1[ax]) > wv) { wv = qmag(v1[ax]); worst = ax; worst_is_v2 = false; }
+        }
+#pragma unroll
+        for (int ax = 3 - NDIM; ax < 3; ++ax)
+            if (ax == worst) {
+                if (worst_is_v2) v2[ax] = DBL_MAX;
+                else active[ax] = false;
+            }
+        if (!worst_is_v2) nactive--;
     }
     return 0.0;
 }
 
 __device__ __forceinline__ bool key_less(double ta, i64 ia, double tb, i64 ib) {
-    const double a = fabs(ta), b = fabs(tb);
+    const float a = qmag(ta), b = qmag(tb);
     return (a < b) || (a == b && ia < ib);
 }
 
@@ -255,8 +302,8 @@ __device__ double replay(i64 l, const double* __restrict__ u, const double* T, c
             const int c1 = coord[ax] + j, c2 = coord[ax] + 2 * j;
             if (c1 >= 0 && c1 < ext[ax]) {
                 const i64 n = l + j * st[ax];
-                const double t = T[n];
-                const u8 s = mask[n];
+                const double t = __ldcg(T + n);       // L2: other CTAs update T concurrently
+                const u8 s = __ldcg(mask + n);
                 t1[ax][d] = t;
                 f1[ax][d] = (s == 1);
                 e1[ax][d] = (s == 2) && (fabs(t) <= band);
@@ -264,8 +311,8 @@ __device__ double replay(i64 l, const double* __restrict__ u, const double* T, c
             }
             if (c2 >= 0 && c2 < ext[ax]) {
                 const i64 n = l + 2 * j * st[ax];
-                const double t = T[n];
-                const u8 s = mask[n];
+                const double t = __ldcg(T + n);
+                const u8 s = __ldcg(mask + n);
                 t2[ax][d] = t;
                 f2[ax][d] = (s == 1);
                 e2[ax][d] = (s == 2) && (fabs(t) <= band);
@@ -350,7 +397,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, u8* mask, i64* list, i
         bool changed = false;
         for (i64 t = tid; t < nc; t += nthreads) {
             const i64 l = list[cap - 1 - t];
-            const double old = T[l];
+            const double old = __ldcg(T + l);
             const double nw = replay<NDIM>(l, u, T, mask, g, band);
             if (__double_as_longlong(old) != __double_as_longlong(nw)) {
                 T[l] = nw;

@@ -16,9 +16,11 @@
  *                          the algorithm below is the published fast-marching method with the
  *                          second-order upwind stencil as scikit-fmm implements it, written
  *                          from the description in SURVEY.md section 8c.  Two points where the
- *                          upstream behaviour is not known for certain are decided here and
- *                          documented at the code: heap ties (broken by flat index) and a
- *                          non-positive discriminant (the update is skipped).
+ *                          upstream behaviour is not known for certain, or is not well defined,
+ *                          are decided here and documented at the code: heap ties (broken by
+ *                          flat index) and non-causal quadratic roots (the farthest neighbour
+ *                          is dropped and the quadratic re-solved, as the published method
+ *                          prescribes; see fmm_solve).
  *   orc_marching_squares_length
  *                          skimage.measure.find_contours(u, 0) total poly-line length with
  *                          lsml's closing chord and dx[::-1] scaling, lsml/feature/provided/shape.py:70-85.
@@ -35,6 +37,13 @@
 #include <string.h>
 
 typedef unsigned char u8;
+
+/* Ordering decisions of the marcher (heap order, upwind admissibility, choice of the nearer
+ * side, second-order switch) are made on |d| rounded to float32: values that are equal in
+ * exact arithmetic but differ by float64 rounding noise (symmetric inputs such as the +-1
+ * step function of a ball initializer) then tie exactly and are ordered by flat index, not by
+ * noise.  The distances themselves stay float64. */
+static inline float qmag(double d) { return (float)fabs(d); }
 
 static inline double dmax(double a, double b) { return a < b ? b : a; } /* helpers.c:57 */
 static inline double dmin(double a, double b) { return a > b ? b : a; } /* helpers.c:58 */
@@ -157,7 +166,7 @@ static long nb(const fmm_t *m, long i, int axis, int step) {
  * (scikit-fmm's own tie behaviour depends on its heap internals and is not reproducible
  * without its source; a total order makes the result well defined.) */
 static int key_less(const fmm_t *m, long i, long j) {
-    double a = fabs(m->dist[i]), b = fabs(m->dist[j]);
+    float a = qmag(m->dist[i]), b = qmag(m->dist[j]);
     return (a < b) || (a == b && i < j);
 }
 static void heap_swap(fmm_t *m, long a, long b) {
@@ -192,46 +201,101 @@ static long heap_pop(fmm_t *m) {
     return top;
 }
 
-/* Second-order upwind update of voxel i from its currently FROZEN stencil.  Per axis the
- * frozen neighbour with the smaller |d| supplies value1; when the voxel two cells away in the
- * same direction is frozen too and not farther from the interface (in the signed sense) the
- * second-order one-sided difference (3T - 4 v1 + v2)/(2 dx) is used, i.e. the term
- * 9/4 (T - (4 v1 - v2)/3)^2 / dx^2.  Returns 0.0 when there is no positive discriminant
- * (the caller then leaves the voxel untouched). */
-static double fmm_update(const fmm_t *m, long i) {
+/* Upwind update of voxel i from its currently FROZEN stencil (scikit-fmm
+ * distanceMarcher::updatePointOrderTwo + solveQuadratic).  Per axis the frozen neighbour with
+ * the smaller |d| supplies value1; when the voxel two cells away in the same direction is
+ * frozen too and not farther from the interface (in the signed sense) the second-order
+ * one-sided difference (3T - 4 v1 + v2)/(2 dx) is used, i.e. the term
+ * 9/4 (T - (4 v1 - v2)/3)^2 / dx^2, else the first-order term (T - v1)^2 / dx^2.
+ *
+ * CAUSALITY (decided here, see the file header): the published fast-marching method is an
+ * upwind scheme -- a value may only be computed from neighbours that are not farther from the
+ * interface than the value itself.  When the quadratic has no positive discriminant, or its
+ * root is smaller in magnitude than one of the values it was computed from, the contributor
+ * with the largest magnitude is removed (a value2: the axis falls back to first order; a
+ * value1: the axis is dropped) and the quadratic is solved again (Sethian 1996, the usual
+ * implementation of max(D-T, -D+T, 0)).  Upstream scikit-fmm does not make this check; its
+ * result then depends on the order in which its heap happens to freeze voxels, which no
+ * specification pins down.  With the check every freeze value is >= the values frozen before
+ * it, the marcher's result is independent of heap internals and a parallel solver can
+ * reproduce it exactly.  Returns 0.0 when there is no frozen neighbour at all. */
+static double fmm_solve(int ndim, const double *idx2, const double *v1in, const double *v2in,
+                        double phi) {
     const double aa = 9.0 / 4.0, one_third = 1.0 / 3.0;
-    double a = 0, b = 0, c = 0;
-    for (int ax = 0; ax < m->ndim; ++ax) {
-        double v1 = DBL_MAX, v2 = DBL_MAX;
-        for (int j = -1; j < 2; j += 2) {
-            long n = nb(m, i, ax, j);
-            if (n != -1 && m->flag[n] == FROZEN && fabs(m->dist[n]) < fabs(v1)) {
-                v1 = m->dist[n];
-                v2 = DBL_MAX;
-                long n2 = nb(m, i, ax, 2 * j);
-                if (n2 != -1 && m->flag[n2] == FROZEN &&
-                    ((m->dist[n2] <= v1 && v1 >= 0) || (m->dist[n2] >= v1 && v1 <= 0)))
-                    v2 = m->dist[n2];
+    double v1[3], v2[3];
+    int active[3];
+    int nactive = 0;
+    for (int ax = 0; ax < ndim; ++ax) {
+        v1[ax] = v1in[ax]; v2[ax] = v2in[ax];
+        active[ax] = v1[ax] < DBL_MAX; nactive += active[ax];
+    }
+    while (nactive > 0) {
+        double a = 0, b = 0, c = 0;
+        for (int ax = 0; ax < ndim; ++ax) {
+            if (!active[ax]) continue;
+            if (v2[ax] < DBL_MAX) {
+                double tp = one_third * (4 * v1[ax] - v2[ax]);
+                a += idx2[ax] * aa;
+                b -= idx2[ax] * 2 * aa * tp;
+                c += idx2[ax] * aa * (tp * tp);
+            } else {
+                a += idx2[ax];
+                b -= idx2[ax] * 2 * v1[ax];
+                c += idx2[ax] * (v1[ax] * v1[ax]);
             }
         }
-        if (v2 < DBL_MAX) {
-            double tp = one_third * (4 * v1 - v2);
-            a += m->idx2[ax] * aa;
-            b -= m->idx2[ax] * 2 * aa * tp;
-            c += m->idx2[ax] * aa * (tp * tp);
-        } else if (v1 < DBL_MAX) {
-            a += m->idx2[ax];
-            b -= m->idx2[ax] * 2 * v1;
-            c += m->idx2[ax] * (v1 * v1);
+        c -= 1;
+        double det = b * b - 4 * a * c;
+        if (det > 0) {
+            double r = (phi > DBL_EPSILON) ? (-b + sqrt(det)) / 2.0 / a
+                                           : (-b - sqrt(det)) / 2.0 / a;
+            int causal = 1;
+            for (int ax = 0; ax < ndim; ++ax) {
+                if (!active[ax]) continue;
+                if (qmag(r) <= qmag(v1[ax])) causal = 0;
+                if (v2[ax] < DBL_MAX && qmag(r) <= qmag(v2[ax])) causal = 0;
+            }
+            if (causal) return r;
         }
-    }
-    c -= 1;
-    double det = b * b - 4 * a * c;
-    if (det > 0) {
-        if (m->phi[i] > DBL_EPSILON) return (-b + sqrt(det)) / 2.0 / a;
-        return (-b - sqrt(det)) / 2.0 / a;
+        /* remove the contributor farthest from the interface: a value2 demotes its axis to
+         * first order, a value1 drops the axis (first maximum in the order ax0.v2, ax0.v1, ...) */
+        int worst = -1, worst_is_v2 = 0;
+        float wv = -1.0f;
+        for (int ax = 0; ax < ndim; ++ax) {
+            if (!active[ax]) continue;
+            if (v2[ax] < DBL_MAX && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = 1; }
+            if (qmag(v1[ax]) > wv) { wv = qmag(v1[ax]); worst = ax; worst_is_v2 = 0; }
+        }
+        if (worst_is_v2) v2[worst] = DBL_MAX;
+        else { active[worst] = 0; nactive--; }
     }
     return 0.0;
+}
+
+/* scikit-fmm's switch `(d2 <= v1 && v1 >= 0) || (d2 >= v1 && v1 <= 0)`: the voxel two cells
+ * away must not be farther from the interface than the direct neighbour, in the signed sense
+ * (a voxel on the other side of the interface always qualifies). */
+static int second_order_ok(double d2, double v1) {
+    return v1 == 0.0 || d2 * v1 < 0 || qmag(d2) <= qmag(v1);
+}
+
+static double fmm_update(const fmm_t *m, long i) {
+    double v1[3], v2[3];
+    for (int ax = 0; ax < m->ndim; ++ax) {
+        v1[ax] = DBL_MAX; v2[ax] = DBL_MAX;
+        for (int j = -1; j < 2; j += 2) {
+            long n = nb(m, i, ax, j);
+            if (n != -1 && m->flag[n] == FROZEN &&
+                (v1[ax] == DBL_MAX || qmag(m->dist[n]) < qmag(v1[ax]))) {
+                v1[ax] = m->dist[n];
+                v2[ax] = DBL_MAX;
+                long n2 = nb(m, i, ax, 2 * j);
+                if (n2 != -1 && m->flag[n2] == FROZEN && second_order_ok(m->dist[n2], v1[ax]))
+                    v2[ax] = m->dist[n2];
+            }
+        }
+    }
+    return fmm_solve(m->ndim, m->idx2, v1, v2, m->phi[i]);
 }
 
 /* phi: level-set values; narrow: band half-width (0 => march the whole grid).
@@ -301,7 +365,10 @@ long orc_fmm_distance(int ndim, const int *shape, const double *phi, const doubl
     /* -- march */
     while (m.nheap > 0) {
         long x = heap_pop(&m);
-        if (narrow != 0 && fabs(m.dist[x]) > narrow) { m.flag[x] = NARROW; break; }
+        /* outside the band: never frozen.  scikit-fmm breaks out of its loop here; with heap
+         * order decided on rounded keys (qmag) a later pop can tie with this one and still be
+         * inside the band, so the loop continues (nothing is pushed from a discarded voxel). */
+        if (narrow != 0 && fabs(m.dist[x]) > narrow) { m.flag[x] = NARROW; continue; }
         m.flag[x] = FROZEN;
         nfrozen++;
         for (int ax = 0; ax < ndim; ++ax)

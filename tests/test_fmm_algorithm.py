@@ -1,0 +1,111 @@
+"""CPU-only checks of the band-rebuild ALGORITHM (no GPU needed).
+
+1. The sequential fast-marching oracle (oracle/lsml_oracle.c:orc_fmm_distance) against the
+   reference's own known answers (lsml/util/test/test_distance_transform.py:11-53) and an
+   analytic sphere.
+2. The fixed point of the local replay operator that lsml_b200/csrc/fmm.cu iterates
+   (stated in plain C in oracle/fmm_replay_model.c) equals the sequential result BIT-EXACTLY --
+   mask and distances -- on random smooth, noisy, symmetric-step and anisotropic inputs, for
+   both in-place and synchronous sweeps (i.e. independent of the GPU's scheduling).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def fixed_point(O, phi, dx, band, jacobi, max_sweeps=500):
+    lib = O._lib()
+    lib.rm_fmm_fixed_point.restype = ctypes.c_long
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    dx = np.asarray(dx, dtype=np.float64).copy()
+    shape = np.asarray(phi.shape, dtype=np.int32)
+    dist = np.zeros_like(phi)
+    frozen = np.zeros(phi.shape, dtype=np.uint8)
+    p = lambda a, t: a.ctypes.data_as(ctypes.POINTER(t))
+    n = lib.rm_fmm_fixed_point(
+        ctypes.c_int(phi.ndim), p(shape, ctypes.c_int), p(phi, ctypes.c_double),
+        p(dx, ctypes.c_double), ctypes.c_double(float(band)), ctypes.c_int(jacobi),
+        ctypes.c_int(max_sweeps), p(dist, ctypes.c_double), p(frozen, ctypes.c_uint8), None)
+    return dist, frozen.astype(bool), n
+
+
+def test_reference_known_answers(oracle):
+    d, m = oracle.distance_transform(np.r_[-1, -1, 1, -1, -1.], 1, [1.])
+    assert (d == np.r_[0., -0.5, 0.5, -0.5, 0.]).all()
+    assert (m == np.r_[False, True, True, True, False]).all()
+    d, m = oracle.distance_transform(np.ones((4, 5, 6)), 0, [1, 1, 1.])
+    assert m.sum() == 0 and (d == np.inf).all()
+    d, m = oracle.distance_transform(-np.ones((4, 5, 6)), 0, [1, 1, 1.])
+    assert m.sum() == 0 and (d == -np.inf).all()
+    arr = np.ones((4, 5, 6))
+    arr[2] = -1
+    d, m = oracle.distance_transform(arr, 0, [1, 1, 1.])
+    assert m.sum() == arr.size
+    d, m = oracle.distance_transform(np.zeros((4, 5, 6)), 0, [1, 1, 1.])
+    assert m.sum() == 120 and (d == 0).all()
+
+
+def test_sphere_distance_is_accurate(oracle):
+    n = 48
+    g = np.indices((n, n, n)).astype(float) - n / 2 + 0.3
+    phi = 15.0 - np.sqrt((g ** 2).sum(0))
+    d, m = oracle.fmm_distance(phi, [1, 1, 1.], 4.0)
+    assert m.sum() > 0 and not m.all()
+    assert np.abs(d - phi)[m].mean() < 0.08
+    # every voxel that the exact distance puts well inside the band is in the mask
+    assert m[np.abs(phi) < 3.0].all() and not m[np.abs(phi) > 5.0].any()
+
+
+def _random_case(rs):
+    ndim = rs.choice([1, 2, 3])
+    shape = tuple(rs.randint(6, 36 if ndim < 3 else 20, size=ndim))
+    dx = np.ones(ndim) if rs.rand() < 0.5 else rs.uniform(0.4, 2.5, size=ndim)
+    band = rs.choice([0.0, 1.0, 2.0, 3.0, 4.5])
+    kind = rs.randint(5)
+    g = np.indices(shape).astype(float)
+    sym = rs.rand() < 0.5
+    c = [s / 2 for s in shape] if sym else [s / 2 + rs.uniform(-2, 2) for s in shape]
+    r = np.sqrt(sum(((g[a] - c[a]) * dx[a]) ** 2 for a in range(ndim)))
+    R = 0.3 * min(np.array(shape) * dx)
+    if kind == 0:
+        u = R - r
+    elif kind in (1, 4):
+        u = 2 * ((R - r) > 0).astype(float) - 1            # InitializerBase: u0 = 2*mask - 1
+        if kind == 4:
+            u = u + 0.3 * rs.randn(*shape) * (np.abs(R - r) < 3)
+    elif kind == 2:
+        u = rs.randn(*shape)
+    else:
+        u = (R - r) * (1 + 0.5 * np.sin(g[0] / 2.0)) + 0.3 * rs.randn(*shape)
+    if rs.rand() < 0.2:
+        u[tuple(rs.randint(0, s) for s in shape)] = 0.0
+    return u, dx, band
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_replay_fixed_point_equals_sequential_marcher(oracle, seed):
+    rs = np.random.RandomState(seed)
+    checked = 0
+    for _ in range(120):
+        u, dx, band = _random_case(rs)
+        if not ((u > 0).any() and (u < 0).any()):
+            continue
+        wd, wm = oracle.distance_transform(u, band, dx)
+        for jacobi in (0, 1):
+            d, m, sweeps = fixed_point(oracle, u, dx, band, jacobi)
+            assert sweeps > 0, "no convergence"
+            assert np.array_equal(m, wm)
+            assert np.array_equal(d, wd)
+        checked += 1
+    assert checked > 80
+
+
+def test_ball_initializer_band_51x51_and_64cubed(oracle):
+    """The first band of every segment() run: +-1 step function of a centred ball."""
+    for shape, radius in (((51, 51), 10.0), ((64, 64, 64), 5.0)):
+        u0 = oracle.ball_init(shape, radius, np.ones(len(shape)))
+        wd, wm = oracle.distance_transform(u0, 3.0, np.ones(len(shape)))
+        d, m, sweeps = fixed_point(oracle, u0, np.ones(len(shape)), 3.0, 0)
+        assert sweeps > 0 and np.array_equal(m, wm) and np.array_equal(d, wd)
+        assert wm.sum() > 0
