@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- narrow-band voxel-iterations / s of the lsml level-set evolution hot path.
+
+Workload (BASELINE.json configs[2], the configuration the north_star target is quoted on;
+SURVEY.md section 8d "C3"): one synthetic 256^3 volume per GPU (a noisy "hamburger" sphere with a
+slab cut), +-1 ball initialisation r=40, band=3, dx=1, F=16 features (8 image features at
+sigma in {0,2}, distance to centre of mass, 6 moments, volume), tree-ensemble velocity
+(StandardScaler + RandomForestRegressor(100, max_samples=300) per iteration, trained on the host
+in the untimed setup), 50 evolution iterations.
+
+A "step" is ONE segmentation pass = (re-)initialise u0 on the device + 50 iterations of
+features -> forest velocity -> upwind update -> band rebuild (fast marching) -> compaction,
+i.e. the full body of lsml/core/model.py:378-398.  The metric counts the band voxels that enter
+every iteration.  `value` is measured with the normalised image planes already resident in
+HBM; `e2e` goes through the public API (LevelSetMachineLearning.segment_batch) with the raw
+image in pinned HOST memory (H2D copy, normalisation, Gaussian/edge planes, evolution, D2H of
+the final mask inside the timed region).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size 256]
+N > 1: torchrun, one volume per rank (independent items, no data-path collective; weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ITERS = 50
+BAND = 3.0
+STEP = 0.35
+INIT_RADIUS = 40.0
+SPECS = ([("image_sample", 0.0), ("image_sample", 2.0), ("image_edge", 0.0), ("image_edge", 2.0),
+          ("band_mean", 0.0), ("band_mean", 2.0), ("band_std", 0.0), ("band_std", 2.0),
+          ("dist_to_com",), ("moments", (0, 1, 2), (1, 2)), ("size",)])
+
+
+def make_features():
+    from lsml_b200.feature import (DistanceToCenterOfMass, Moments, Size,
+                                   get_basic_image_features)
+    return (get_basic_image_features(ndim=3, sigmas=[0, 2]) +
+            [DistanceToCenterOfMass(ndim=3), Moments(ndim=3, axes=(0, 1, 2), orders=(1, 2)),
+             Size(ndim=3)])
+
+
+def make_volume(n, seed):
+    """Sphere with a slab removed, noise added (after lsml/data/dim3/hamburger.py:7-79, written
+    independently; float64).  Returns (img, radius, centre)."""
+    rs = np.random.RandomState(seed)
+    scale = n / 256.0
+    radius = rs.uniform(60, 90) * scale
+    c = n / 2.0 + rs.uniform(-4, 4, size=3) * scale
+    ax = [np.arange(n, dtype=np.float64) - c[a] for a in range(3)]
+    r2 = ax[0][:, None, None] ** 2 + ax[1][None, :, None] ** 2 + ax[2][None, None, :] ** 2
+    nrm = rs.randn(3)
+    nrm /= np.linalg.norm(nrm)
+    plane = np.abs(nrm[0] * ax[0][:, None, None] + nrm[1] * ax[1][None, :, None] +
+                   nrm[2] * ax[2][None, None, :])
+    img = ((r2 <= radius * radius) & (plane > 5 * scale)).astype(np.float64)
+    img += 0.25 * rs.standard_normal(img.shape)
+    return img, radius, c
+
+
+def target_distance_on_band(band_idx, n, radius, c):
+    """Ground-truth signed distance to the enclosing sphere at the band voxels (the regression
+    target, fit_job_handler.py:371-375)."""
+    k = band_idx % n
+    j = (band_idx // n) % n
+    i = band_idx // (n * n)
+    return radius - np.sqrt((i - c[0]) ** 2 + (j - c[1]) ** 2 + (k - c[2]) ** 2)
+
+
+def train_regressors(eng, u0, n, radius, c, seed, n_iters=N_ITERS, log=None):
+    """Untimed setup: one RandomForest per iteration, trained on the host from the device
+    feature matrix (the reference's fit loop, fit_job_handler.py:381-428, without its files)."""
+    import warnings
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    rs = np.random.RandomState(seed)
+    eng.set_level_sets(u0)
+    regs = []
+    for it in range(n_iters):
+        nb = eng.n_band
+        X = eng.compute_features().cpu().numpy()
+        idx = eng.band_idx[:nb].cpu().numpy()
+        y = target_distance_on_band(idx, n, radius, c)
+        sub = rs.choice(nb, size=min(nb, 20000), replace=False)
+        reg = Pipeline([("standardscaler", StandardScaler()),
+                        ("regressor", RandomForestRegressor(n_estimators=100, max_samples=300,
+                                                            random_state=rs))])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            reg.fit(X[sub], y[sub])
+        regs.append(reg)
+        eng.step(reg, STEP)
+        if log and it % 10 == 0:
+            log("  trained iteration %d (band %d)" % (it, nb))
+    return regs
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for q, nm in enumerate(names)
+                   if any(len(s) > 2 + q and s[2 + q].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference path, timed on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_run(n, seed, steps, warmup, regs=None, budget_s=150.0, log=None):
+    """Times the reference's CPU path (oracle port: numpy/scipy feature work with the
+    reference's work pattern + sklearn predict + the reference's own compiled C for the upwind
+    gradient when oracle/_ref exists + the sequential fast-marching restatement) for
+    `warmup + steps` evolution iterations.  Each step is ONE iteration on a centred crop of the
+    volume whose size is chosen so that the whole run fits `budget_s`."""
+    import warnings
+    from oracle import oracle as O
+    O.build()
+    t0 = time.perf_counter()
+    # crop size: the reference's iteration cost is ~1 us per grid voxel per feature pass
+    est_per_voxel = 1.0e-6
+    total_steps = max(1, steps + warmup)
+    crop = n
+    while crop > 64 and est_per_voxel * crop ** 3 * total_steps > budget_s:
+        crop //= 2
+    img, radius, c = make_volume(n, seed)
+    lo = (n - crop) // 2
+    img = np.ascontiguousarray(img[lo:lo + crop, lo:lo + crop, lo:lo + crop])
+    c = c - lo
+    dx = np.ones(3)
+    img_ = O.normalize_image(img)
+    r_init = min(INIT_RADIUS * n / 256.0, 0.3 * crop)
+    u = O.ball_init(img.shape, r_init, dx)
+    dist, mask = O.distance_transform(u, BAND, dx)
+    if regs is None:
+        from sklearn.ensemble import RandomForestRegressor
+        from sklearn.pipeline import Pipeline
+        from sklearn.preprocessing import StandardScaler
+        X = O.feature_matrix(SPECS, u, img_, dist, mask, dx)
+        idx = np.flatnonzero(mask.ravel())
+        y = target_distance_on_band(idx, crop, radius, c)
+        rs = np.random.RandomState(seed)
+        reg = Pipeline([("standardscaler", StandardScaler()),
+                        ("regressor", RandomForestRegressor(n_estimators=100, max_samples=300,
+                                                            random_state=rs))])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            reg.fit(X, y)
+        regs = [reg]
+    use_ref = O.reference_lib() is not None
+    times, counts = [], []
+    for it in range(total_steps):
+        nb = int(mask.sum())
+        t1 = time.perf_counter()
+        u, dist, mask, _ = O.evolve_step(u, img_, dist, mask, dx, SPECS, regs[it % len(regs)],
+                                         STEP, BAND, use_reference=use_ref)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            times.append(t2 - t1)
+            counts.append(nb)
+        if log:
+            log("  cpu iteration %d: band %d, %.2f s" % (it, nb, t2 - t1))
+    return {"seconds": float(sum(times)), "band_voxel_iterations": int(sum(counts)),
+            "steps": len(times), "crop": crop, "kind": "port",
+            "gradient_kernel": "oracle/_ref (reference C)" if use_ref else "oracle C port",
+            "setup_s": time.perf_counter() - t0 - float(sum(times))}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res = cpu_reference_run(args.size, 1234, args.steps, args.warmup, budget_s=150.0)
+    value = res["band_voxel_iterations"] / res["seconds"]
+    cores = 1
+    sample = ("%d evolution iterations (features+RF-100 velocity+update+band rebuild) on the "
+              "centred %d^3 crop of the %d^3 volume, single thread (the reference is "
+              "single-threaded)" % (res["steps"], res["crop"], args.size))
+    line = {
+        "impl": "reference", "metric": "narrow-band voxel-iterations/sec (feat+velocity+update+band rebuild)",
+        "value": value, "unit": "band-voxel-iterations/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(1, res["steps"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C3: 256^3 volume, RF-100 velocity, band=3, F=16 (CPU arm: one "
+                               "iteration per step on a crop)", "crop": res["crop"]},
+        "cpu_baseline": {"value": value, "unit": "band-voxel-iterations/s", "cores": cores,
+                         "kind": res["kind"], "sample": sample,
+                         "gradient_kernel": res["gradient_kernel"]},
+        "e2e": {"value": value, "unit": "band-voxel-iterations/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    log = (lambda m: print("[rank %d] %s" % (rank, m), file=sys.stderr, flush=True)) \
+        if args.verbose else None
+
+    from lsml_b200 import LevelSetMachineLearning, _lib
+    from lsml_b200.core.engine import BandEngine
+    from lsml_b200.core.model import _ball_u0
+    from lsml_b200.initializer import BallInitializer
+
+    n = args.size
+    seed = 1234 + rank                      # every rank evolves its own volume
+    img, radius, c = make_volume(n, seed)
+    dx = np.ones(3)
+    r_init = INIT_RADIUS * n / 256.0
+    eng = BandEngine((n, n, n), 1, dx=dx, band=BAND, specs=SPECS, device=device)
+    eng.load_images(img[None], normalize=True)
+    centre = 0.5 * np.array([n, n, n], dtype=np.float64)
+    u0 = _ball_u0(eng, centre[None], [r_init]).clone()
+    regs = train_regressors(eng, u0, n, radius, c, seed, log=log)
+    model = LevelSetMachineLearning.from_regressors(make_features(), BallInitializer(radius=r_init),
+                                                    regs, step=STEP, band=BAND)
+    dev_regs = [model._device_model(i, device) for i in range(N_ITERS)]
+
+    def one_pass():
+        eng.set_level_sets(u0)
+        total = 0
+        for i in range(N_ITERS):
+            total += eng.step(dev_regs[i], STEP)
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bvi = 0
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            bvi += one_pass()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+
+    # ---- end to end through the public API, host buffers --------------------------------------
+    img_pinned = torch.from_numpy(img[None]).pin_memory()
+    out_host = torch.empty((1, n, n, n), dtype=torch.bool).pin_memory()
+
+    def e2e_pass():
+        u_fin, m_fin = model.segment_batch(img_pinned, dx=dx, n_iters=N_ITERS, device=device)
+        out_host.copy_(u_fin > 0, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_pass()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_pass()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    seg_voxels = int(out_host.sum())
+
+    # ---- per-kernel evidence: dense stencil kernel at the same grid (HBM roofline) ------------
+    from lsml_b200.gradient import masked_gradient as mg
+    A = eng.u[0]
+    nu = torch.randn_like(A)
+    full = torch.ones_like(A, dtype=torch.bool)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > L2 (126 MB)
+    for _ in range(3):
+        mg.gradient_magnitude_osher_sethian(A, nu, mask=full, dx=dx)
+    st_ms = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mg.gradient_magnitude_osher_sethian(A, nu, mask=full, dx=dx)
+        b.record()
+        torch.cuda.synchronize()
+        st_ms.append(a.elapsed_time(b))
+    st_ms = float(np.median(st_ms))
+    peak, peak_src = measured_peak_gbs()
+    # gmag_os allocates + zero-fills its output (8 B/voxel write) before the kernel, as the
+    # reference wrapper does; the kernel itself moves 25 B/voxel algorithmic
+    stencil_bytes = 25.0 * n ** 3 + 8.0 * n ** 3
+    stencil_gbs = stencil_bytes / (st_ms * 1e-3) / 1e9
+
+    # ---- aggregate over ranks ------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    cnt = torch.tensor([bvi, launches], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    bvi_all, launches_all = int(cnt[0]), int(cnt[1])
+    value = bvi_all / (ms_max * 1e-3)
+    e2e_value = (bvi_all / args.steps * e2e_steps) / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        line = {
+            "metric": "narrow-band voxel-iterations/sec (feat+velocity+update+band rebuild)",
+            "value": value, "unit": "band-voxel-iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C3: one synthetic %d^3 volume per GPU, RF-100 tree-ensemble "
+                                   "velocity, band=3, dx=1, F=16, %d iterations per step "
+                                   "(one step = one full segmentation pass)" % (n, N_ITERS),
+                       "band_voxel_iterations_per_step": bvi_all // max(1, args.steps),
+                       "l2": "working set > L2: 5 x %d MB planes + u; stencil probe flushes L2 "
+                             "between launches" % (8 * n ** 3 // 2 ** 20),
+                       "final_segmentation_voxels": seg_voxels},
+            "e2e": {"value": e2e_value, "unit": "band-voxel-iterations/s",
+                    "h2d_bytes_per_step": int(img_pinned.numel() * 8),
+                    "d2h_bytes_per_step": int(out_host.numel()),
+                    "api": "LevelSetMachineLearning.segment_batch(host image) -> host mask",
+                    "ms_per_step": e2e_ms_max / e2e_steps},
+            "gpu_launches": launches_all,
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": "gmag_os_kernel<double,3> (dense %d^3, full mask)" % n,
+                         "achieved": stencil_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": stencil_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "ms": st_ms},
+        }
+        if not args.no_cpu_baseline:
+            res = cpu_reference_run(n, 1234, 1, 0, regs=None, budget_s=25.0, log=log)
+            v = res["band_voxel_iterations"] / res["seconds"]
+            line["cpu_baseline"] = {
+                "value": v, "unit": "band-voxel-iterations/s", "cores": 1, "kind": res["kind"],
+                "sample": "1 evolution iteration (features+RF-100+update+band rebuild) on the "
+                          "centred %d^3 crop, single thread, %.1f s" % (res["crop"], res["seconds"]),
+                "gradient_kernel": res["gradient_kernel"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,18 @@ int lsml_fmm_rebuild(int ndim, const int *shape, long long batch, const double *
  * {n_init, n_cand, changed, sweeps, converged, prev_init, prev_cand, -} */
 int lsml_fmm_counters(long long total, void *workspace, long long *out, void *stream);
 
+/* ---- either side of the path -------------------------------------------------- */
+/* u0 = 2*ball - 1 with ball = (radius - |idx*dx - location*dx|) > 0
+ * (lsml/initializer/provided/ball.py:13-31, initializer_base.py:56).  location: HOST double[ndim]
+ * in index units (used when centres == NULL); centres / radii: optional DEVICE per-item arrays
+ * (centres[item*3 + padded axis], physical units; radii[item]). */
+int lsml_ball_init(int ndim, const int *shape, long long batch, const double *dx, double *u,
+                   const double *location, double radius, const double *centres,
+                   const double *radii, void *stream);
+/* counts[item*2 + {0,1}] = |{u>0} & seg|, |{u>0} | seg|  (lsml/score_functions.py:4-30) */
+int lsml_overlap_counts(long long voxels, long long batch, const double *u, const uint8_t *seg,
+                        unsigned long long *counts, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

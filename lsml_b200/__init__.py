@@ -12,3 +12,11 @@ Every numerical operation runs in hand-written CUDA kernels behind the C ABI of
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is not built)
 
 __version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # lazy: importing the model pulls in torch
+    if name in ("LevelSetMachineLearning", "SegmentationModel"):
+        from .core.model import LevelSetMachineLearning
+        return LevelSetMachineLearning
+    raise AttributeError(name)

@@ -378,10 +378,13 @@ class BandEngine:
                 _lib.ptr(self.u), _lib.ptr(self.vel), _lib.ptr(self.band_idx),
                 _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)), _lib.ptr(self.new_u),
                 _lib.c_p(0), ctypes.c_int(1), self._stream()), "band_update")
+            # band indices of THIS iteration (the rebuild below overwrites band_idx); together
+            # with new_u[:nb] this is the sparse record `segment` rebuilds the iterates from
+            self._last_idx = self.band_idx[:nb].clone()
             if record:
                 if self.history is None:
                     self.history = []
-                self.history.append((self.band_idx[:nb].clone(), self.new_u[:nb].clone()))
+                self.history.append((self._last_idx, self.new_u[:nb].clone()))
             self.band_voxel_iterations += nb
             self._global_stats()
             if rebuild:

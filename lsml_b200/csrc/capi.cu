@@ -305,4 +305,15 @@ int lsml_fmm_counters(long long total, void* workspace, long long* out, void* st
     return 0;
 }
 
+int lsml_ball_init(int ndim, const int* shape, long long batch, const double* dx, double* u,
+                   const double* location, double radius, const double* centres,
+                   const double* radii, void* stream) {
+    GEOM(g);
+    return ball_init(g, u, location, radius, centres, radii, (cudaStream_t)stream);
+}
+int lsml_overlap_counts(long long voxels, long long batch, const double* u, const uint8_t* seg,
+                        unsigned long long* counts, void* stream) {
+    return overlap_counts(voxels, batch, u, seg, counts, (cudaStream_t)stream);
+}
+
 }  // extern "C"

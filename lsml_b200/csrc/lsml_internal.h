@@ -71,4 +71,10 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
                 double* dist_out, void* workspace, cudaStream_t s);
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
 
+// misc.cu
+int ball_init(const Geom& g, double* u, const double* location, double radius,
+              const double* centres_dev, const double* radii_dev, cudaStream_t s);
+int overlap_counts(i64 voxels, i64 batch, const double* u, const u8* seg, u64* counts,
+                   cudaStream_t s);
+
 }  // namespace lsml
