@@ -57,6 +57,7 @@ struct FmmCounters {      // device-resident, 8 x i64
     i64 converged;        // 1 when the last march reached its fixed point
     i64 prev_init, prev_cand;   // extents to clear at the next rebuild
     i64 pad;
+    i64 flags[4];         // rotating per-sweep "changed" flags of the march kernel
 };
 
 // Ordering decisions are made on |d| rounded to float32 (see oracle/lsml_oracle.c:qmag): values
@@ -66,12 +67,16 @@ __device__ __forceinline__ float qmag(double d) { return __double2float_rn(fabs(
 
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// claim voxel g (state 0 -> 2); returns true for the single winner.  The state is one byte of
+// State byte of a voxel during the march: 0 far, 1 initial frozen, 2 candidate (clean),
+// 6 candidate whose stencil changed since it was last evaluated (dirty).
+constexpr u8 ST_INIT = 1, ST_CAND = 2, ST_DIRTY = 6;
+
+// claim voxel g (state 0 -> 6); returns true for the single winner.  The state is one byte of
 // a 32-bit word; atomicOr on the word keeps the other three bytes intact.
 __device__ __forceinline__ bool claim(u8* mask, i64 g) {
     unsigned* word = reinterpret_cast<unsigned*>(mask + (g & ~(i64)3));
     const unsigned shift = 8u * (unsigned)(g & 3);
-    const unsigned old = atomicOr(word, 2u << shift);
+    const unsigned old = atomicOr(word, (unsigned)ST_DIRTY << shift);
     return ((old >> shift) & 0xffu) == 0u;
 }
 
@@ -305,8 +310,8 @@ __device__ double replay(i64 l, const double* __restrict__ u, const double* T, c
                 const double t = __ldcg(T + n);       // L2: other CTAs update T concurrently
                 const u8 s = __ldcg(mask + n);
                 t1[ax][d] = t;
-                f1[ax][d] = (s == 1);
-                e1[ax][d] = (s == 2) && (fabs(t) <= band);
+                f1[ax][d] = (s == ST_INIT);
+                e1[ax][d] = (s & ST_CAND) && (fabs(t) <= band);
                 any_direct_frozen |= f1[ax][d];
             }
             if (c2 >= 0 && c2 < ext[ax]) {
@@ -314,8 +319,8 @@ __device__ double replay(i64 l, const double* __restrict__ u, const double* T, c
                 const double t = __ldcg(T + n);
                 const u8 s = __ldcg(mask + n);
                 t2[ax][d] = t;
-                f2[ax][d] = (s == 1);
-                e2[ax][d] = (s == 2) && (fabs(t) <= band);
+                f2[ax][d] = (s == ST_INIT);
+                e2[ax][d] = (s & ST_CAND) && (fabs(t) <= band);
             }
         }
     }
@@ -378,48 +383,79 @@ __device__ double replay(i64 l, const double* __restrict__ u, const double* T, c
 
 constexpr int FMM_MAX_SWEEPS = 4096;
 
+// every candidate that has x in its stencil (one or two cells along an axis) must look again
+template <int NDIM>
+__device__ __forceinline__ void mark_stencil_dirty(i64 l, const FmmGeom& g, u8* mask) {
+    int coord[3];
+    coords_of(l, g, coord);
+    const int ext[3] = {g.n0, g.n1, g.n2};
+    const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+#pragma unroll
+    for (int ax = 3 - NDIM; ax < 3; ++ax) {
+#pragma unroll
+        for (int j = -2; j <= 2; ++j) {
+            if (j == 0) continue;
+            const int cc = coord[ax] + j;
+            if (cc < 0 || cc >= ext[ax]) continue;
+            const i64 n = l + j * st[ax];
+            if (__ldcg(mask + n) & ST_CAND) __stcg(mask + n, ST_DIRTY);   // unconditional re-set
+        }
+    }
+}
+
+// Sweeps of the replay operator over the candidate list until nothing changes.  Only DIRTY
+// candidates are evaluated: a candidate becomes dirty when it is created and whenever a voxel of
+// its stencil changes value, so after the first sweep the work follows the front outwards
+// instead of touching the whole band every time.  One grid barrier per sweep; the "something
+// changed" flags rotate through three slots so that no second barrier is needed to reset them.
+// Ordering of the dirty protocol (per voxel): clear own flag -> fence -> read stencil; a writer
+// does: store T -> fence -> set the readers' flags.  Either the reader sees the new T, or its
+// flag is set again after it cleared it.
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 fmm_march_kernel(const double* __restrict__ u, double* T, u8* mask, i64* list, i64 cap,
-                 FmmGeom g, double band, FmmCounters* ctr) {
+                 FmmGeom g, double band, FmmCounters* ctr, i64* flags /* [3] */) {
     cg::grid_group grid = cg::this_grid();
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 nthreads = (i64)gridDim.x * blockDim.x;
-    volatile i64* vchanged = &ctr->changed;
+    volatile i64* vflags = flags;
     volatile i64* vcand = &ctr->n_cand;
-    i64 done = 0;          // candidates already known at the previous sweep
     int sweep = 0;
     bool converged = false;
+    i64 nc = *vcand;
     for (; sweep < FMM_MAX_SWEEPS; ++sweep) {
-        const i64 nc = *vcand;
-        if (tid == 0) *vchanged = 0;
-        grid.sync();
+        const int slot = sweep % 3;
+        if (tid == 0) vflags[(sweep + 1) % 3] = 0;
         bool changed = false;
         for (i64 t = tid; t < nc; t += nthreads) {
             const i64 l = list[cap - 1 - t];
+            if (__ldcg(mask + l) != ST_DIRTY) continue;
+            __stcg(mask + l, ST_CAND);
+            __threadfence();
             const double old = __ldcg(T + l);
             const double nw = replay<NDIM>(l, u, T, mask, g, band);
             if (__double_as_longlong(old) != __double_as_longlong(nw)) {
-                T[l] = nw;
+                __stcg(T + l, nw);
+                __threadfence();
                 changed = true;
+                mark_stencil_dirty<NDIM>(l, g, mask);
+                // a voxel whose value enters the band exposes its direct neighbours
+                if (fabs(nw) <= band && !(fabs(old) <= band))
+                    push_neighbours<NDIM>(l, g, T, mask, list, cap, ctr);
             }
-            // a voxel with a value inside the band exposes its direct neighbours (once)
-            if (fabs(nw) <= band && !(fabs(old) <= band))
-                push_neighbours<NDIM>(l, g, T, mask, list, cap, ctr);
         }
-        if (changed) *vchanged = 1;
+        if (changed) vflags[slot] = 1;
         __threadfence();
         grid.sync();
-        const bool any = (*vchanged != 0) || (*vcand != nc);
-        done = nc;
-        grid.sync();
+        const i64 nc_new = *vcand;
+        const bool any = (vflags[slot] != 0) || (nc_new != nc);
+        nc = nc_new;
         if (!any) { converged = true; ++sweep; break; }
     }
     // final mask: candidates frozen by the marcher are those with |d| <= band
-    const i64 nc = *vcand;
     for (i64 t = tid; t < nc; t += nthreads) {
         const i64 l = list[cap - 1 - t];
-        if (fabs(T[l]) <= band) mask[l] = 1;
+        if (fabs(__ldcg(T + l)) <= band) mask[l] = 1;
         else { mask[l] = 0; T[l] = pos_inf(); }
     }
     if (tid == 0) {
@@ -427,8 +463,8 @@ fmm_march_kernel(const double* __restrict__ u, double* T, u8* mask, i64* list, i
         ctr->converged = converged ? 1 : 0;
         ctr->prev_init = ctr->n_init;
         ctr->prev_cand = nc;
+        vflags[0] = 0; vflags[1] = 0; vflags[2] = 0;
     }
-    (void)done;
 }
 
 // dist_out = T where mask else 0  (skfmm masked data after post-processing)
@@ -459,11 +495,12 @@ static int march_launch(const double* u, double* T, u8* mask, i64* list, i64 cap
         LSML_CUDA(cudaGetDevice(&dev));
         LSML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (per_sm < 1) { set_error("fmm_march_kernel does not fit on an SM"); return 1; }
-        if (per_sm > 4) per_sm = 4;
+        if (per_sm > 2) per_sm = 2;
         g_march_blocks[NDIM] = per_sm * sms;
     }
+    i64* flags = ctr->flags;
     void* args[] = {(void*)&u, (void*)&T, (void*)&mask, (void*)&list, (void*)&cap, (void*)&fg,
-                    (void*)&band, (void*)&ctr};
+                    (void*)&band, (void*)&ctr, (void*)&flags};
     LSML_CUDA(cudaLaunchCooperativeKernel((void*)fmm_march_kernel<NDIM>, dim3(g_march_blocks[NDIM]),
                                           dim3(256), args, 0, s));
     count_launch();

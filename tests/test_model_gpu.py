@@ -145,7 +145,8 @@ def test_fit_in_memory_learns_to_segment():
     model.fit(imgs=list(imgs), segs=list(segs), regression_model_class=Pipeline,
               regression_model_kwargs=dict(steps=[("s", StandardScaler()),
                                                   ("r", LinearRegression())]),
-              max_iters=25, random_state=rs, validation_history_len=25)
+              max_iters=25, random_state=rs, validation_history_len=25,
+              balance_regression_targets=False)
     assert model.validation_scores.shape[0] == model.iteration + 1
     # the evolution must improve the overlap with the ground truth substantially
     assert model.training_scores[-1].mean() > model.training_scores[0].mean() + 0.2
