@@ -1,0 +1,191 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python -m oracle.gen_golden
+
+Every array stored here is an output of the reference's own code imported through
+oracle/ref_shim.py (its compiled C kernels, its feature classes, its FeatureMap, its
+initializers, its `LevelSetMachineLearning.segment` loop).  The two third-party functions that
+are absent from this container are plugged with the oracle's restatements and that is recorded
+per fixture in the `notes` entry:
+
+  skfmm.distance            -> oracle.skfmm_distance   (PARITY UNPINNED, lsml_oracle.c header)
+  skimage find_contours     -> not used: BoundarySize / IsoperimetricRatio are left out of the
+                               reference-generated feature fixtures
+
+The GPU box has no /root/reference: tests read these files instead.
+"""
+import os
+import pickle
+import sys
+import types
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    warnings.simplefilter("ignore")
+    from oracle import oracle as O
+    from oracle.ref_shim import import_reference
+    O.build()
+    lsml = import_reference(skfmm_distance=O.skfmm_distance)
+    from lsml.gradient import masked_gradient as mg
+    from lsml.feature import (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                              InteriorImageVariation, Size, Moments, DistanceToCenterOfMass)
+    from lsml.feature.feature_map import FeatureMap
+    from lsml.initializer import BallInitializer, RandomBallInitializer
+    from lsml.util.distance_transform import distance_transform as ref_dt
+    from lsml.data.dim2 import hamburger
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---------------------------------------------------------------- a1 / a2: C kernels
+    rs = np.random.RandomState(1234)
+    g = {}
+    for ndim in (1, 2, 3):
+        dims = rs.randint(12, 28, size=ndim)
+        arr, nu = rs.randn(*dims), rs.randn(*dims)
+        mask = rs.rand(*dims) > 0.4
+        dx = rs.rand(ndim) + 0.5
+        g["arr%d" % ndim], g["nu%d" % ndim], g["mask%d" % ndim], g["dx%d" % ndim] = arr, nu, mask, dx
+        g["gmag_os%d" % ndim] = mg.gradient_magnitude_osher_sethian(arr, nu, mask, dx)
+        g["gmag_os_full%d" % ndim] = mg.gradient_magnitude_osher_sethian(arr, nu)
+        for norm in (0, 1):
+            grads, gm = mg.gradient_centered(arr, mask, dx, normalize=bool(norm))
+            g["gc%d_n%d_grads" % (ndim, norm)] = np.stack(grads)
+            g["gc%d_n%d_gmag" % (ndim, norm)] = gm
+    np.savez_compressed(os.path.join(OUT, "masked_gradient.npz"),
+                        notes="reference C (masked_gradient.c) via its own ctypes wrapper", **g)
+
+    # ---------------------------------------------------------------- images: reference generator
+    imgs, segs = hamburger.make_dataset(N=6, n=51, random_state=np.random.RandomState(1234))
+    imgs, segs = np.asarray(imgs, dtype=float), np.asarray(segs, dtype=bool)
+
+    # ---------------------------------------------------------------- a4-a10: features
+    f = {"imgs": imgs[:3], "segs": segs[:3]}
+    rs = np.random.RandomState(7)
+    feats2 = ([cls(ndim=2, sigma=s) for cls in (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                                                InteriorImageVariation) for s in (0, 2)] +
+              [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
+    fm2 = FeatureMap(feats2)
+    for b, dx in enumerate([np.ones(2), np.ones(2), np.array([0.8, 1.25])]):
+        gg = np.indices((51, 51)).astype(float)
+        u = 11.0 - np.sqrt((gg[0] - 25.2) ** 2 + (gg[1] - 26.1) ** 2) + 0.3 * rs.randn(51, 51)
+        dist, mask = ref_dt(u, band=3, dx=dx)
+        f["u2_%d" % b], f["mask2_%d" % b], f["dx2_%d" % b] = u, mask, dx
+        f["X2_%d" % b] = fm2(u=u, img=imgs[b], dist=dist, mask=mask, dx=dx)[mask]
+    feats3 = ([cls(ndim=3, sigma=s) for cls in (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                                                InteriorImageVariation) for s in (0, 1.5)] +
+              [DistanceToCenterOfMass(ndim=3), Moments(ndim=3, axes=(0, 1, 2), orders=(1, 2)),
+               Size(ndim=3)])
+    fm3 = FeatureMap(feats3)
+    n3 = 24
+    gg = np.indices((n3, n3, n3)).astype(float)
+    r3 = np.sqrt(((gg - 11.6) ** 2).sum(0))
+    img3 = (r3 < 7).astype(float) + 0.2 * rs.randn(n3, n3, n3)
+    u3 = 6.0 - r3 + 0.2 * rs.randn(n3, n3, n3)
+    dx3 = np.array([1.0, 1.0, 1.0])
+    dist3, mask3 = ref_dt(u3, band=3, dx=dx3)
+    f.update(img3=img3, u3=u3, mask3=mask3, dx3=dx3,
+             X3=fm3(u=u3, img=img3, dist=dist3, mask=mask3, dx=dx3)[mask3])
+    f["specs2"] = repr([("image_sample", 0), ("image_sample", 2), ("image_edge", 0),
+                        ("image_edge", 2), ("band_mean", 0), ("band_mean", 2), ("band_std", 0),
+                        ("band_std", 2), ("dist_to_com",), ("moments", (0, 1), (1, 2)), ("size",)])
+    f["specs3"] = repr([("image_sample", 0), ("image_sample", 1.5), ("image_edge", 0),
+                        ("image_edge", 1.5), ("band_mean", 0), ("band_mean", 1.5),
+                        ("band_std", 0), ("band_std", 1.5), ("dist_to_com",),
+                        ("moments", (0, 1, 2), (1, 2)), ("size",)])
+    np.savez_compressed(os.path.join(OUT, "features.npz"),
+                        notes="reference FeatureMap / feature classes; band masks from the "
+                              "reference distance_transform wrapper with skfmm plugged by the "
+                              "oracle (parity unpinned for the mask only; features pinned)", **f)
+
+    # ---------------------------------------------------------------- initializers
+    ini = {}
+    u0, d0, m0 = BallInitializer(radius=10)(imgs[0], band=3, dx=np.ones(2))
+    ini.update(ball_u0=u0, ball_mask=m0)
+    u0, d0, m0 = BallInitializer(radius=4, location=[10, 12, 9])(
+        np.zeros((20, 22, 18)), band=2, dx=np.array([1.0, 0.8, 1.2]))
+    ini.update(ball3_u0=u0, ball3_mask=m0)
+    img_ = (imgs[1] - imgs[1].mean()) / imgs[1].std()
+    rb = RandomBallInitializer(random_state=np.random.RandomState(99))
+    u0, d0, m0 = rb(img_, band=3, dx=np.ones(2))
+    ini.update(rand_img=img_, rand_u0=u0, rand_mask=m0)
+    np.savez_compressed(os.path.join(OUT, "initializers.npz"),
+                        notes="reference BallInitializer / RandomBallInitializer through "
+                              "InitializerBase.__call__ (u0 pinned; band mask via plugged skfmm)",
+                        **ini)
+
+    # ---------------------------------------------------------------- a15: the segment loop
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.linear_model import LinearRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    sys.path.insert(0, ROOT)
+    from lsml_b200.core.regressors import pack_trees
+
+    seg_fix = {}
+    band, step, n_iters = 3, 0.3, 6
+    dx = np.ones(2)
+    for kind in ("linear", "forest"):
+        model = lsml.LevelSetMachineLearning(features=feats2, initializer=BallInitializer(radius=10),
+                                             band=band)
+        # train with the reference's own step (features -> fit -> update), no HDF5 bookkeeping
+        img, seg = imgs[4], segs[4]
+        img_ = (img - img.mean()) / img.std()
+        gt = O.skfmm_distance(2 * seg.astype(float) - 1, dx=1.0)
+        u, dist, mask = model.initializer(img_, band, dx=dx)
+        regs = []
+        rs2 = np.random.RandomState(5)
+        for it in range(n_iters):
+            X = model.feature_map(u=u, img=img_, dist=dist, mask=mask, dx=dx)[mask]
+            if kind == "linear":
+                reg = Pipeline([("s", StandardScaler()), ("r", LinearRegression())])
+            else:
+                reg = Pipeline([("s", StandardScaler()),
+                                ("r", RandomForestRegressor(n_estimators=30, max_samples=200,
+                                                            random_state=rs2))])
+            reg.fit(X, np.asarray(gt)[mask])
+            regs.append(reg)
+            vel = np.zeros_like(u)
+            vel[mask] = reg.predict(X)
+            gm = mg.gradient_magnitude_osher_sethian(u, vel, mask, dx)
+            u = u.copy()
+            u[mask] += step * vel[mask] * gm[mask]
+            dist, mask = ref_dt(u, band=band, dx=dx)
+        model._is_fitted = True
+        model.fit_job_handler = types.SimpleNamespace(
+            step=step, iteration=n_iters,
+            _load_regression_model=lambda iteration, regs=regs: regs[iteration - 1])
+        us = model.segment(img, dx=dx, verbose=False, iterate_until_validation_max=False)
+        seg_fix["%s_img" % kind] = img
+        seg_fix["%s_seg" % kind] = seg
+        seg_fix["%s_us" % kind] = us
+        for i, reg in enumerate(regs):
+            sc = reg.steps[0][1]
+            seg_fix["%s_mean_%d" % (kind, i)] = sc.mean_
+            seg_fix["%s_scale_%d" % (kind, i)] = sc.scale_
+            fin = reg.steps[1][1]
+            if kind == "linear":
+                seg_fix["linear_coef_%d" % i] = fin.coef_
+                seg_fix["linear_intercept_%d" % i] = np.asarray(fin.intercept_)
+            else:
+                nodes, bases, root = pack_trees([e.tree_ for e in fin.estimators_], X.shape[1])
+                seg_fix["forest_nodes_%d" % i] = nodes
+                seg_fix["forest_bases_%d" % i] = bases
+                seg_fix["forest_root_%d" % i] = root
+    seg_fix.update(band=band, step=step, n_iters=n_iters)
+    np.savez_compressed(os.path.join(OUT, "segment.npz"),
+                        notes="iterates `us` returned by the reference's own "
+                              "LevelSetMachineLearning.segment (model.py:283-411) with skfmm "
+                              "plugged by the oracle; regressors stored as exported parameters",
+                        **seg_fix)
+    for name in sorted(os.listdir(OUT)):
+        print(name, os.path.getsize(os.path.join(OUT, name)))
+
+
+if __name__ == "__main__":
+    main()

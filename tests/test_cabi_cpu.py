@@ -1,0 +1,131 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/lsml_b200.h declares
+(no compute call is made -- there is no GPU here), and the product fails loudly without one."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lsml_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+    skip = {"defined", "C"}
+    return sorted({n for n in names if n not in skip and (n.startswith("lsml_") or
+                                                        n.startswith("gmag_os") or
+                                                        n.startswith("gradient_centered"))})
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as entry
+    entry.build()
+    lib = ctypes.CDLL(os.path.join(ROOT, "lsml_b200", "liblsml_b200.so"))
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for dropin in ("gmag_os1d", "gmag_os2d", "gmag_os3d", "gradient_centered1d",
+                   "gradient_centered2d", "gradient_centered3d"):
+        assert dropin in syms
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.lsml_version() >= 100
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lsml_b200 import _lib
+    from lsml_b200.gradient import masked_gradient as mg
+    with pytest.raises(_lib.LsmlError):
+        mg.gradient_magnitude_osher_sethian(np.zeros((4, 4)), np.zeros((4, 4)))
+    from lsml_b200.core.engine import BandEngine
+    with pytest.raises(_lib.LsmlError):
+        BandEngine((8, 8), 1)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "lsml_b200")):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text, name
+                assert "liblsml_oracle" not in text, name
+
+
+def test_reference_validation_errors_of_masked_gradient():
+    from lsml_b200.gradient import masked_gradient as mg
+    with pytest.raises(AssertionError):
+        mg.gradient_centered(np.zeros((2, 2, 2, 2)))
+    with pytest.raises(ValueError):
+        mg.gradient_centered(np.zeros((4, 4), dtype=np.float32))
+    with pytest.raises(ValueError):
+        mg.gradient_magnitude_osher_sethian(np.zeros((4, 4)), np.zeros((4, 4)), dx=[1.0])
+    with pytest.raises(ValueError):
+        mg.gradient_magnitude_osher_sethian(np.zeros((4, 4)), np.zeros((4, 4)),
+                                            mask=np.ones(4, dtype=bool))
+
+
+def test_gaussian_weights_identical_to_scipy():
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    from lsml_b200.core.engine import gaussian_kernel1d, gaussian_weights
+    for sigma in (0.5, 1.0, 2.0, 2.0 / 0.7, 3.0, 7.5):
+        for order in (0, 1, 2):
+            lw = int(4.0 * sigma + 0.5)
+            assert np.array_equal(gaussian_kernel1d(sigma, order, lw),
+                                  _gaussian_kernel1d(sigma, order, lw))
+        w, r = gaussian_weights(sigma, 1)
+        assert len(w) == 2 * r + 1
+
+
+def test_feature_program_and_api_surface():
+    from lsml_b200.core.engine import FeatureProgram
+    from lsml_b200.feature import (BoundarySize, COMRaySample, FeatureMap, Moments,
+                                   get_basic_image_features, get_basic_shape_features)
+    feats = get_basic_image_features() + get_basic_shape_features()
+    fm = FeatureMap(feats)
+    assert fm.n_features == 16 and fm.feature_slices[11] == slice(11, 15)
+    assert [f.name for f in feats][:2] == ["Image sample (σ = 0.000)", "Image sample (σ = 2.000)"]
+    prog = FeatureProgram(fm.specs(), 2)
+    assert prog.nfeat == 16 and len(prog.planes) == 4 and prog.needs_boundary
+    with pytest.raises(NotImplementedError):
+        FeatureProgram([BoundarySize(3).spec()], 3)          # Lewiner MC area not implemented
+    with pytest.raises(NotImplementedError):
+        FeatureProgram([Moments(2, orders=(3,)).spec()], 2)
+    with pytest.raises(NotImplementedError):
+        COMRaySample(2).spec()
+    with pytest.raises(ValueError):
+        Moments(2, axes=(2,))
+    with pytest.raises(ValueError):
+        BoundarySize(1)
+
+
+def test_pack_trees_round_trip():
+    """The 8-byte node packing reproduces sklearn's predictions (numpy traversal)."""
+    from sklearn.ensemble import RandomForestRegressor
+    from lsml_b200.core.regressors import pack_trees
+    rs = np.random.RandomState(0)
+    X = rs.randn(500, 6)
+    y = X[:, 0] * 2 + np.sin(X[:, 1]) + 0.1 * rs.randn(500)
+    rf = RandomForestRegressor(n_estimators=8, max_depth=7, random_state=0).fit(X, y)
+    nodes, bases, root = pack_trees([e.tree_ for e in rf.estimators_], 6)
+    Xt = rs.randn(200, 6)
+    Xt[:50] = X[:50]
+    X32 = Xt.astype(np.float32)
+    acc = np.zeros(200)
+    for t in range(len(bases)):
+        tree = nodes[bases[t]:]
+        for i in range(200):
+            idx, leaf = 0, bool(root[t])
+            while not leaf:
+                thr = tree[idx, 0:1].view(np.float32)[0]
+                meta = int(tree[idx, 1])
+                right = not (X32[i, meta >> 24] <= thr)
+                leaf = bool((meta >> 22) & 1) if right else bool((meta >> 23) & 1)
+                idx = (meta & 0x3fffff) + int(right)
+            acc[i] += tree[idx].view(np.float64)[0]
+    assert np.array_equal(acc / len(bases), rf.predict(Xt))
