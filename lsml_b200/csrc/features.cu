@@ -36,14 +36,15 @@ __global__ void __launch_bounds__(256)
 gauss1d_kernel(const double* __restrict__ in, double* __restrict__ out,
                const double* __restrict__ w /* centre at w[r] */, int r, int antisym,
                int n0, int n1, int n2, int axis, i64 rows, int mode) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
-    if (k >= n2 || row >= rows) return;
-    const i64 l = row * n2 + k;
+    // blockIdx.x = item*n0 + i, blockIdx.y = j tile, blockIdx.z = k tile (no per-thread division)
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= n2 || j >= n1) return;
+    const i64 l = ((i64)blockIdx.x * n1 + j) * n2 + k;
     int c, n; i64 st;
     if (axis == 2) { c = k; n = n2; st = 1; }
-    else if (axis == 1) { c = (int)(row % n1); n = n1; st = n2; }
-    else { c = (int)((row / n1) % n0); n = n0; st = (i64)n1 * n2; }
+    else if (axis == 1) { c = j; n = n1; st = n2; }
+    else { c = (int)(blockIdx.x % (unsigned)n0); n = n0; st = (i64)n1 * n2; }
     const double* base = in + (l - (i64)c * st);
     double tmp = __ldg(base + (i64)c * st) * __ldg(w + r);
     const bool interior = (c - r >= 0) && (c + r < n);
@@ -74,17 +75,17 @@ template <int NDIM>
 __global__ void __launch_bounds__(256)
 np_gradient_mag_kernel(const double* __restrict__ A, double* __restrict__ out, int n0, int n1,
                        int n2, i64 rows, double dx0, double dx1, double dx2) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
-    if (k >= n2 || row >= rows) return;
-    const i64 l = row * n2 + k;
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= n2 || j >= n1) return;
+    const i64 l = ((i64)blockIdx.x * n1 + j) * n2 + k;
     double acc = 0.0;   // reduce(lambda a, b: a + b**2, gradients, zeros) ** 0.5  (image.py:59-61)
     if (NDIM >= 3) {
-        const double g = np_grad_axis(A, l, (i64)n1 * n2, (int)((row / n1) % n0), n0, dx0);
+        const double g = np_grad_axis(A, l, (i64)n1 * n2, (int)(blockIdx.x % (unsigned)n0), n0, dx0);
         acc = acc + g * g;
     }
     if (NDIM >= 2) {
-        const double g = np_grad_axis(A, l, (i64)n2, (int)(row % n1), n1, dx1);
+        const double g = np_grad_axis(A, l, (i64)n2, j, n1, dx1);
         acc = acc + g * g;
     }
     const double g = np_grad_axis(A, l, (i64)1, k, n2, dx2);
@@ -408,10 +409,12 @@ assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
 static void rows_launch(const Geom& g, dim3& grid, dim3& block, i64& rows) {
     int bx = 32;
     while (bx < 256 && bx < g.n[2]) bx <<= 1;
-    const int by = 256 / bx;
+    int by = 256 / bx;
+    if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
     rows = g.batch * g.n[0] * g.n[1];
     block = dim3(bx, by, 1);
-    grid = dim3((unsigned)((rows + by - 1) / by), (unsigned)((g.n[2] + bx - 1) / bx), 1);
+    grid = dim3((unsigned)(g.batch * g.n[0]), (unsigned)((g.n[1] + by - 1) / by),
+                (unsigned)((g.n[2] + bx - 1) / bx));
 }
 
 int gauss1d(const Geom& g, const double* in, double* out, const double* w, int radius,

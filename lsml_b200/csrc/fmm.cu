@@ -105,22 +105,20 @@ __global__ void __launch_bounds__(256)
 fmm_init_kernel(const double* __restrict__ u, double* __restrict__ T, u8* __restrict__ mask,
                 i64* __restrict__ list, FmmGeom g, const u64* __restrict__ stats,
                 FmmCounters* ctr) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
-    const i64 rows = g.batch * g.n0 * g.n1;
-    if (k >= g.n2 || row >= rows) return;
-    const i64 rows_per_item = (i64)g.n0 * g.n1;
-    const i64 item = row / rows_per_item;
+    // blockIdx.x = item*n0 + i, blockIdx.y = j tile, blockIdx.z = k tile (no per-thread division)
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int cj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= g.n2 || cj >= g.n1) return;
+    const i64 item = blockIdx.x / (unsigned)g.n0;
+    const int ci = (int)(blockIdx.x % (unsigned)g.n0);
     const u64 npos = stats[item * 8 + 0], nzero = stats[item * 8 + 7];
     if (nzero != (u64)g.voxels && (npos == 0 || npos == (u64)g.voxels)) return;
-    const i64 l = row * g.n2 + k;
+    const i64 l = ((i64)blockIdx.x * g.n1 + cj) * g.n2 + k;
     const double c = __ldg(u + l);
     double d;
     if (c == 0.0) {
         d = 0.0;
     } else {
-        const i64 r = row - item * rows_per_item;
-        const int cj = (int)(r % g.n1), ci = (int)(r / g.n1);
         const int coord[3] = {ci, cj, k};
         const int ext[3] = {g.n0, g.n1, g.n2};
         const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
@@ -546,9 +544,10 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
 
     int bx = 32;
     while (bx < 256 && bx < g.n[2]) bx <<= 1;
-    const int by = 256 / bx;
-    const i64 rows = g.batch * g.n[0] * g.n[1];
-    const dim3 block(bx, by), grid((unsigned)((rows + by - 1) / by), (unsigned)((g.n[2] + bx - 1) / bx));
+    int by = 256 / bx;
+    if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
+    const dim3 block(bx, by), grid((unsigned)(g.batch * g.n[0]), (unsigned)((g.n[1] + by - 1) / by),
+                                   (unsigned)((g.n[2] + bx - 1) / bx));
     int st = 0;
     if (g.ndim == 3) {
         fmm_init_kernel<3><<<grid, block, 0, s>>>(u, T, mask, list, fg, stats, ctr);

@@ -47,23 +47,24 @@ template <typename T, int NDIM>
 __global__ void __launch_bounds__(256)
 gmag_os_kernel(const T* __restrict__ A, const u8* __restrict__ mask, const T* __restrict__ nu,
                T* __restrict__ out, StencilParams p) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
-    if (k >= p.n2 || row >= p.rows) return;
-    const i64 l = row * p.n2 + k;
+    // blockIdx.x = item*n0 + i (one plane per CTA row), blockIdx.y = j tile, blockIdx.z = k tile:
+    // no per-thread integer division (64-bit div/mod cost ~200 instructions per voxel before)
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= p.n2 || j >= p.n1) return;
+    const int i = (int)(blockIdx.x % (unsigned)p.n0);
+    const i64 l = ((i64)blockIdx.x * p.n1 + j) * p.n2 + k;
     if (mask != nullptr && !mask[l]) return;
     const T c = __ldg(A + l);
     const bool neg = __ldg(nu + l) < T(0);
     T acc = T(0), f, b;
     bool first = true;
     if (NDIM >= 3) {
-        const int i = (int)((row / p.n1) % p.n0);
         fwd_bwd(A, l, p.st0, i, p.n0, c, f, b);
         f = div_dx(f, (T)p.dx0, (T)p.r0); b = div_dx(b, (T)p.dx0, (T)p.r0);
         acc = os_terms(b, f, neg, acc, first); first = false;
     }
     if (NDIM >= 2) {
-        const int j = (int)(row % p.n1);
         fwd_bwd(A, l, p.st1, j, p.n1, c, f, b);
         f = div_dx(f, (T)p.dx1, (T)p.r1); b = div_dx(b, (T)p.dx1, (T)p.r1);
         acc = os_terms(b, f, neg, acc, first); first = false;
@@ -89,19 +90,20 @@ __global__ void __launch_bounds__(256)
 gradient_centered_kernel(const T* __restrict__ A, const u8* __restrict__ mask,
                          T* __restrict__ grads, T* __restrict__ gmag, StencilParams p,
                          i64 plane, int normalize) {
-    const int k = blockIdx.y * blockDim.x + threadIdx.x;
-    const i64 row = (i64)blockIdx.x * blockDim.y + threadIdx.y;
-    if (k >= p.n2 || row >= p.rows) return;
-    const i64 l = row * p.n2 + k;
+    // blockIdx.x = item*n0 + i (one plane per CTA row), blockIdx.y = j tile, blockIdx.z = k tile:
+    // no per-thread integer division (64-bit div/mod cost ~200 instructions per voxel before)
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= p.n2 || j >= p.n1) return;
+    const int i = (int)(blockIdx.x % (unsigned)p.n0);
+    const i64 l = ((i64)blockIdx.x * p.n1 + j) * p.n2 + k;
     if (mask != nullptr && !mask[l]) return;
     const T c = __ldg(A + l);
     T d0 = T(0), d1 = T(0), d2;
     if (NDIM >= 3) {
-        const int i = (int)((row / p.n1) % p.n0);
         d0 = div_dx(centered(A, l, p.st0, i, p.n0, c), (T)p.dx0, (T)p.r0);
     }
     if (NDIM >= 2) {
-        const int j = (int)(row % p.n1);
         d1 = div_dx(centered(A, l, p.st1, j, p.n1, c), (T)p.dx1, (T)p.r1);
     }
     d2 = div_dx(centered(A, l, (i64)1, k, p.n2, c), (T)p.dx2, (T)p.r2);
@@ -125,8 +127,10 @@ static void launch_shape(const Geom& g, dim3& grid, dim3& block, StencilParams& 
     p.rows = g.batch * g.n[0] * g.n[1];
     p.dx0 = g.dx[0]; p.dx1 = g.dx[1]; p.dx2 = g.dx[2];
     p.r0 = g.rdx[0]; p.r1 = g.rdx[1]; p.r2 = g.rdx[2];
+    if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
     block = dim3(bx, by, 1);
-    grid = dim3((unsigned)((p.rows + by - 1) / by), (unsigned)((g.n[2] + bx - 1) / bx), 1);
+    grid = dim3((unsigned)(g.batch * g.n[0]), (unsigned)((g.n[1] + by - 1) / by),
+                (unsigned)((g.n[2] + bx - 1) / bx));
 }
 
 template <typename T>
