@@ -1,22 +1,37 @@
-import sys, time, numpy as np, torch
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
-import bench
+"""Times the band rebuild (fast marching) and the other per-iteration phases on an evolving
+volume.  Usage: python tools/fmm_probe.py [n] [iters]"""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sklearn.linear_model import LinearRegression
 from lsml_b200.core.engine import BandEngine
-from lsml_b200.core.model import _ball_u0
+from lsml_b200.core.regressors import export_regressor
+import bench
+
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+dev = torch.device("cuda")
 img, radius, c = bench.make_volume(n, 1234)
-eng = BandEngine((n,n,n), 1, dx=np.ones(3), band=3.0, specs=bench.SPECS)
-eng.load_images(img[None])
-u0 = _ball_u0(eng, 0.5*np.array([[n,n,n]], dtype=float), [40.0*n/256]).clone()
-eng.set_level_sets(u0)
-print('init band', eng.n_band, eng.fmm_counters())
-# perturb u on the band like an evolution step and time rebuilds
-g = torch.Generator(device='cuda').manual_seed(0)
-for it in range(5):
-    idx = eng.band_idx[:eng.n_band]
-    eng.u.view(-1)[idx] += 0.3*torch.randn(idx.numel(), device='cuda', dtype=torch.float64, generator=g)
-    eng._global_stats()
-    torch.cuda.synchronize(); t=time.perf_counter()
-    eng._rebuild_band()
-    torch.cuda.synchronize(); dt=time.perf_counter()-t
-    print(it, 'band', eng.n_band, 'rebuild+compact %.3f ms' % (dt*1e3), eng.fmm_counters())
+specs = [("image_sample", 2.0)]
+eng = BandEngine((n, n, n), 1, dx=np.ones(3), band=3.0, specs=specs, device=dev)
+eng.load_images(img[None], normalize=True)
+from lsml_b200.core.model import _ball_u0
+u0 = _ball_u0(eng, 0.5 * np.array([[n, n, n]], dtype=np.float64), [40.0 * n / 256]).clone()
+reg = LinearRegression().fit(np.array([[0.0], [1.0]]), np.array([0.0, 1.0]))   # v = smoothed image
+dreg = export_regressor(reg, dev)
+
+def timed(fn):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record(); fn(); b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3
+
+for rep in range(2):
+    eng.set_level_sets(u0)
+    for it in range(iters):
+        nb = eng.n_band
+        t_step = timed(lambda: eng.step(dreg, 0.35, rebuild=False))
+        t_fmm = timed(lambda: eng._rebuild_band())
+        ctr = eng.fmm_counters()
+        if rep == 1:
+            print("it %2d band %7d  step(no rebuild) %8.1f us  rebuild+compact %8.1f us  init %d cand %d sweeps %d conv %s"
+                  % (it, nb, t_step, t_fmm, ctr["n_init"], ctr["n_cand"], ctr["sweeps"], ctr["converged"]))
