@@ -163,9 +163,20 @@ int lsml_fmm_workspace_init(long long total, void *workspace, void *stream);
 int lsml_fmm_rebuild(int ndim, const int *shape, long long batch, const double *dx,
                      const double *u, double band, const unsigned long long *stats,
                      uint8_t *mask, double *dist_out, void *workspace, void *stream);
+/* Same, for the evolution loop (model.py:394-397): u has changed ONLY on the band of the
+ * previous rebuild (prev_band_idx[0 .. *prev_n_band), device arrays as written by
+ * lsml_compact_mask), so the interface is located from that band instead of a dense pass. */
+int lsml_fmm_rebuild_from_band(int ndim, const int *shape, long long batch, const double *dx,
+                               const double *u, double band, const unsigned long long *stats,
+                               uint8_t *mask, double *dist_out, void *workspace,
+                               const long long *prev_band_idx, const long long *prev_n_band,
+                               void *stream);
 /* synchronous: copies the 8 int64 counters of the last rebuild to HOST out
- * {n_init, n_cand, changed, sweeps, converged, prev_init, prev_cand, -} */
+ * {n_init, n_cand, single-CTA sweeps, sweeps, converged, prev_init, prev_cand, replays} */
 int lsml_fmm_counters(long long total, void *workspace, long long *out, void *stream);
+/* diagnostics: work-set size of the first 32 grid-wide sweeps of the last rebuild, followed by
+ * their start times in ns (HOST out[64]) */
+int lsml_fmm_sweep_sizes(long long total, void *workspace, long long *out, void *stream);
 
 /* ---- either side of the path -------------------------------------------------- */
 /* u0 = 2*ball - 1 with ball = (radius - |idx*dx - location*dx|) > 0

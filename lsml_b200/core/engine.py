@@ -181,6 +181,7 @@ class BandEngine:
         self.band_voxel_iterations = 0
         self.history = None           # list of (band_idx, new_u) per iteration when recording
         self.last_fmm_counters = None
+        self._band_is_rebuilt = False
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -282,6 +283,7 @@ class BandEngine:
                 m = mask if torch.is_tensor(mask) else torch.from_numpy(np.ascontiguousarray(mask))
                 self.mask.copy_(m.to(self.device).reshape(self.mask.shape).to(torch.uint8))
                 self._ws_fmm = None   # the marcher's sparse state no longer matches `mask`
+                self._band_is_rebuilt = False
                 self._compact()
 
     def _global_stats(self):
@@ -289,25 +291,39 @@ class BandEngine:
             ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(self.u),
             _lib.ptr(self.stats), self._stream()), "global_stats")
 
-    def _rebuild_band(self, dist_out=None):
+    def _rebuild_band(self, dist_out=None, from_band=False):
+        """distance_transform(u, band, dx) -> mask, band_idx.  ``from_band``: u has changed only
+        on the current band since the rebuild that produced it (the evolution loop), so the
+        interface is located from that band instead of a dense pass over u."""
+        from_band = from_band and self._band_is_rebuilt and self._ws_fmm is not None
         if self._ws_fmm is None:
             nbytes = int(_lib.lib.lsml_fmm_workspace_bytes(_lib.c_i64(self.total)))
             self._ws_fmm = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self.mask.zero_()
             _lib.check(_lib.lib.lsml_fmm_workspace_init(
                 _lib.c_i64(self.total), _lib.ptr(self._ws_fmm), self._stream()), "fmm_init")
-        _lib.check(_lib.lib.lsml_fmm_rebuild(
+        _lib.check(_lib.lib.lsml_fmm_rebuild_from_band(
             ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
             _lib.ptr(self.u), ctypes.c_double(self.band), _lib.ptr(self.stats),
-            _lib.ptr(self.mask), _lib.ptr(dist_out), _lib.ptr(self._ws_fmm), self._stream()),
+            _lib.ptr(self.mask), _lib.ptr(dist_out), _lib.ptr(self._ws_fmm),
+            _lib.ptr(self.band_idx if from_band else None),
+            _lib.ptr(self.n_band_dev if from_band else None), self._stream()),
             "fmm_rebuild")
         self._compact()
+        self._band_is_rebuilt = True
 
     def fmm_counters(self):
         out = (ctypes.c_longlong * 8)()
         _lib.check(_lib.lib.lsml_fmm_counters(_lib.c_i64(self.total), _lib.ptr(self._ws_fmm), out,
                                               self._stream()), "fmm_counters")
-        return dict(n_init=out[0], n_cand=out[1], sweeps=out[3], converged=bool(out[4]))
+        return dict(n_init=out[0], n_cand=out[1], tail_sweeps=out[2], sweeps=out[3],
+                    converged=bool(out[4]), replays=out[7])
+
+    def fmm_sweep_sizes(self):
+        out = (ctypes.c_longlong * 64)()
+        _lib.check(_lib.lib.lsml_fmm_sweep_sizes(_lib.c_i64(self.total), _lib.ptr(self._ws_fmm),
+                                                 out, self._stream()), "fmm_sweep_sizes")
+        return list(out)
 
     def distance(self):
         """The reference's ``dist`` (signed distance inside the band, 0 elsewhere)."""
@@ -388,5 +404,7 @@ class BandEngine:
             self.band_voxel_iterations += nb
             self._global_stats()
             if rebuild:
-                self._rebuild_band()
+                self._rebuild_band(from_band=True)
+            else:
+                self._band_is_rebuilt = False     # u moved on; the band no longer brackets it
             return nb

@@ -295,12 +295,31 @@ int lsml_fmm_rebuild(int ndim, const int* shape, long long batch, const double* 
                      const double* u, double band, const unsigned long long* stats,
                      uint8_t* mask, double* dist_out, void* workspace, void* stream) {
     GEOM(g);
-    return fmm_rebuild(g, u, band, stats, mask, dist_out, workspace, (cudaStream_t)stream);
+    return fmm_rebuild(g, u, band, stats, mask, dist_out, workspace, nullptr, nullptr,
+                       (cudaStream_t)stream);
+}
+int lsml_fmm_rebuild_from_band(int ndim, const int* shape, long long batch, const double* dx,
+                               const double* u, double band, const unsigned long long* stats,
+                               uint8_t* mask, double* dist_out, void* workspace,
+                               const long long* prev_band_idx, const long long* prev_n_band,
+                               void* stream) {
+    GEOM(g);
+    return fmm_rebuild(g, u, band, stats, mask, dist_out, workspace, prev_band_idx, prev_n_band,
+                       (cudaStream_t)stream);
 }
 int lsml_fmm_counters(long long total, void* workspace, long long* out, void* stream) {
     const i64* dev = nullptr;
     fmm_counters_ptr(total, workspace, &dev);
     LSML_CUDA(cudaMemcpyAsync(out, dev, 8 * sizeof(i64), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LSML_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int lsml_fmm_sweep_sizes(long long total, void* workspace, long long* out, void* stream) {
+    const i64* dev = nullptr;
+    fmm_counters_ptr(total, workspace, &dev);
+    LSML_CUDA(cudaMemcpyAsync(out, reinterpret_cast<const char*>(dev) + fmm_counters_sizes_offset(),
+                              64 * sizeof(i64), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     LSML_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }

@@ -36,6 +36,7 @@
 // 2 candidate during the march; 0/1 = the reference's `mask` afterwards.
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstddef>
 #include "lsml_internal.h"
 
 namespace cg = cooperative_groups;
@@ -47,17 +48,38 @@ struct FmmGeom {
     i64 voxels, batch;
     double dx[3];     // padded
     double idx2[3];   // 1/dx/dx
+    // list entries are "packed coordinates" (item, i, j, k) in bit fields: k at bit 0, j at sh1,
+    // i at sh0, item at shb -- decoding is shifts and masks, never a 64-bit division
+    int sh1, sh0, shb;
 };
 
-struct FmmCounters {      // device-resident, 8 x i64
+static int bits_for(i64 n) { int b = 0; while (((i64)1 << b) < n) ++b; return b; }
+
+static int make_fmm_geom(const Geom& g, FmmGeom& fg) {
+    fg.n0 = g.n[0]; fg.n1 = g.n[1]; fg.n2 = g.n[2]; fg.voxels = g.voxels; fg.batch = g.batch;
+    for (int a = 0; a < 3; ++a) { fg.dx[a] = g.dx[a]; fg.idx2[a] = 1.0 / g.dx[a] / g.dx[a]; }
+    fg.sh1 = bits_for(g.n[2]);
+    fg.sh0 = fg.sh1 + bits_for(g.n[1]);
+    fg.shb = fg.sh0 + bits_for(g.n[0]);
+    if (fg.shb + bits_for(g.batch) > 62) { set_error("grid too large for packed band entries"); return 1; }
+    return 0;
+}
+
+struct FmmCounters {      // device-resident
     i64 n_init;           // initial frozen voxels: list[0 .. n_init)
     i64 n_cand;           // candidates: list[cap-1 .. cap-n_cand] (growing downwards)
-    i64 changed;          // per-sweep change flag
+    i64 tail_sweeps;      // sweeps of the last march that ran on one CTA (diagnostic)
     i64 sweeps;           // sweeps executed by the last march
     i64 converged;        // 1 when the last march reached its fixed point
     i64 prev_init, prev_cand;   // extents to clear at the next rebuild
-    i64 pad;
-    i64 flags[4];         // rotating per-sweep "changed" flags of the march kernel
+    i64 replays;          // replay evaluations of the last march (diagnostic)
+    // ---- work ring: packed entries of the candidates that became dirty, in push order
+    i64 tail;             // next free ring position (monotonic; slot = position % ring_cap)
+    i64 pub_begin, pub_end;     // window published by CTA 0 after a run of single-CTA sweeps
+    i64 pub_sweep;              // ... and the sweep number reached
+    i64 overflow[3];      // rotating "a push was dropped" flags => next sweep scans the list
+    i64 sizes[32];        // dirty-set size of the first 32 sweeps (diagnostic)
+    i64 stamps[32];       // %globaltimer (ns) at the start of those sweeps (diagnostic)
 };
 
 // Ordering decisions are made on |d| rounded to float32 (see oracle/lsml_oracle.c:qmag): values
@@ -67,39 +89,104 @@ __device__ __forceinline__ float qmag(double d) { return __double2float_rn(fabs(
 
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// State byte of a voxel during the march: 0 far, 1 initial frozen, 2 candidate (clean),
-// 6 candidate whose stencil changed since it was last evaluated (dirty).
-constexpr u8 ST_INIT = 1, ST_CAND = 2, ST_DIRTY = 6;
+// State byte of a voxel during the march: 0 far, 1 initial frozen, 2 candidate.
+constexpr u8 ST_INIT = 1, ST_CAND = 2;
 
-// claim voxel g (state 0 -> 6); returns true for the single winner.  The state is one byte of
-// a 32-bit word; atomicOr on the word keeps the other three bytes intact.
-__device__ __forceinline__ bool claim(u8* mask, i64 g) {
+// claim voxel g (state 0 -> `value`); returns true for the single winner.  The state is one
+// byte of a 32-bit word; atomicOr on the word keeps the other three bytes intact.
+__device__ __forceinline__ bool claim(u8* mask, i64 g, unsigned value) {
     unsigned* word = reinterpret_cast<unsigned*>(mask + (g & ~(i64)3));
     const unsigned shift = 8u * (unsigned)(g & 3);
-    const unsigned old = atomicOr(word, (unsigned)ST_DIRTY << shift);
+    const unsigned old = atomicOr(word, value << shift);
     return ((old >> shift) & 0xffu) == 0u;
 }
 
+// Scheduling record of a voxel (8 bytes, next to T):
+//   epoch  the last sweep this voxel was queued for (0 = never); voxel y is in the work set of
+//          sweep s exactly when epoch == s, so queueing is an atomicMax and needs no clearing;
+//   reach  how far y's last replay looked: max(magnitude of the last event it consumed,
+//          magnitude of its result), +inf when it ended without a value.  A stencil voxel whose
+//          old AND new magnitudes are both beyond `reach` was not consumed by that replay and
+//          would not be consumed by a new one (every event before it is unchanged and the
+//          replay stops at it), so its change cannot alter y -- y is not queued for it.
+struct __align__(8) Aux {
+    unsigned epoch;
+    float reach;
+};
+
+__device__ __forceinline__ i64 decode(i64 e, const FmmGeom& g, int coord[3]) {
+    coord[2] = (int)(e & (((i64)1 << g.sh1) - 1));
+    coord[1] = (int)((e >> g.sh1) & (((i64)1 << (g.sh0 - g.sh1)) - 1));
+    coord[0] = (int)((e >> g.sh0) & (((i64)1 << (g.shb - g.sh0)) - 1));
+    const i64 item = e >> g.shb;
+    return ((item * g.n0 + coord[0]) * g.n1 + coord[1]) * g.n2 + coord[2];
+}
+__device__ __forceinline__ i64 encode(i64 item, int i, int j, int k, const FmmGeom& g) {
+    return (item << g.shb) | ((i64)i << g.sh0) | ((i64)j << g.sh1) | (i64)k;
+}
+
 __global__ void __launch_bounds__(256)
-fmm_clear_kernel(double* __restrict__ T, u8* __restrict__ mask, const i64* __restrict__ list,
-                 i64 cap, FmmCounters* ctr) {
+fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__ mask,
+                 const i64* __restrict__ list, i64 cap, FmmGeom g, FmmCounters* ctr) {
     const i64 ni = ctr->prev_init, nc = ctr->prev_cand;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni + nc;
          t += (i64)gridDim.x * blockDim.x) {
-        const i64 g = t < ni ? list[t] : list[cap - 1 - (t - ni)];
-        T[g] = pos_inf();
-        mask[g] = 0;
+        int coord[3];
+        const i64 l = decode(t < ni ? list[t] : list[cap - 1 - (t - ni)], g, coord);
+        T[l] = pos_inf();
+        aux[l] = Aux{0u, __int_as_float(0x7f800000)};
+        mask[l] = 0;
     }
 }
 
 __global__ void fmm_reset_counters_kernel(FmmCounters* ctr) {
-    ctr->n_init = 0; ctr->n_cand = 0; ctr->changed = 0; ctr->sweeps = 0; ctr->converged = 0;
+    ctr->n_init = 0; ctr->n_cand = 0; ctr->tail_sweeps = 0; ctr->sweeps = 0; ctr->converged = 0;
+    ctr->replays = 0; ctr->tail = 0; ctr->pub_begin = 0; ctr->pub_end = 0; ctr->pub_sweep = 0;
+    ctr->overflow[0] = 0; ctr->overflow[1] = 0; ctr->overflow[2] = 0;
 }
 
-// Initial frozen set (orc_fmm_distance "initial frozen set"): zeros, and voxels with an axis
-// neighbour of opposite sign; d = sign / sqrt(sum_a 1/d_a^2), d_a = nearer linear crossing.
+// Initial frozen value of voxel l (orc_fmm_distance "initial frozen set"): zeros, and voxels
+// with an axis neighbour of opposite sign; d = sign / sqrt(sum_a 1/d_a^2), d_a = nearer linear
+// crossing.  Returns false when l is not in the initial frozen set.
+template <int NDIM>
+__device__ __forceinline__ bool init_distance(const double* __restrict__ u, i64 l,
+                                              const int (&coord)[3], const FmmGeom& g, double& d) {
+    const double c = __ldg(u + l);
+    if (c == 0.0) { d = 0.0; return true; }
+    const int ext[3] = {g.n0, g.n1, g.n2};
+    const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    bool borders = false;
+    double dsum = 0.0;
+#pragma unroll
+    for (int ax = 3 - NDIM; ax < 3; ++ax) {
+        double ld = 0.0;
+#pragma unroll
+        for (int j = -1; j < 2; j += 2) {
+            const int cc = coord[ax] + j;
+            if (cc < 0 || cc >= ext[ax]) continue;
+            const double nv = __ldg(u + l + j * st[ax]);
+            if (c * nv < 0) {
+                borders = true;
+                const double dd = g.dx[ax] * c / (c - nv);
+                if (ld == 0 || ld > dd) ld = dd;
+            }
+        }
+        if (ld > 0) dsum += 1 / ld / ld;
+    }
+    if (!borders) return false;
+    d = c < 0 ? -sqrt(1 / dsum) : sqrt(1 / dsum);
+    return true;
+}
+
 // Items that are single-signed (no positive or no non-positive... see distance_transform.py:42)
 // are left untouched => empty mask.  stats[item*8+0] = #(u>0), stats[item*8+7] = #(u==0).
+__device__ __forceinline__ bool item_has_contour(const u64* __restrict__ stats, i64 item,
+                                                 const FmmGeom& g) {
+    const u64 npos = stats[item * 8 + 0], nzero = stats[item * 8 + 7];
+    return nzero == (u64)g.voxels || !(npos == 0 || npos == (u64)g.voxels);
+}
+
+// Dense pass over u (first rebuild of a level set): 8 B/voxel read, HBM-bound.
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 fmm_init_kernel(const double* __restrict__ u, double* __restrict__ T, u8* __restrict__ mask,
@@ -111,60 +198,107 @@ fmm_init_kernel(const double* __restrict__ u, double* __restrict__ T, u8* __rest
     if (k >= g.n2 || cj >= g.n1) return;
     const i64 item = blockIdx.x / (unsigned)g.n0;
     const int ci = (int)(blockIdx.x % (unsigned)g.n0);
-    const u64 npos = stats[item * 8 + 0], nzero = stats[item * 8 + 7];
-    if (nzero != (u64)g.voxels && (npos == 0 || npos == (u64)g.voxels)) return;
+    if (!item_has_contour(stats, item, g)) return;
     const i64 l = ((i64)blockIdx.x * g.n1 + cj) * g.n2 + k;
-    const double c = __ldg(u + l);
+    const int coord[3] = {ci, cj, k};
     double d;
-    if (c == 0.0) {
-        d = 0.0;
-    } else {
-        const int coord[3] = {ci, cj, k};
-        const int ext[3] = {g.n0, g.n1, g.n2};
-        const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
-        bool borders = false;
-        double dsum = 0.0;
+    if (!init_distance<NDIM>(u, l, coord, g, d)) return;
+    T[l] = d;
+    mask[l] = ST_INIT;
+    const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_init), (u64)1);
+    list[pos] = encode(item, ci, cj, k, g);
+}
+
+// Sparse variant for the evolution loop: between two rebuilds u changes only on the previous
+// band, so a voxel can only be in the new initial frozen set if it is in the previous band or
+// is the opposite-signed direct neighbour of a previous-band voxel (a voxel outside the band
+// whose neighbours are all outside the band kept its status, and that status was "not frozen").
+// One thread per previous-band voxel x evaluates x and every direct neighbour of opposite
+// sign; duplicates are resolved by the atomic claim on the state byte.
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+fmm_init_band_kernel(const double* __restrict__ u, double* __restrict__ T, u8* __restrict__ mask,
+                     i64* __restrict__ list, FmmGeom g, const u64* __restrict__ stats,
+                     const i64* __restrict__ band_idx, const i64* __restrict__ n_band,
+                     FmmCounters* ctr) {
+    const i64 nb = *n_band;
+    const int ext[3] = {g.n0, g.n1, g.n2};
+    const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+         b += (i64)gridDim.x * blockDim.x) {
+        const i64 l = __ldg(band_idx + b);
+        const i64 item = l / g.voxels, loc = l - item * g.voxels;
+        if (!item_has_contour(stats, item, g)) continue;
+        int coord[3];
+        coord[2] = (int)(loc % g.n2);
+        const i64 r = loc / g.n2;
+        coord[1] = (int)(r % g.n1);
+        coord[0] = (int)(r / g.n1);
+        const double c = __ldg(u + l);
+        double d;
+        if (init_distance<NDIM>(u, l, coord, g, d) && claim(mask, l, ST_INIT)) {
+            T[l] = d;
+            const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_init), (u64)1);
+            list[pos] = encode(item, coord[0], coord[1], coord[2], g);
+        }
 #pragma unroll
         for (int ax = 3 - NDIM; ax < 3; ++ax) {
-            double ld = 0.0;
 #pragma unroll
             for (int j = -1; j < 2; j += 2) {
                 const int cc = coord[ax] + j;
                 if (cc < 0 || cc >= ext[ax]) continue;
-                const double nv = __ldg(u + l + j * st[ax]);
-                if (c * nv < 0) {
-                    borders = true;
-                    const double dd = g.dx[ax] * c / (c - nv);
-                    if (ld == 0 || ld > dd) ld = dd;
+                const i64 n = l + j * st[ax];
+                if (!(c * __ldg(u + n) < 0)) continue;
+                if (__ldcg(mask + n) != 0) continue;             // already claimed
+                int nc[3] = {coord[0], coord[1], coord[2]};
+                nc[ax] = cc;
+                double dn;
+                if (init_distance<NDIM>(u, n, nc, g, dn) && claim(mask, n, ST_INIT)) {
+                    T[n] = dn;
+                    const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_init), (u64)1);
+                    list[pos] = encode(item, nc[0], nc[1], nc[2], g);
                 }
             }
-            if (ld > 0) dsum += 1 / ld / ld;
         }
-        if (!borders) return;
-        d = c < 0 ? -sqrt(1 / dsum) : sqrt(1 / dsum);
     }
-    T[l] = d;
-    mask[l] = 1;
-    const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_init), (u64)1);
-    list[pos] = l;
 }
 
-// voxel coordinates (padded axes) of flat index l
-__device__ __forceinline__ void coords_of(i64 l, const FmmGeom& g, int coord[3]) {
-    const i64 loc = l % g.voxels;
-    coord[2] = (int)(loc % g.n2);
-    const i64 r = loc / g.n2;
-    coord[1] = (int)(r % g.n1);
-    coord[0] = (int)(r / g.n1);
+// Work ring: position p lives in slot p % ring_cap.  A sweep consumes the window
+// [begin, end) and appends the candidates it dirties behind `end`; an append that would lap the
+// window being consumed is dropped and reported (the next sweep then finds the dirty
+// candidates by scanning the candidate list instead).
+struct Ring {
+    i64* slots;
+    i64 cap;
+};
+
+// everything a thread needs to queue work for the next sweep
+struct Sched {
+    Aux* aux;
+    Ring ring;
+    FmmCounters* ctr;
+    i64 begin;           // start of the ring window being consumed (overflow test)
+    unsigned next;       // epoch of the sweep being filled
+    int ovf_slot;
+};
+
+// queue voxel n (packed entry e) for sweep sc.next unless it already is
+__device__ __forceinline__ void enqueue(const Sched& sc, i64 n, i64 e) {
+    if (atomicMax(&sc.aux[n].epoch, sc.next) >= sc.next) return;
+    const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail), (u64)1);
+    if (pos - sc.begin < sc.ring.cap) sc.ring.slots[pos & (sc.ring.cap - 1)] = e;
+    else *reinterpret_cast<volatile i64*>(&sc.ctr->overflow[sc.ovf_slot]) = 1;
 }
 
+// far direct neighbours of a voxel that is frozen (or whose value entered the band) become
+// candidates and are queued for their first evaluation
 template <int NDIM>
-__device__ __forceinline__ void push_neighbours(i64 l, const FmmGeom& g, double* T, u8* mask,
-                                                i64* list, i64 cap, FmmCounters* ctr) {
-    int coord[3];
-    coords_of(l, g, coord);
+__device__ __forceinline__ void expose_neighbours(i64 e, i64 l, const int (&coord)[3],
+                                                  const FmmGeom& g, u8* mask, i64* list, i64 cap,
+                                                  const Sched& sc) {
     const int ext[3] = {g.n0, g.n1, g.n2};
     const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    const i64 est[3] = {(i64)1 << g.sh0, (i64)1 << g.sh1, 1};
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
 #pragma unroll
@@ -172,9 +306,10 @@ __device__ __forceinline__ void push_neighbours(i64 l, const FmmGeom& g, double*
             const int cc = coord[ax] + j;
             if (cc < 0 || cc >= ext[ax]) continue;
             const i64 n = l + j * st[ax];
-            if (__ldcg(mask + n) == 0 && claim(mask, n)) {
-                const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_cand), (u64)1);
-                list[cap - 1 - pos] = n;
+            if (__ldcg(mask + n) == 0 && claim(mask, n, ST_CAND)) {
+                const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)1);
+                list[cap - 1 - pos] = e + j * est[ax];
+                enqueue(sc, n, e + j * est[ax]);
             }
         }
     }
@@ -182,41 +317,57 @@ __device__ __forceinline__ void push_neighbours(i64 l, const FmmGeom& g, double*
 
 template <int NDIM>
 __global__ void __launch_bounds__(256)
-fmm_seed_kernel(double* T, u8* mask, i64* list, i64 cap, FmmGeom g, FmmCounters* ctr) {
+fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* ctr, Ring ring) {
     const i64 ni = ctr->n_init;
+    const Sched sc{aux, ring, ctr, 0, 1u, 2};
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni;
-         t += (i64)gridDim.x * blockDim.x)
-        push_neighbours<NDIM>(list[t], g, T, mask, list, cap, ctr);
+         t += (i64)gridDim.x * blockDim.x) {
+        int coord[3];
+        const i64 e = list[t];
+        const i64 l = decode(e, g, coord);
+        expose_neighbours<NDIM>(e, l, coord, g, mask, list, cap, sc);
+    }
 }
 
 // ---- the marcher's upwind update on a local stencil ------------------------------------------
-// t1/t2: values one / two cells away, index [ax][dir] with dir 0 = -1, 1 = +1;
-// f1/f2: "frozen now" predicates.  Same expressions, in the same order, as the oracle's
-// fmm_update()/fmm_solve() (oracle/lsml_oracle.c), including the causality rule: a root that is
-// smaller in magnitude than a value it was computed from (or a non-positive discriminant)
-// removes the contributor with the largest magnitude and solves again.
+// Stencil slots are numbered by their RANK in flat-index order around x (rank 6 = x itself):
+//   0: -2 along axis 0   1: -1 axis 0   2: -2 axis 1   3: -1 axis 1   4: -2 axis 2   5: -1 axis 2
+//   7: +1 axis 2   8: +2 axis 2   9: +1 axis 1   10: +2 axis 1   11: +1 axis 0   12: +2 axis 0
+// (whenever two slots both exist their flat indices are ordered like their ranks).  Direct
+// neighbours have odd ranks; the voxel in between a two-away slot r and x is r+1 (r < 6) or r-1.
+__device__ __forceinline__ constexpr int slot_rank(int ax, int d, int which) {
+    return d == 0 ? (2 * ax + (which == 1 ? 1 : 0)) : (7 + 2 * (2 - ax) + (which == 1 ? 0 : 1));
+}
+
+// Per-axis contributors of the upwind update (oracle/lsml_oracle.c:fmm_update): the frozen direct
+// neighbour with the smaller magnitude supplies v1; the voxel two cells away in the same
+// direction supplies v2 when it is frozen and passes scikit-fmm's second-order switch.
+struct AxisState {
+    double v1, v2;
+    float k1, k2;        // float32 ordering magnitudes of v1 / v2
+    bool active, second;
+    int dir;             // direction (0 = -1, 1 = +1) v1 was taken from
+};
+
+// scikit-fmm's switch `(d2 <= v1 && v1 >= 0) || (d2 >= v1 && v1 <= 0)` on rounded magnitudes
+// (oracle/lsml_oracle.c:second_order_ok)
+__device__ __forceinline__ bool second_order_ok(double d2, float q2, double v1, float k1) {
+    return v1 == 0.0 || d2 * v1 < 0 || q2 <= k1;
+}
+
+// The quadratic of oracle/lsml_oracle.c:fmm_solve on the contributors in `ax` -- the same
+// expressions in the same order, including the causality rule: a root that is not larger in
+// magnitude than a value it was computed from (or a non-positive discriminant) removes the
+// contributor with the largest magnitude and solves again.  Returns 0.0 without contributors.
 template <int NDIM>
-__device__ __forceinline__ double stencil_update(const double (&t1)[3][2], const double (&t2)[3][2],
-                                                 const bool (&f1)[3][2], const bool (&f2)[3][2],
-                                                 const FmmGeom& g, double phi) {
+__device__ __forceinline__ double solve_quadratic(const AxisState (&in)[3], const FmmGeom& g,
+                                                  bool phi_pos) {
     const double aa = 9.0 / 4.0, one_third = 1.0 / 3.0;
-    double v1[3], v2[3];
-    bool active[3];
+    bool active[3], second[3];
     int nactive = 0;
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
-        v1[ax] = DBL_MAX; v2[ax] = DBL_MAX;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            if (f1[ax][d] && (v1[ax] == DBL_MAX || qmag(t1[ax][d]) < qmag(v1[ax]))) {
-                v1[ax] = t1[ax][d];
-                v2[ax] = DBL_MAX;
-                if (f2[ax][d] && (v1[ax] == 0.0 || t2[ax][d] * v1[ax] < 0 ||
-                                  qmag(t2[ax][d]) <= qmag(v1[ax])))
-                    v2[ax] = t2[ax][d];
-            }
-        }
-        active[ax] = v1[ax] < DBL_MAX;
+        active[ax] = in[ax].active; second[ax] = in[ax].second;
         nactive += active[ax] ? 1 : 0;
     }
 #pragma unroll 1
@@ -225,28 +376,29 @@ __device__ __forceinline__ double stencil_update(const double (&t1)[3][2], const
 #pragma unroll
         for (int ax = 3 - NDIM; ax < 3; ++ax) {
             if (!active[ax]) continue;
-            if (v2[ax] < DBL_MAX) {
-                const double tp = one_third * (4 * v1[ax] - v2[ax]);
+            if (second[ax]) {
+                const double tp = one_third * (4 * in[ax].v1 - in[ax].v2);
                 a += g.idx2[ax] * aa;
                 b -= g.idx2[ax] * 2 * aa * tp;
                 c += g.idx2[ax] * aa * (tp * tp);
             } else {
                 a += g.idx2[ax];
-                b -= g.idx2[ax] * 2 * v1[ax];
-                c += g.idx2[ax] * (v1[ax] * v1[ax]);
+                b -= g.idx2[ax] * 2 * in[ax].v1;
+                c += g.idx2[ax] * (in[ax].v1 * in[ax].v1);
             }
         }
         c -= 1;
         const double det = b * b - 4 * a * c;
         if (det > 0) {
-            const double r = (phi > DBL_EPSILON) ? (-b + sqrt(det)) / 2.0 / a
-                                                 : (-b - sqrt(det)) / 2.0 / a;
+            const double sq = sqrt(det);
+            const double r = (phi_pos ? (-b + sq) : (-b - sq)) / 2.0 / a;
+            const float qr = qmag(r);
             bool causal = true;
 #pragma unroll
             for (int ax = 3 - NDIM; ax < 3; ++ax) {
                 if (!active[ax]) continue;
-                if (qmag(r) <= qmag(v1[ax])) causal = false;
-                if (v2[ax] < DBL_MAX && qmag(r) <= qmag(v2[ax])) causal = false;
+                if (qr <= in[ax].k1) causal = false;
+                if (second[ax] && qr <= in[ax].k2) causal = false;
             }
             if (causal) return r;
         }
@@ -258,13 +410,13 @@ __device__ __forceinline__ double stencil_update(const double (&t1)[3][2], const
 #pragma unroll
         for (int ax = 3 - NDIM; ax < 3; ++ax) {
             if (!active[ax]) continue;
-            if (v2[ax] < DBL_MAX && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = true; }
-            if (qmag(v1[ax]) > wv) { wv = qmag(v1[ax]); worst = ax; worst_is_v2 = false; }
+            if (second[ax] && in[ax].k2 > wv) { wv = in[ax].k2; worst = ax; worst_is_v2 = true; }
+            if (in[ax].k1 > wv) { wv = in[ax].k1; worst = ax; worst_is_v2 = false; }
         }
 #pragma unroll
         for (int ax = 3 - NDIM; ax < 3; ++ax)
             if (ax == worst) {
-                if (worst_is_v2) v2[ax] = DBL_MAX;
+                if (worst_is_v2) second[ax] = false;
                 else active[ax] = false;
             }
         if (!worst_is_v2) nactive--;
@@ -272,196 +424,400 @@ __device__ __forceinline__ double stencil_update(const double (&t1)[3][2], const
     return 0.0;
 }
 
-__device__ __forceinline__ bool key_less(double ta, i64 ia, double tb, i64 ib) {
-    const float a = qmag(ta), b = qmag(tb);
-    return (a < b) || (a == b && ia < ib);
-}
-
 // V(x): replay of the marcher around x (see the header).  Returns +inf when x never gets a value.
+//
+// The stencil voxels that will be frozen before x ("events") are applied in key order.  The
+// marcher re-evaluates x's update after every one of them from ALL frozen stencil voxels; here
+// the per-axis contributors are maintained incrementally and the quadratic is only solved when
+// an event actually changed them (an unchanged contributor set gives the identical value):
+//   * a direct neighbour freezing on an axis that already has a frozen direct neighbour only
+//     replaces it when fmm_update's own loop would prefer it (possible against an INITIAL frozen
+//     voxel; among marched voxels events arrive in increasing key order and the earlier stays);
+//   * a voxel two cells away matters only if the voxel in between supplies v1 of that axis.
 template <int NDIM>
-__device__ double replay(i64 l, const double* __restrict__ u, const double* T, const u8* mask,
-                         const FmmGeom& g, double band) {
-    int coord[3];
-    coords_of(l, g, coord);
+__device__ double replay(i64 l, const int (&coord)[3], const double* __restrict__ u,
+                         const double* T, const u8* mask, const FmmGeom& g, double band,
+                         float& reach) {
     const int ext[3] = {g.n0, g.n1, g.n2};
     const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
-    double t1[3][2], t2[3][2];
-    bool f1[3][2], f2[3][2];          // frozen now
-    bool e1[3][2], e2[3][2];          // pending event (marched voxel with a value inside the band)
+    double tv[13];                    // by slot rank; dynamically indexed => local memory (L1)
+    float qr[13];                     // the same magnitudes again in registers for the selection
+    unsigned F = 0u;                  // frozen now
+    unsigned E = 0u;                  // pending event (marched voxel with a value inside the band)
     const double inf = pos_inf();
 #pragma unroll
-    for (int ax = 0; ax < 3; ++ax)
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            t1[ax][d] = inf; t2[ax][d] = inf;
-            f1[ax][d] = f2[ax][d] = e1[ax][d] = e2[ax][d] = false;
-        }
-    bool any_direct_frozen = false;
+    for (int r = 0; r < 13; ++r) { tv[r] = inf; qr[r] = 0.f; }
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
             const int j = d ? 1 : -1;
-            const int c1 = coord[ax] + j, c2 = coord[ax] + 2 * j;
-            if (c1 >= 0 && c1 < ext[ax]) {
-                const i64 n = l + j * st[ax];
-                const double t = __ldcg(T + n);       // L2: other CTAs update T concurrently
-                const u8 s = __ldcg(mask + n);
-                t1[ax][d] = t;
-                f1[ax][d] = (s == ST_INIT);
-                e1[ax][d] = (s & ST_CAND) && (fabs(t) <= band);
-                any_direct_frozen |= f1[ax][d];
-            }
-            if (c2 >= 0 && c2 < ext[ax]) {
-                const i64 n = l + 2 * j * st[ax];
-                const double t = __ldcg(T + n);
-                const u8 s = __ldcg(mask + n);
-                t2[ax][d] = t;
-                f2[ax][d] = (s == ST_INIT);
-                e2[ax][d] = (s & ST_CAND) && (fabs(t) <= band);
+#pragma unroll
+            for (int which = 1; which <= 2; ++which) {
+                const int cc = coord[ax] + which * j;
+                if (cc >= 0 && cc < ext[ax]) {
+                    const i64 n = l + which * j * st[ax];
+                    const double t = __ldcg(T + n);   // L2: other CTAs update T concurrently
+                    const u8 s = __ldcg(mask + n);
+                    const int r = slot_rank(ax, d, which);
+                    tv[r] = t; qr[r] = qmag(t);
+                    if (s == ST_INIT) F |= 1u << r;
+                    else if ((s & ST_CAND) && (fabs(t) <= band)) E |= 1u << r;
+                }
             }
         }
     }
-    const double phi = __ldg(u + l);
-    bool narrow = false;
-    double t = inf;
-    if (any_direct_frozen) {
-        const double d0 = stencil_update<NDIM>(t1, t2, f1, f2, g, phi);
-        if (d0 != 0.0) { t = d0; narrow = true; }
-    }
-    // at most 4*NDIM events
-#pragma unroll 1
-    for (int it = 0; it < 4 * NDIM; ++it) {
-        // next event: smallest key among pending stencil voxels
-        int bax = -1, bd = 0, bwhich = 0;
-        double bt = inf; i64 bi = 0;
+    float ql[13];                     // dynamically indexed copy
 #pragma unroll
-        for (int ax = 3 - NDIM; ax < 3; ++ax)
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const int j = d ? 1 : -1;
-                if (e1[ax][d]) {
-                    const i64 n = l + j * st[ax];
-                    if (bax < 0 || key_less(t1[ax][d], n, bt, bi)) { bax = ax; bd = d; bwhich = 1; bt = t1[ax][d]; bi = n; }
-                }
-                if (e2[ax][d]) {
-                    const i64 n = l + 2 * j * st[ax];
-                    if (bax < 0 || key_less(t2[ax][d], n, bt, bi)) { bax = ax; bd = d; bwhich = 2; bt = t2[ax][d]; bi = n; }
-                }
-            }
-        if (bax < 0) break;
-        if (narrow && key_less(t, l, bt, bi)) break;      // x is frozen before that voxel
-        bool reeval;
-#pragma unroll
-        for (int ax = 3 - NDIM; ax < 3; ++ax)
-#pragma unroll
-            for (int d = 0; d < 2; ++d)
-                if (ax == bax && d == bd) {
-                    if (bwhich == 1) { e1[ax][d] = false; f1[ax][d] = true; }
-                    else { e2[ax][d] = false; f2[ax][d] = true; }
-                }
-        if (bwhich == 1) {
-            reeval = true;                                 // direct neighbour frozen
-        } else {
-            bool mid = false;                              // two cells away: needs the voxel in
-#pragma unroll                                             // between frozen and x already narrow
-            for (int ax = 3 - NDIM; ax < 3; ++ax)
-#pragma unroll
-                for (int d = 0; d < 2; ++d)
-                    if (ax == bax && d == bd) mid = f1[ax][d];
-            reeval = mid && narrow;
-        }
-        if (reeval) {
-            const double dn = stencil_update<NDIM>(t1, t2, f1, f2, g, phi);
-            if (dn != 0.0) { t = dn; narrow = true; }
-        }
-    }
-    return narrow ? t : inf;
-}
+    for (int r = 0; r < 13; ++r) ql[r] = qr[r];
+    const bool phi_pos = __ldg(u + l) > DBL_EPSILON;
 
-constexpr int FMM_MAX_SWEEPS = 4096;
-
-// every candidate that has x in its stencil (one or two cells along an axis) must look again
-template <int NDIM>
-__device__ __forceinline__ void mark_stencil_dirty(i64 l, const FmmGeom& g, u8* mask) {
-    int coord[3];
-    coords_of(l, g, coord);
-    const int ext[3] = {g.n0, g.n1, g.n2};
-    const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    // contributors from the initial frozen set (oracle/lsml_oracle.c:fmm_update's loop)
+    AxisState axs[3];
+    bool any_direct = false;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        axs[ax].active = false; axs[ax].second = false; axs[ax].dir = 0;
+        axs[ax].v1 = 0.0; axs[ax].v2 = 0.0; axs[ax].k1 = 0.f; axs[ax].k2 = 0.f;
+    }
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
 #pragma unroll
-        for (int j = -2; j <= 2; ++j) {
-            if (j == 0) continue;
-            const int cc = coord[ax] + j;
-            if (cc < 0 || cc >= ext[ax]) continue;
-            const i64 n = l + j * st[ax];
-            if (__ldcg(mask + n) & ST_CAND) __stcg(mask + n, ST_DIRTY);   // unconditional re-set
+        for (int d = 0; d < 2; ++d) {
+            const int r1 = slot_rank(ax, d, 1), r2 = slot_rank(ax, d, 2);
+            if (((F >> r1) & 1u) && (!axs[ax].active || qr[r1] < axs[ax].k1)) {
+                axs[ax].active = true; axs[ax].dir = d;
+                axs[ax].v1 = tv[r1]; axs[ax].k1 = qr[r1];
+                axs[ax].v2 = tv[r2]; axs[ax].k2 = qr[r2];
+                axs[ax].second = ((F >> r2) & 1u) &&
+                                 second_order_ok(tv[r2], qr[r2], tv[r1], qr[r1]);
+                any_direct = true;
+            }
         }
+    }
+    bool narrow = false;
+    double t = inf;
+    unsigned self_q = 0xffffffffu;
+    if (any_direct) {
+        const double d0 = solve_quadratic<NDIM>(axs, g, phi_pos);
+        if (d0 != 0.0) { t = d0; narrow = true; self_q = __float_as_uint(qmag(t)); }
+    }
+    bool stale = false;               // contributors changed since the last solve
+    float last_q = 0.f;               // magnitude of the last consumed event
+#pragma unroll 1
+    while (E != 0u) {
+        // next event: smallest (magnitude, rank) among the pending slots
+        unsigned best_q = 0xffffffffu, best_r = 15u;
+#pragma unroll
+        for (int r = 0; r < 13; ++r) {
+            if (r == 6) continue;
+            if (NDIM < 3 && (r < 2 || r > 10)) continue;
+            if (NDIM < 2 && (r < 4 || r > 8)) continue;
+            const unsigned q = __float_as_uint(qr[r]);
+            if (((E >> r) & 1u) && q < best_q) { best_q = q; best_r = (unsigned)r; }
+        }
+        // x is frozen before that voxel
+        if (narrow && (self_q < best_q || (self_q == best_q && 6u < best_r))) break;
+        const unsigned r = best_r;
+        E &= ~(1u << r);
+        F |= 1u << r;
+        const bool lower = r < 6u;
+        const unsigned rr = lower ? r : r - 7u;
+        const int eax = lower ? (int)(rr >> 1) : 2 - (int)(rr >> 1);
+        const int ed = lower ? 0 : 1;
+        const bool direct = (r & 1u) != 0u;
+        const double te = tv[r];
+        const float qe = ql[r];
+        last_q = qe;
+        bool changed = false;
+        if (direct) {
+            const unsigned r2 = lower ? r - 1u : r + 1u;        // two cells away, same direction
+            const double t2 = tv[r2];
+            const float q2 = ql[r2];
+            const bool fr2 = (F >> r2) & 1u;
+#pragma unroll
+            for (int ax = 3 - NDIM; ax < 3; ++ax)
+                // takes over v1 when the axis has none yet, or when it beats the frozen direct
+                // neighbour on the other side exactly as fmm_update's loop decides (-1 side
+                // first, +1 side only if strictly smaller); among marched voxels the earlier
+                // event always stays, an initial frozen voxel can be overtaken
+                if (ax == eax && (!axs[ax].active ||
+                                  (ed == 1 ? qe < axs[ax].k1 : qe <= axs[ax].k1))) {
+                    axs[ax].active = true; axs[ax].dir = ed;
+                    axs[ax].v1 = te; axs[ax].k1 = qe; axs[ax].v2 = t2; axs[ax].k2 = q2;
+                    axs[ax].second = fr2 && second_order_ok(t2, q2, te, qe);
+                    changed = true;
+                }
+        } else {
+#pragma unroll
+            for (int ax = 3 - NDIM; ax < 3; ++ax)
+                if (ax == eax && axs[ax].active && axs[ax].dir == ed && !axs[ax].second &&
+                    second_order_ok(te, qe, axs[ax].v1, axs[ax].k1)) {
+                    axs[ax].v2 = te; axs[ax].k2 = qe; axs[ax].second = true;
+                    changed = true;
+                }
+        }
+        // the marcher updates x when a direct neighbour freezes, and when a voxel two cells away
+        // freezes behind a frozen one while x is already narrow
+        const unsigned rmid = lower ? r + 1u : r - 1u;
+        const bool evaluates = direct || (((F >> rmid) & 1u) && narrow);
+        if (evaluates) {
+            if (changed || stale) {
+                const double dn = solve_quadratic<NDIM>(axs, g, phi_pos);
+                if (dn != 0.0) { t = dn; narrow = true; self_q = __float_as_uint(qmag(t)); }
+                stale = false;
+            }
+        } else if (changed) {
+            stale = true;
+        }
+    }
+    reach = narrow ? fmaxf(last_q, qmag(t)) : __int_as_float(0x7f800000);
+    return narrow ? t : inf;
+}
+
+constexpr int FMM_MAX_SWEEPS = 1 << 20;
+constexpr int FMM_THREADS = 128;
+constexpr int FMM_WARPS = FMM_THREADS / 32;
+#ifndef FMM_MIN_BLOCKS
+#define FMM_MIN_BLOCKS 1
+#endif
+constexpr int FMM_TAIL_MAX = 2 * FMM_THREADS;   // dirty sets this small are swept by ONE CTA
+
+// x (entry e, index l) changed from magnitude q_old to q_new during sweep `cur`: queue, for the
+// next sweep, every candidate whose stencil contains x and whose result can depend on it.
+//   * a candidate that is itself in the work set of THIS sweep (epoch == cur) may have read
+//     either value and its `reach` is in flux: queued unconditionally;
+//   * any other candidate's `reach` is stable (written before the last barrier) and describes
+//     a replay that saw x's old value: queued only if x is, or was, within its reach.
+// When x's value entered the band (`expose`), its far direct neighbours become candidates and
+// are queued for their first evaluation.
+// Written as straight-line predicated phases (state bytes -> records -> claims/atomicMax -> one
+// reservation per list) so that the dozen L2 round trips of each phase overlap instead of
+// forming one long dependent chain per neighbour.
+template <int NDIM>
+__device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[3], float q_min,
+                                               bool expose, const FmmGeom& g, u8* mask, i64* list,
+                                               i64 cap, const Sched& sc) {
+    const int ext[3] = {g.n0, g.n1, g.n2};
+    const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    const i64 est[3] = {(i64)1 << g.sh0, (i64)1 << g.sh1, 1};
+    const unsigned cur = sc.next - 1u;
+    constexpr int NS = 4 * NDIM;
+    const int offs[4] = {-2, -1, 1, 2};
+    // phase 1: state bytes of the stencil
+    unsigned valid = 0u;
+    u8 s[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        const int cc = coord[ax] + j;
+        s[k] = 0xff;
+        if (cc >= 0 && cc < ext[ax]) { valid |= 1u << k; s[k] = __ldcg(mask + l + j * st[ax]); }
+    }
+    // phase 2: scheduling records of the candidates; claims of far direct neighbours
+    uint2 a[NS];
+    unsigned won = 0u;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        const i64 n = l + j * st[ax];
+        a[k] = make_uint2(0xffffffffu, 0u);
+        if (s[k] == ST_CAND) a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
+        if (expose && (j == 1 || j == -1) && s[k] == 0 && claim(mask, n, ST_CAND)) won |= 1u << k;
+    }
+    // phase 3: queue (atomicMax on the epoch; the thread that raises it owns the push)
+    unsigned prev[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        const i64 n = l + j * st[ax];
+        const bool want = ((won >> k) & 1u) ||
+                          (a[k].x < sc.next && (a[k].x == cur || q_min <= __uint_as_float(a[k].y)));
+        prev[k] = 0xffffffffu;
+        if (want) prev[k] = atomicMax(&sc.aux[n].epoch, sc.next);
+    }
+    unsigned push = 0u;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (prev[k] < sc.next) push |= 1u << k;
+    // phase 4: one reservation in the ring, one in the candidate list
+    const int npush = __popc(push), nwon = __popc(won);
+    i64 pos = 0, cpos = 0;
+    if (npush) pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail), (u64)npush);
+    if (nwon) cpos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)nwon);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        const i64 en = e + j * est[ax];
+        if ((push >> k) & 1u) {
+            if (pos - sc.begin < sc.ring.cap) sc.ring.slots[pos & (sc.ring.cap - 1)] = en;
+            else *reinterpret_cast<volatile i64*>(&sc.ctr->overflow[sc.ovf_slot]) = 1;
+            ++pos;
+        }
+        if ((won >> k) & 1u) { list[cap - 1 - cpos] = en; ++cpos; }
     }
 }
 
-// Sweeps of the replay operator over the candidate list until nothing changes.  Only DIRTY
-// candidates are evaluated: a candidate becomes dirty when it is created and whenever a voxel of
-// its stencil changes value, so after the first sweep the work follows the front outwards
-// instead of touching the whole band every time.  One grid barrier per sweep; the "something
-// changed" flags rotate through three slots so that no second barrier is needed to reset them.
-// Ordering of the dirty protocol (per voxel): clear own flag -> fence -> read stencil; a writer
-// does: store T -> fence -> set the readers' flags.  Either the reader sees the new T, or its
-// flag is set again after it cleared it.
+// One queued candidate: replay, publish a changed value.  T is updated in place; there are no
+// fences -- a reader in the same sweep may see the old or the new value, and is queued again
+// for the next sweep by the writer (see publish_change), after the barrier.
 template <int NDIM>
-__global__ void __launch_bounds__(256)
-fmm_march_kernel(const double* __restrict__ u, double* T, u8* mask, i64* list, i64 cap,
-                 FmmGeom g, double band, FmmCounters* ctr, i64* flags /* [3] */) {
+__device__ __forceinline__ void process_candidate(i64 e, const double* __restrict__ u, double* T,
+                                                  u8* mask, i64* list, i64 cap, const FmmGeom& g,
+                                                  double band, const Sched& sc) {
+    int coord[3];
+    const i64 l = decode(e, g, coord);
+    const double old = __ldcg(T + l);
+    float reach;
+    const double nw = replay<NDIM>(l, coord, u, T, mask, g, band, reach);
+    sc.aux[l].reach = reach;
+    if (__double_as_longlong(old) == __double_as_longlong(nw)) return;
+    __stcg(T + l, nw);
+    // a voxel whose value enters the band exposes its direct neighbours
+    publish_change<NDIM>(e, l, coord, fminf(qmag(old), qmag(nw)),
+                         fabs(nw) <= band && !(fabs(old) <= band), g, mask, list, cap, sc);
+}
+
+// Sweeps of the replay operator until no candidate is queued.  A candidate is queued when it is
+// created and whenever a stencil voxel within its reach changes value; the thread that queues
+// it appends it to the work ring, so a sweep touches exactly the queued set and the work
+// follows the front outwards.  Large sets are swept by the whole grid with one grid barrier per
+// sweep.  The tail of a march -- a few dozen voxels per sweep chasing dependency chains along
+// the interface -- is swept by CTA 0 alone with block barriers.  If the ring overflows, the
+// next sweep finds its work by scanning the candidate list for epoch == sweep.
+template <int NDIM>
+__global__ void __launch_bounds__(FMM_THREADS, FMM_MIN_BLOCKS)
+fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i64* list, i64 cap,
+                 FmmGeom g, double band, FmmCounters* ctr, Ring ring) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ i64 queue[FMM_WARPS][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 nthreads = (i64)gridDim.x * blockDim.x;
-    volatile i64* vflags = flags;
-    volatile i64* vcand = &ctr->n_cand;
-    int sweep = 0;
+    const i64 gwarp = tid >> 5, nwarps = nthreads >> 5;
+    volatile i64* vtail = &ctr->tail;
+    volatile i64* vovf = ctr->overflow;
+    volatile i64* vpub = &ctr->pub_begin;
+    unsigned sweep = 1u;               // epoch of the work set being consumed
+    int barriers = 0, tail_sweeps = 0;
     bool converged = false;
-    i64 nc = *vcand;
-    for (; sweep < FMM_MAX_SWEEPS; ++sweep) {
-        const int slot = sweep % 3;
-        if (tid == 0) vflags[(sweep + 1) % 3] = 0;
-        bool changed = false;
-        for (i64 t = tid; t < nc; t += nthreads) {
-            const i64 l = list[cap - 1 - t];
-            if (__ldcg(mask + l) != ST_DIRTY) continue;
-            __stcg(mask + l, ST_CAND);
-            __threadfence();
-            const double old = __ldcg(T + l);
-            const double nw = replay<NDIM>(l, u, T, mask, g, band);
-            if (__double_as_longlong(old) != __double_as_longlong(nw)) {
-                __stcg(T + l, nw);
-                __threadfence();
-                changed = true;
-                mark_stencil_dirty<NDIM>(l, g, mask);
-                // a voxel whose value enters the band exposes its direct neighbours
-                if (fabs(nw) <= band && !(fabs(old) <= band))
-                    push_neighbours<NDIM>(l, g, T, mask, list, cap, ctr);
+    i64 begin = 0, end = *vtail;
+    bool scan = vovf[2] != 0;          // the seed kernel reports into slot 2
+    i64 nreplay = 0;
+    while (barriers < FMM_MAX_SWEEPS) {
+        if (end == begin && !scan) { converged = true; break; }
+        const int slot = barriers % 3;
+        if (tid == 0) {
+            vovf[(barriers + 1) % 3] = 0;
+            if (barriers < 32) {
+                ctr->sizes[barriers] = scan ? -1 : end - begin;
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                ctr->stamps[barriers] = (i64)now;
             }
         }
-        if (changed) vflags[slot] = 1;
+        if (!scan && end - begin <= FMM_TAIL_MAX) {
+            // ---- a run of small sweeps on CTA 0; everybody else waits at the barrier
+            if (blockIdx.x == 0) {
+                i64 b = begin, e = end;
+                int inner = 0;
+                while (e > b && e - b <= FMM_TAIL_MAX && inner < 4096) {
+                    const Sched sc{aux, ring, ctr, b, sweep + 1u, slot};
+                    for (i64 t = b + threadIdx.x; t < e; t += FMM_THREADS) {
+                        process_candidate<NDIM>(ring.slots[t & (ring.cap - 1)], u, T, mask, list,
+                                                cap, g, band, sc);
+                        ++nreplay;
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    b = e;
+                    e = *vtail;
+                    ++sweep;
+                    ++inner;
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) {
+                    vpub[0] = b; vpub[1] = e; vpub[2] = (i64)sweep;
+                    ctr->tail_sweeps += inner;
+                }
+                tail_sweeps += inner;
+            }
+            __threadfence();
+            grid.sync();
+            begin = vpub[0];
+            end = vpub[1];
+            sweep = (unsigned)vpub[2];
+            scan = vovf[slot] != 0;
+            ++barriers;
+            continue;
+        }
+        if (!scan) {
+            const Sched sc{aux, ring, ctr, begin, sweep + 1u, slot};
+            // entry k of the window goes to warp k % nwarps, lane k / nwarps: a small work set
+            // is spread one entry per warp (a lone lane runs its own path, not the union of 32
+            // divergent ones), a large one fills the warps evenly
+            for (i64 k = (i64)lane * nwarps + gwarp; k < end - begin; k += nthreads) {
+                process_candidate<NDIM>(ring.slots[(begin + k) & (ring.cap - 1)], u, T, mask, list,
+                                        cap, g, band, sc);
+                ++nreplay;
+            }
+        } else {
+            // ---- fallback: scan the candidate list; a warp collects its queued entries in
+            // shared memory and evaluates them 32 at a time
+            const Sched sc{aux, ring, ctr, end, sweep + 1u, slot};
+            const i64 nc = *reinterpret_cast<volatile i64*>(&ctr->n_cand);
+            int qn = 0;
+            for (i64 base = gwarp * 32; base < nc; base += nwarps * 32) {
+                const i64 t = base + lane;
+                i64 e = -1;
+                bool queued = false;
+                if (t < nc) {
+                    e = list[cap - 1 - t];
+                    int coord[3];
+                    queued = __ldcg(&aux[decode(e, g, coord)].epoch) == sweep;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, queued);
+                if (queued) queue[warp][qn + __popc(bal & ((1u << lane) - 1u))] = e;
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) {
+                    const i64 e2 = queue[warp][qn - 32 + lane];
+                    qn -= 32;
+                    __syncwarp();
+                    process_candidate<NDIM>(e2, u, T, mask, list, cap, g, band, sc);
+                    ++nreplay;
+                }
+            }
+            if (lane < qn) {
+                process_candidate<NDIM>(queue[warp][lane], u, T, mask, list, cap, g, band, sc);
+                ++nreplay;
+            }
+            __syncwarp();
+        }
         __threadfence();
         grid.sync();
-        const i64 nc_new = *vcand;
-        const bool any = (vflags[slot] != 0) || (nc_new != nc);
-        nc = nc_new;
-        if (!any) { converged = true; ++sweep; break; }
+        // ring entries behind `end` are complete unless this sweep overflowed, in which case the
+        // next sweep scans instead
+        begin = end;
+        end = *vtail;
+        scan = vovf[slot] != 0;
+        ++sweep;
+        ++barriers;
     }
     // final mask: candidates frozen by the marcher are those with |d| <= band
+    const i64 nc = *reinterpret_cast<volatile i64*>(&ctr->n_cand);
     for (i64 t = tid; t < nc; t += nthreads) {
-        const i64 l = list[cap - 1 - t];
+        int coord[3];
+        const i64 l = decode(list[cap - 1 - t], g, coord);
         if (fabs(__ldcg(T + l)) <= band) mask[l] = 1;
         else { mask[l] = 0; T[l] = pos_inf(); }
     }
+    if (nreplay) atomicAdd(reinterpret_cast<u64*>(&ctr->replays), (u64)nreplay);
     if (tid == 0) {
-        ctr->sweeps = sweep;
+        ctr->sweeps = (i64)sweep - 1;
         ctr->converged = converged ? 1 : 0;
         ctr->prev_init = ctr->n_init;
         ctr->prev_cand = nc;
-        vflags[0] = 0; vflags[1] = 0; vflags[2] = 0;
     }
 }
 
@@ -481,106 +837,152 @@ fill_inf_kernel(double* __restrict__ T, i64 total) {
         T[i] = pos_inf();
 }
 
+__global__ void __launch_bounds__(256)
+fill_aux_kernel(Aux* __restrict__ aux, i64 total) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (i64)gridDim.x * blockDim.x)
+        aux[i] = Aux{0u, __int_as_float(0x7f800000)};
+}
+
 // ---------------------------------------------------------------------------------- host side
+// workspace layout: T (total f64) | aux (total x 8 B) | list (total i64) | ring (ring_cap i64)
+// | counters
+struct FmmWorkspace {
+    double* T;
+    Aux* aux;
+    i64* list;
+    Ring ring;
+    FmmCounters* ctr;
+};
+
+static i64 ring_capacity(i64 total) {
+    // a power of two (slot = position & (cap-1) ... kept as % for clarity) that holds every
+    // dirty set seen in practice: a quarter of the grid, at least 64 Ki entries, at most total
+    i64 want = total / 4 > 65536 ? total / 4 : 65536;
+    i64 cap = 1;
+    while (cap < want) cap <<= 1;
+    return cap;
+}
+
+static FmmWorkspace carve(void* workspace, i64 total) {
+    FmmWorkspace w;
+    char* p = static_cast<char*>(workspace);
+    w.T = reinterpret_cast<double*>(p); p += total * sizeof(double);
+    w.aux = reinterpret_cast<Aux*>(p); p += total * sizeof(Aux);
+    w.list = reinterpret_cast<i64*>(p); p += total * sizeof(i64);
+    w.ring.slots = reinterpret_cast<i64*>(p); w.ring.cap = ring_capacity(total);
+    p += w.ring.cap * sizeof(i64);
+    w.ctr = reinterpret_cast<FmmCounters*>(p);
+    return w;
+}
+
 static int g_march_blocks[4] = {0, 0, 0, 0};
 
 template <int NDIM>
-static int march_launch(const double* u, double* T, u8* mask, i64* list, i64 cap, FmmGeom fg,
-                        double band, FmmCounters* ctr, cudaStream_t s) {
+static int march_launch(const double* u, const FmmWorkspace& w, u8* mask, i64 cap, FmmGeom fg,
+                        double band, cudaStream_t s) {
     if (g_march_blocks[NDIM] == 0) {
         int per_sm = 0, dev = 0, sms = 0;
-        LSML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmm_march_kernel<NDIM>, 256, 0));
+        LSML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmm_march_kernel<NDIM>,
+                                                                FMM_THREADS, 0));
         LSML_CUDA(cudaGetDevice(&dev));
         LSML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (per_sm < 1) { set_error("fmm_march_kernel does not fit on an SM"); return 1; }
-        if (per_sm > 2) per_sm = 2;
         g_march_blocks[NDIM] = per_sm * sms;
     }
-    i64* flags = ctr->flags;
-    void* args[] = {(void*)&u, (void*)&T, (void*)&mask, (void*)&list, (void*)&cap, (void*)&fg,
-                    (void*)&band, (void*)&ctr, (void*)&flags};
+    double* T = w.T; Aux* aux = w.aux; i64* list = w.list; FmmCounters* ctr = w.ctr;
+    Ring ring = w.ring;
+    void* args[] = {(void*)&u, (void*)&T, (void*)&aux, (void*)&mask, (void*)&list, (void*)&cap,
+                    (void*)&fg, (void*)&band, (void*)&ctr, (void*)&ring};
     LSML_CUDA(cudaLaunchCooperativeKernel((void*)fmm_march_kernel<NDIM>, dim3(g_march_blocks[NDIM]),
-                                          dim3(256), args, 0, s));
+                                          dim3(FMM_THREADS), args, 0, s));
     count_launch();
     return 0;
 }
 
 i64 fmm_workspace_bytes(i64 total) {
-    // T (f64) + list (i64) + counters
-    return total * (i64)(sizeof(double) + sizeof(i64)) + (i64)sizeof(FmmCounters);
+    return total * (i64)(sizeof(double) + sizeof(Aux) + sizeof(i64)) +
+           ring_capacity(total) * (i64)sizeof(i64) +
+           (i64)sizeof(FmmCounters);
 }
 
 // first use of a workspace: T = +inf everywhere, counters zero
 int fmm_workspace_init(i64 total, void* workspace, cudaStream_t s) {
-    double* T = static_cast<double*>(workspace);
-    FmmCounters* ctr = reinterpret_cast<FmmCounters*>(static_cast<char*>(workspace) +
-                                                      total * (sizeof(double) + sizeof(i64)));
-    fill_inf_kernel<<<LSML_SMS * 8, 256, 0, s>>>(T, total);
+    const FmmWorkspace w = carve(workspace, total);
+    fill_inf_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, total);
     LSML_LAUNCH_CHECK("fill_inf_kernel");
-    LSML_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FmmCounters), s));
+    fill_aux_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.aux, total);
+    LSML_LAUNCH_CHECK("fill_aux_kernel");
+    LSML_CUDA(cudaMemsetAsync(w.ctr, 0, sizeof(FmmCounters), s));
     return 0;
+}
+
+template <int NDIM>
+static int rebuild_nd(const Geom& g, const FmmGeom& fg, const double* u, double eff_band,
+                      const u64* stats, u8* mask, const FmmWorkspace& w, i64 total,
+                      const i64* prev_band_idx, const i64* prev_n_band, cudaStream_t s) {
+    if (prev_band_idx != nullptr) {
+        fmm_init_band_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(u, w.T, mask, w.list, fg, stats,
+                                                              prev_band_idx, prev_n_band, w.ctr);
+        LSML_LAUNCH_CHECK("fmm_init_band_kernel");
+    } else {
+        int bx = 32;
+        while (bx < 256 && bx < g.n[2]) bx <<= 1;
+        int by = 256 / bx;
+        if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
+        const dim3 block(bx, by), grid((unsigned)(g.batch * g.n[0]),
+                                       (unsigned)((g.n[1] + by - 1) / by),
+                                       (unsigned)((g.n[2] + bx - 1) / bx));
+        fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr);
+        LSML_LAUNCH_CHECK("fmm_init_kernel");
+    }
+    fmm_seed_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(mask, w.aux, w.list, total, fg, w.ctr, w.ring);
+    LSML_LAUNCH_CHECK("fmm_seed_kernel");
+    return march_launch<NDIM>(u, w, mask, total, fg, eff_band, s);
 }
 
 // Rebuild the band of every item from u.  mask must be all-zero on first use of the workspace
 // and is thereafter maintained by this function.  band == 0 => whole grid (no narrow band).
 // stats: the exact {u>0} statistics of the SAME u (global_stats), used for the reference's
 // single-sign / all-zero edge cases.  dist_out may be null.
+// prev_band_idx / prev_n_band (device; may be null): the compacted band of the PREVIOUS rebuild
+// when u has since changed only on that band (the evolution loop) -- the initial frozen set is
+// then found from the band instead of a dense pass over u.
 int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u8* mask,
-                double* dist_out, void* workspace, cudaStream_t s) {
+                double* dist_out, void* workspace, const i64* prev_band_idx,
+                const i64* prev_n_band, cudaStream_t s) {
     const i64 total = g.voxels * g.batch;
-    double* T = static_cast<double*>(workspace);
-    i64* list = reinterpret_cast<i64*>(static_cast<char*>(workspace) + total * sizeof(double));
-    FmmCounters* ctr = reinterpret_cast<FmmCounters*>(static_cast<char*>(workspace) +
-                                                      total * (sizeof(double) + sizeof(i64)));
+    const FmmWorkspace w = carve(workspace, total);
     FmmGeom fg;
-    fg.n0 = g.n[0]; fg.n1 = g.n[1]; fg.n2 = g.n[2]; fg.voxels = g.voxels; fg.batch = g.batch;
-    for (int a = 0; a < 3; ++a) { fg.dx[a] = g.dx[a]; fg.idx2[a] = 1.0 / g.dx[a] / g.dx[a]; }
+    if (make_fmm_geom(g, fg)) return 1;
     const double eff_band = band != 0.0 ? band : DBL_MAX;
 
-    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(T, mask, list, total, ctr);
+    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
     LSML_LAUNCH_CHECK("fmm_clear_kernel");
-    fmm_reset_counters_kernel<<<1, 1, 0, s>>>(ctr);
+    fmm_reset_counters_kernel<<<1, 1, 0, s>>>(w.ctr);
     LSML_LAUNCH_CHECK("fmm_reset_counters_kernel");
 
-    int bx = 32;
-    while (bx < 256 && bx < g.n[2]) bx <<= 1;
-    int by = 256 / bx;
-    if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
-    const dim3 block(bx, by), grid((unsigned)(g.batch * g.n[0]), (unsigned)((g.n[1] + by - 1) / by),
-                                   (unsigned)((g.n[2] + bx - 1) / bx));
     int st = 0;
-    if (g.ndim == 3) {
-        fmm_init_kernel<3><<<grid, block, 0, s>>>(u, T, mask, list, fg, stats, ctr);
-        LSML_LAUNCH_CHECK("fmm_init_kernel");
-        fmm_seed_kernel<3><<<LSML_SMS * 8, 256, 0, s>>>(T, mask, list, total, fg, ctr);
-        LSML_LAUNCH_CHECK("fmm_seed_kernel");
-        st = march_launch<3>(u, T, mask, list, total, fg, eff_band, ctr, s);
-    } else if (g.ndim == 2) {
-        fmm_init_kernel<2><<<grid, block, 0, s>>>(u, T, mask, list, fg, stats, ctr);
-        LSML_LAUNCH_CHECK("fmm_init_kernel");
-        fmm_seed_kernel<2><<<LSML_SMS * 8, 256, 0, s>>>(T, mask, list, total, fg, ctr);
-        LSML_LAUNCH_CHECK("fmm_seed_kernel");
-        st = march_launch<2>(u, T, mask, list, total, fg, eff_band, ctr, s);
-    } else {
-        fmm_init_kernel<1><<<grid, block, 0, s>>>(u, T, mask, list, fg, stats, ctr);
-        LSML_LAUNCH_CHECK("fmm_init_kernel");
-        fmm_seed_kernel<1><<<LSML_SMS * 8, 256, 0, s>>>(T, mask, list, total, fg, ctr);
-        LSML_LAUNCH_CHECK("fmm_seed_kernel");
-        st = march_launch<1>(u, T, mask, list, total, fg, eff_band, ctr, s);
-    }
+    if (g.ndim == 3) st = rebuild_nd<3>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
+    else if (g.ndim == 2) st = rebuild_nd<2>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
+    else st = rebuild_nd<1>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
     if (st) return st;
     if (dist_out != nullptr) {
-        fmm_export_kernel<<<LSML_SMS * 8, 256, 0, s>>>(T, mask, dist_out, total);
+        fmm_export_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, mask, dist_out, total);
         LSML_LAUNCH_CHECK("fmm_export_kernel");
     }
     return 0;
 }
 
-// copies {n_init, n_cand, sweeps, converged} of the last rebuild into out[4] (device -> device)
+// device address of the counters {n_init, n_cand, tail_sweeps, sweeps, converged, prev_init,
+// prev_cand, replays, ...} of the last rebuild
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out) {
-    *out = reinterpret_cast<const i64*>(static_cast<char*>(workspace) +
-                                        total * (sizeof(double) + sizeof(i64)));
+    *out = reinterpret_cast<const i64*>(carve(workspace, total).ctr);
     return 0;
 }
+
+// byte offset of FmmCounters::sizes inside the counters (diagnostics)
+i64 fmm_counters_sizes_offset() { return (i64)offsetof(FmmCounters, sizes); }
+i64 fmm_counters_stamps_offset() { return (i64)offsetof(FmmCounters, stamps); }
 
 }  // namespace lsml

@@ -68,8 +68,11 @@ int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx
 i64 fmm_workspace_bytes(i64 total);
 int fmm_workspace_init(i64 total, void* workspace, cudaStream_t s);
 int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u8* mask,
-                double* dist_out, void* workspace, cudaStream_t s);
+                double* dist_out, void* workspace, const i64* prev_band_idx,
+                const i64* prev_n_band, cudaStream_t s);
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
+i64 fmm_counters_sizes_offset();
+i64 fmm_counters_stamps_offset();
 
 // misc.cu
 int ball_init(const Geom& g, double* u, const double* location, double radius,

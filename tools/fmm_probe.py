@@ -30,8 +30,12 @@ for rep in range(2):
     for it in range(iters):
         nb = eng.n_band
         t_step = timed(lambda: eng.step(dreg, 0.35, rebuild=False))
-        t_fmm = timed(lambda: eng._rebuild_band())
+        eng._band_is_rebuilt = True
+        t_fmm = timed(lambda: eng._rebuild_band(from_band=True))
         ctr = eng.fmm_counters()
         if rep == 1:
-            print("it %2d band %7d  step(no rebuild) %8.1f us  rebuild+compact %8.1f us  init %d cand %d sweeps %d conv %s"
-                  % (it, nb, t_step, t_fmm, ctr["n_init"], ctr["n_cand"], ctr["sweeps"], ctr["converged"]))
+            print("it %2d band %7d  step(no rebuild) %8.1f us  rebuild+compact %8.1f us  init %d cand %d sweeps %d (tail %d) replays %d conv %s"
+                  % (it, nb, t_step, t_fmm, ctr["n_init"], ctr["n_cand"], ctr["sweeps"], ctr["tail_sweeps"], ctr["replays"], ctr["converged"]))
+ss = eng.fmm_sweep_sizes()
+print("sweep sizes:", ss[:32])
+print("sweep us   :", [round((ss[32+i+1]-ss[32+i])/1e3,1) for i in range(31) if ss[32+i+1] > 0])
