@@ -579,7 +579,7 @@ constexpr int FMM_MAX_SWEEPS = 1 << 20;
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
 #ifndef FMM_MIN_BLOCKS
-#define FMM_MIN_BLOCKS 1
+#define FMM_MIN_BLOCKS 3
 #endif
 constexpr int FMM_TAIL_MAX = 2 * FMM_THREADS;   // dirty sets this small are swept by ONE CTA
 
