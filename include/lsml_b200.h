@@ -136,7 +136,8 @@ int lsml_assemble_features(int nfeat, const int *kind, const int *a, const int *
 int lsml_linear_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
                         const double *scale, const double *coef, double intercept, double *out,
                         void *stream);
-/* nodes: 8-byte packed nodes (see regress.cu); divisor = n_estimators */
+/* nodes: 8-byte packed nodes (see regress.cu); tree_base: int[n_trees + 1], first node of each
+ * tree followed by the total node count; divisor = n_estimators */
 int lsml_forest_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
                         const double *scale, const void *nodes, const int *tree_base,
                         const uint8_t *root_is_leaf, int n_trees, double divisor, double *out,

@@ -70,7 +70,7 @@ def _round_down_to_f32(thr):
 
 
 def pack_trees(trees, n_features):
-    """sklearn ``Tree`` objects -> (nodes uint32[n,2], tree_base int32[T], root_is_leaf uint8[T]).
+    """sklearn ``Tree`` objects -> (nodes uint32[n,2], tree_base int32[T+1], root_is_leaf uint8[T]).
 
     Nodes are renumbered breadth-first per tree so that the two children of an internal node are
     adjacent; see regress.cu for the 8-byte layout.
@@ -116,6 +116,7 @@ def pack_trees(trees, n_features):
         bases.append(base)
         root_leaf.append(1 if left[0] == -1 else 0)
         base += n
+    bases.append(base)            # sentinel: tree t has bases[t+1] - bases[t] nodes
     return (np.concatenate(all_nodes, axis=0), np.asarray(bases, dtype=np.int32),
             np.asarray(root_leaf, dtype=np.uint8))
 
@@ -124,7 +125,7 @@ class ForestDeviceRegressor(DeviceRegressor):
     def __init__(self, trees, n_features, divisor, scaler, device):
         super().__init__(n_features, scaler, device)
         nodes, bases, root_leaf = pack_trees(trees, n_features)
-        self.n_trees = len(bases)
+        self.n_trees = len(bases) - 1
         self.n_nodes = int(nodes.shape[0])
         self.nodes = _dev(nodes, device)
         self.tree_base = _dev(bases, device)

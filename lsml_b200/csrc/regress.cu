@@ -17,6 +17,11 @@
 // A 100-tree forest of ~600-node trees is ~480 KB: L2-resident, partly L1-resident.  The
 // traversal is latency-bound pointer chasing (not HBM-bound); one thread per band voxel with
 // the voxel's float32 features staged in shared memory as [feature][thread] (conflict-free).
+// Measured alternative (round 1, tools/forest_probe.py, 270k x 16, RF-100): walking the forest
+// tree by tree with the current tree staged in shared memory and 4 voxels per thread was 2x
+// SLOWER (738 us vs 388 us): the plain kernel runs at full occupancy (64 warps/SM) and is bound
+// by L1 tag throughput on divergent node fetches, which the staged version only replaces by
+// shared-memory bank conflicts at a quarter of the occupancy.
 #include "lsml_internal.h"
 
 namespace lsml {
@@ -50,7 +55,7 @@ linear_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_ba
 // --------------------------------------------------------------------------------- forest
 struct ForestView {
     const uint2* nodes;        // 8-byte nodes of all trees back to back
-    const int* tree_base;      // [n_trees] first node of each tree
+    const int* tree_base;      // [n_trees + 1] first node of each tree, then the node count
     const u8* root_is_leaf;    // [n_trees]
     int n_trees;
     double divisor;            // n_estimators for forests, 1 for a single tree

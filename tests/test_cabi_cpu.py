@@ -117,8 +117,9 @@ def test_pack_trees_round_trip():
     Xt[:50] = X[:50]
     X32 = Xt.astype(np.float32)
     acc = np.zeros(200)
-    for t in range(len(bases)):
-        tree = nodes[bases[t]:]
+    assert len(bases) == len(root) + 1 and bases[-1] == nodes.shape[0]
+    for t in range(len(root)):
+        tree = nodes[bases[t]:bases[t + 1]]
         for i in range(200):
             idx, leaf = 0, bool(root[t])
             while not leaf:
@@ -128,4 +129,4 @@ def test_pack_trees_round_trip():
                 leaf = bool((meta >> 22) & 1) if right else bool((meta >> 23) & 1)
                 idx = (meta & 0x3fffff) + int(right)
             acc[i] += tree[idx].view(np.float64)[0]
-    assert np.array_equal(acc / len(bases), rf.predict(Xt))
+    assert np.array_equal(acc / len(root), rf.predict(Xt))

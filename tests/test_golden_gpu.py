@@ -89,9 +89,12 @@ def test_segment_reproduces_reference_segment(kind):
             fr = ForestDeviceRegressor.__new__(ForestDeviceRegressor)
             from lsml_b200.core.regressors import DeviceRegressor
             DeviceRegressor.__init__(fr, len(r.mean), (r.mean, r.scale), dev)
-            fr.nodes, fr.tree_base = _dev(r.nodes, dev), _dev(r.bases, dev)
-            fr.root_is_leaf, fr.n_trees = _dev(r.root, dev), len(r.bases)
-            fr.n_nodes, fr.divisor = int(r.nodes.shape[0]), float(len(r.bases))
+            bases = np.asarray(r.bases, dtype=np.int32)
+            if len(bases) == len(r.root):      # fixture written before the node-count sentinel
+                bases = np.append(bases, np.int32(r.nodes.shape[0]))
+            fr.nodes, fr.tree_base = _dev(r.nodes, dev), _dev(bases, dev)
+            fr.root_is_leaf, fr.n_trees = _dev(r.root, dev), len(r.root)
+            fr.n_nodes, fr.divisor = int(r.nodes.shape[0]), float(len(r.root))
             regs.append(fr)
     feats = (get_basic_image_features(ndim=2, sigmas=[0, 2]) +
              [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
