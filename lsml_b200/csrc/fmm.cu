@@ -35,8 +35,10 @@
 // touched voxels are reset), mask doubles as the state array: 0 far, 1 initial frozen,
 // 2 candidate during the march; 0/1 = the reference's `mask` afterwards.
 #include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
 #include <cfloat>
 #include <cstddef>
+#include <cstdlib>
 #include "lsml_internal.h"
 
 namespace cg = cooperative_groups;
@@ -73,12 +75,21 @@ struct FmmCounters {      // device-resident
     i64 converged;        // 1 when the last march reached its fixed point
     i64 prev_init, prev_cand;   // extents to clear at the next rebuild
     i64 replays;          // replay evaluations of the last march (diagnostic)
-    // ---- work ring: packed entries of the candidates that became dirty, in push order
-    i64 tail;             // next free ring position (monotonic; slot = position % ring_cap)
+    // ---- work ring: packed entries of the candidates queued for the next sweep, in push order
+    i64 tail3[3];         // entries queued for the r-th executed sweep are counted in tail3[r % 3]:
+                          // stable while that sweep reads it, zeroed during the next one, refilled
+                          // during the one after (no reader can race a writer, no extra barrier)
     i64 pub_begin, pub_end;     // window published by CTA 0 after a run of single-CTA sweeps
-    i64 pub_sweep;              // ... and the sweep number reached
+    i64 pub_sweep, pub_rix;     // ... and the sweep number / executed-sweep count reached
     i64 overflow[3];      // rotating "a push was dropped" flags => next sweep scans the list
-    i64 sizes[32];        // dirty-set size of the first 32 sweeps (diagnostic)
+    // ---- schedule hints carried from one rebuild to the next (see Aux::lvl)
+    i64 gen;              // rebuild counter (low 8 bits tag the hints)
+    i64 use_hints;        // this rebuild parks candidates until the sweep of their hint
+    i64 last_bucket;      // largest sweep number anything is parked for
+    i64 hist[2][256];     // [gen & 1][level]: voxels whose hint of that rebuild is `level`
+    i64 offs[257];        // start of each level's bucket in the parking array (scan of hist[prev])
+    i64 fill[256];        // entries parked per level so far
+    i64 sizes[32];        // work-set size of the first 32 grid-wide sweeps (diagnostic)
     i64 stamps[32];       // %globaltimer (ns) at the start of those sweeps (diagnostic)
 };
 
@@ -89,8 +100,10 @@ __device__ __forceinline__ float qmag(double d) { return __double2float_rn(fabs(
 
 __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// State byte of a voxel during the march: 0 far, 1 initial frozen, 2 candidate.
+// State byte of a voxel during the march: 0 far, 1 initial frozen, (level << 2) | 2 candidate,
+// where level is the candidate's dependency depth in this rebuild (see Aux::lvl).
 constexpr u8 ST_INIT = 1, ST_CAND = 2;
+constexpr unsigned MAX_LEVEL = 63u;
 
 // claim voxel g (state 0 -> `value`); returns true for the single winner.  The state is one
 // byte of a 32-bit word; atomicOr on the word keeps the other three bytes intact.
@@ -105,14 +118,30 @@ __device__ __forceinline__ bool claim(u8* mask, i64 g, unsigned value) {
 //   epoch  the last sweep this voxel was queued for (0 = never); voxel y is in the work set of
 //          sweep s exactly when epoch == s, so queueing is an atomicMax and needs no clearing;
 //   reach  how far y's last replay looked: max(magnitude of the last event it consumed,
-//          magnitude of its result), +inf when it ended without a value.  A stencil voxel whose
-//          old AND new magnitudes are both beyond `reach` was not consumed by that replay and
-//          would not be consumed by a new one (every event before it is unchanged and the
-//          replay stops at it), so its change cannot alter y -- y is not queued for it.
+//          magnitude of its result), +inf when it ended without a value, rounded UP to the top
+//          16 bits of a float32.  A stencil voxel whose old AND new magnitudes are both beyond
+//          `reach` was not consumed by that replay and would not be consumed by a new one
+//          (every event before it is unchanged and the replay stops at it), so its change
+//          cannot alter y -- y is not queued for it.
+//   lvl    schedule hint: (rebuild tag << 8) | dependency depth of y in that rebuild, i.e.
+//          1 + the largest depth among the stencil voxels its last replay consumed (initial
+//          frozen voxels have depth 0).  A voxel of depth d cannot have its final value before
+//          sweep d, and has it at sweep d if everything shallower was evaluated on time.  The
+//          dependency structure barely moves between two evolution iterations, so in the NEXT
+//          rebuild y is parked until sweep d instead of being re-evaluated every time one of
+//          its still-unsettled upwind voxels moves.  A hint only changes WHEN y is evaluated,
+//          never the fixed point the sweeps converge to.
 struct __align__(8) Aux {
     unsigned epoch;
-    float reach;
+    unsigned short reach16;
+    unsigned short lvl;
 };
+
+__device__ __forceinline__ unsigned short reach_up16(float r) {
+    return (unsigned short)((__float_as_uint(r) + 0xffffu) >> 16);
+}
+__device__ __forceinline__ float reach_from16(unsigned r16) { return __uint_as_float(r16 << 16); }
+constexpr unsigned REACH16_INF = 0x7f80u;
 
 __device__ __forceinline__ i64 decode(i64 e, const FmmGeom& g, int coord[3]) {
     coord[2] = (int)(e & (((i64)1 << g.sh1) - 1));
@@ -134,15 +163,40 @@ fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__
         int coord[3];
         const i64 l = decode(t < ni ? list[t] : list[cap - 1 - (t - ni)], g, coord);
         T[l] = pos_inf();
-        aux[l] = Aux{0u, __int_as_float(0x7f800000)};
+        aux[l] = Aux{0u, (unsigned short)REACH16_INF, aux[l].lvl};      // the hint survives
         mask[l] = 0;
     }
 }
 
-__global__ void fmm_reset_counters_kernel(FmmCounters* ctr) {
-    ctr->n_init = 0; ctr->n_cand = 0; ctr->tail_sweeps = 0; ctr->sweeps = 0; ctr->converged = 0;
-    ctr->replays = 0; ctr->tail = 0; ctr->pub_begin = 0; ctr->pub_end = 0; ctr->pub_sweep = 0;
-    ctr->overflow[0] = 0; ctr->overflow[1] = 0; ctr->overflow[2] = 0;
+// Start of a rebuild (one CTA of 256 threads): reset the per-rebuild counters, advance the hint
+// generation, turn last rebuild's hint histogram into parking-bucket offsets.
+__global__ void __launch_bounds__(256)
+fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap) {
+    __shared__ i64 scan[256];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        ctr->n_init = 0; ctr->n_cand = 0; ctr->tail_sweeps = 0; ctr->sweeps = 0; ctr->converged = 0;
+        ctr->replays = 0; ctr->tail3[0] = 0; ctr->tail3[1] = 0; ctr->tail3[2] = 0; ctr->pub_begin = 0; ctr->pub_end = 0; ctr->pub_sweep = 0; ctr->pub_rix = 0;
+        ctr->overflow[0] = 0; ctr->overflow[1] = 0; ctr->overflow[2] = 0;
+        ctr->last_bucket = 0;
+        ctr->gen = ctr->gen + 1;
+    }
+    __syncthreads();
+    const int cur = (int)(ctr->gen & 1), prev = cur ^ 1;
+    scan[t] = ctr->hist[prev][t];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const i64 v = t >= o ? scan[t - o] : 0;
+        __syncthreads();
+        scan[t] += v;
+        __syncthreads();
+    }
+    ctr->offs[t + 1] = scan[t];
+    if (t == 0) ctr->offs[0] = 0;
+    ctr->hist[cur][t] = 0;
+    ctr->fill[t] = 0;
+    // every 16th rebuild runs without hints so that they cannot drift upwards for ever
+    if (t == 255) ctr->use_hints = (allow_hints && (ctr->gen % 16) != 0 && scan[255] <= park_cap) ? 1 : 0;
 }
 
 // Initial frozen value of voxel l (orc_fmm_distance "initial frozen set"): zeros, and voxels
@@ -272,22 +326,71 @@ struct Ring {
     i64 cap;
 };
 
-// everything a thread needs to queue work for the next sweep
+// Same-address atomics serialise in L2 (about one per clock per address): a sweep that made every
+// one of its ~10^5 threads bump the same ring / list / histogram counter spent most of its
+// time there.  These helpers let the currently converged lanes of a warp that target the SAME
+// counter issue ONE atomic between them.
+// returns this lane's slot: (old counter value) + (rank among the lanes sharing `key`)
+__device__ __forceinline__ i64 warp_agg_reserve(i64* counter, unsigned key) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    i64 base = 0;
+    if ((int)lane == leader)
+        base = (i64)atomicAdd(reinterpret_cast<u64*>(counter), (u64)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+// counter[key] += delta for every lane, one reduction-atomic per distinct key
+__device__ __forceinline__ void warp_agg_add(i64* counters, unsigned key, i64 delta) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, key);
+    const unsigned lane = threadIdx.x & 31u;
+    if ((int)lane == __ffs(peers) - 1)
+        atomicAdd(reinterpret_cast<u64*>(counters + key), (u64)(delta * __popc(peers)));
+}
+
+// everything a thread needs to queue work
 struct Sched {
     Aux* aux;
     Ring ring;
+    i64* park;           // parking array: bucket of level h = park[offs[h] .. offs[h] + fill[h])
     FmmCounters* ctr;
     i64 begin;           // start of the ring window being consumed (overflow test)
+    i64 base;            // ring position of the first entry of the sweep being filled
     unsigned next;       // epoch of the sweep being filled
+    int tslot;           // its counter: tail3[tslot]
+    unsigned hint_tag;   // (tag of the previous rebuild) << 8, or ~0 when hints are off
     int ovf_slot;
 };
 
-// queue voxel n (packed entry e) for sweep sc.next unless it already is
+// sweep a voxel with hint word `lvl` should be queued for: the next one, or later if last
+// rebuild's hint says its value settled later
+__device__ __forceinline__ unsigned target_sweep(const Sched& sc, unsigned lvl) {
+    const unsigned h = lvl & 0xffu;
+    return ((lvl & 0xff00u) == sc.hint_tag && h > sc.next) ? h : sc.next;
+}
+
+// store entry e for sweep `target` (the caller has raised the epoch and owns the push)
+__device__ __forceinline__ void push_entry(const Sched& sc, unsigned target, i64 e) {
+    if (target == sc.next) {
+        const i64 pos = sc.base + warp_agg_reserve(&sc.ctr->tail3[sc.tslot], 0u);
+        if (pos - sc.begin < sc.ring.cap) sc.ring.slots[pos & (sc.ring.cap - 1)] = e;
+        else *reinterpret_cast<volatile i64*>(&sc.ctr->overflow[sc.ovf_slot]) = 1;
+    } else {
+        const i64 pos = warp_agg_reserve(&sc.ctr->fill[target], target);
+        sc.park[sc.ctr->offs[target] + pos] = e;
+        if (pos == 0 || (i64)target > *reinterpret_cast<volatile i64*>(&sc.ctr->last_bucket))
+            atomicMax(reinterpret_cast<u64*>(&sc.ctr->last_bucket), (u64)target);
+    }
+}
+
+// queue voxel n (packed entry e) unless it already is queued for that sweep or a later one
 __device__ __forceinline__ void enqueue(const Sched& sc, i64 n, i64 e) {
-    if (atomicMax(&sc.aux[n].epoch, sc.next) >= sc.next) return;
-    const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail), (u64)1);
-    if (pos - sc.begin < sc.ring.cap) sc.ring.slots[pos & (sc.ring.cap - 1)] = e;
-    else *reinterpret_cast<volatile i64*>(&sc.ctr->overflow[sc.ovf_slot]) = 1;
+    const unsigned target = target_sweep(sc, sc.aux[n].lvl);
+    if (atomicMax(&sc.aux[n].epoch, target) >= target) return;
+    push_entry(sc, target, e);
 }
 
 // far direct neighbours of a voxel that is frozen (or whose value entered the band) become
@@ -317,9 +420,11 @@ __device__ __forceinline__ void expose_neighbours(i64 e, i64 l, const int (&coor
 
 template <int NDIM>
 __global__ void __launch_bounds__(256)
-fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* ctr, Ring ring) {
+fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* ctr, Ring ring,
+                i64* park) {
     const i64 ni = ctr->n_init;
-    const Sched sc{aux, ring, ctr, 0, 1u, 2};
+    const unsigned tag = ctr->use_hints ? (unsigned)(((ctr->gen - 1) & 0xff) << 8) : 0xffffffffu;
+    const Sched sc{aux, ring, park, ctr, 0, 0, 1u, 1, tag, 2};
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni;
          t += (i64)gridDim.x * blockDim.x) {
         int coord[3];
@@ -437,16 +542,17 @@ __device__ __forceinline__ double solve_quadratic(const AxisState (&in)[3], cons
 template <int NDIM>
 __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict__ u,
                          const double* T, const u8* mask, const FmmGeom& g, double band,
-                         float& reach) {
+                         float& reach, unsigned& level) {
     const int ext[3] = {g.n0, g.n1, g.n2};
     const i64 st[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
     double tv[13];                    // by slot rank; dynamically indexed => local memory (L1)
+    unsigned char lv[13];             // dependency depth of the slot's voxel
     float qr[13];                     // the same magnitudes again in registers for the selection
     unsigned F = 0u;                  // frozen now
     unsigned E = 0u;                  // pending event (marched voxel with a value inside the band)
     const double inf = pos_inf();
 #pragma unroll
-    for (int r = 0; r < 13; ++r) { tv[r] = inf; qr[r] = 0.f; }
+    for (int r = 0; r < 13; ++r) { tv[r] = inf; qr[r] = 0.f; lv[r] = 0; }
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
 #pragma unroll
@@ -460,7 +566,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
                     const double t = __ldcg(T + n);   // L2: other CTAs update T concurrently
                     const u8 s = __ldcg(mask + n);
                     const int r = slot_rank(ax, d, which);
-                    tv[r] = t; qr[r] = qmag(t);
+                    tv[r] = t; qr[r] = qmag(t); lv[r] = s >> 2;
                     if (s == ST_INIT) F |= 1u << r;
                     else if ((s & ST_CAND) && (fabs(t) <= band)) E |= 1u << r;
                 }
@@ -504,6 +610,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
     }
     bool stale = false;               // contributors changed since the last solve
     float last_q = 0.f;               // magnitude of the last consumed event
+    unsigned deepest = 0u;            // largest depth among the consumed events
 #pragma unroll 1
     while (E != 0u) {
         // next event: smallest (magnitude, rank) among the pending slots
@@ -529,6 +636,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
         const double te = tv[r];
         const float qe = ql[r];
         last_q = qe;
+        deepest = max(deepest, (unsigned)lv[r]);
         bool changed = false;
         if (direct) {
             const unsigned r2 = lower ? r - 1u : r + 1u;        // two cells away, same direction
@@ -572,6 +680,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
         }
     }
     reach = narrow ? fmaxf(last_q, qmag(t)) : __int_as_float(0x7f800000);
+    level = min(deepest + 1u, MAX_LEVEL);
     return narrow ? t : inf;
 }
 
@@ -579,7 +688,7 @@ constexpr int FMM_MAX_SWEEPS = 1 << 20;
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
 #ifndef FMM_MIN_BLOCKS
-#define FMM_MIN_BLOCKS 3
+#define FMM_MIN_BLOCKS 4
 #endif
 constexpr int FMM_TAIL_MAX = 2 * FMM_THREADS;   // dirty sets this small are swept by ONE CTA
 
@@ -622,37 +731,55 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const i64 n = l + j * st[ax];
         a[k] = make_uint2(0xffffffffu, 0u);
-        if (s[k] == ST_CAND) a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
+        if ((s[k] & 3) == ST_CAND || (expose && (j == 1 || j == -1) && s[k] == 0))
+            a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
         if (expose && (j == 1 || j == -1) && s[k] == 0 && claim(mask, n, ST_CAND)) won |= 1u << k;
     }
     // phase 3: queue (atomicMax on the epoch; the thread that raises it owns the push)
-    unsigned prev[NS];
+    unsigned prev[NS], target[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const i64 n = l + j * st[ax];
+        target[k] = target_sweep(sc, a[k].y >> 16);
         const bool want = ((won >> k) & 1u) ||
-                          (a[k].x < sc.next && (a[k].x == cur || q_min <= __uint_as_float(a[k].y)));
+                          ((s[k] & 3) == ST_CAND && a[k].x < target[k] &&
+                           (a[k].x == cur || q_min <= reach_from16(a[k].y & 0xffffu)));
         prev[k] = 0xffffffffu;
-        if (want) prev[k] = atomicMax(&sc.aux[n].epoch, sc.next);
+        if (want) prev[k] = atomicMax(&sc.aux[n].epoch, target[k]);
     }
-    unsigned push = 0u;
+    unsigned push = 0u, ringp = 0u;
 #pragma unroll
     for (int k = 0; k < NS; ++k)
-        if (prev[k] < sc.next) push |= 1u << k;
-    // phase 4: one reservation in the ring, one in the candidate list
-    const int npush = __popc(push), nwon = __popc(won);
-    i64 pos = 0, cpos = 0;
-    if (npush) pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail), (u64)npush);
-    if (nwon) cpos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)nwon);
+        if (prev[k] < target[k]) { push |= 1u << k; if (target[k] == sc.next) ringp |= 1u << k; }
+    // phase 4: one reservation in the ring, one in the candidate list; parked entries go to
+    // the bucket of their sweep
+    // (aggregated over the lanes of the warp that are publishing together)
+    const int nring = __popc(ringp), nwon = __popc(won);
+    i64 pos, cpos;
+    {
+        cg::coalesced_group cgp = cg::coalesced_threads();
+        const int last = (int)cgp.size() - 1;
+        const int ir = cg::inclusive_scan(cgp, nring), iw = cg::inclusive_scan(cgp, nwon);
+        const int tr = cgp.shfl(ir, last), tw = cgp.shfl(iw, last);
+        i64 br = 0, bw = 0;
+        if (cgp.thread_rank() == 0) {
+            if (tr) br = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail3[sc.tslot]), (u64)tr);
+            if (tw) bw = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)tw);
+        }
+        pos = sc.base + cgp.shfl(br, 0) + ir - nring;
+        cpos = cgp.shfl(bw, 0) + iw - nwon;
+    }
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const i64 en = e + j * est[ax];
-        if ((push >> k) & 1u) {
+        if ((ringp >> k) & 1u) {
             if (pos - sc.begin < sc.ring.cap) sc.ring.slots[pos & (sc.ring.cap - 1)] = en;
             else *reinterpret_cast<volatile i64*>(&sc.ctr->overflow[sc.ovf_slot]) = 1;
             ++pos;
+        } else if ((push >> k) & 1u) {
+            push_entry(sc, target[k], en);
         }
         if ((won >> k) & 1u) { list[cap - 1 - cpos] = en; ++cpos; }
     }
@@ -664,14 +791,27 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
 template <int NDIM>
 __device__ __forceinline__ void process_candidate(i64 e, const double* __restrict__ u, double* T,
                                                   u8* mask, i64* list, i64 cap, const FmmGeom& g,
-                                                  double band, const Sched& sc) {
+                                                  double band, const Sched& sc, unsigned gen_tag) {
     int coord[3];
     const i64 l = decode(e, g, coord);
     const double old = __ldcg(T + l);
+    unsigned lvl = sc.aux[l].lvl;
     float reach;
-    const double nw = replay<NDIM>(l, coord, u, T, mask, g, band, reach);
-    sc.aux[l].reach = reach;
-    if (__double_as_longlong(old) == __double_as_longlong(nw)) return;
+    unsigned level;
+    const double nw = replay<NDIM>(l, coord, u, T, mask, g, band, reach, level);
+    const bool changed = __double_as_longlong(old) != __double_as_longlong(nw);
+    // depth: visible to the neighbours' replays through the state byte, and kept (tagged with
+    // this rebuild) as the hint for the next rebuild
+    mask[l] = (u8)((level << 2) | ST_CAND);
+    if (lvl != (gen_tag | level)) {
+        i64* hist = sc.ctr->hist[(gen_tag >> 8) & 1u];
+        if ((lvl & 0xff00u) == gen_tag) warp_agg_add(hist, lvl & 0xffu, -1);
+        warp_agg_add(hist, level, 1);
+        lvl = gen_tag | level;
+    }
+    // reach and hint share a 32-bit word that only this voxel's evaluator writes
+    reinterpret_cast<unsigned*>(sc.aux + l)[1] = (unsigned)reach_up16(reach) | (lvl << 16);
+    if (!changed) return;
     __stcg(T + l, nw);
     // a voxel whose value enters the band exposes its direct neighbours
     publish_change<NDIM>(e, l, coord, fminf(qmag(old), qmag(nw)),
@@ -680,64 +820,92 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
 
 // Sweeps of the replay operator until no candidate is queued.  A candidate is queued when it is
 // created and whenever a stencil voxel within its reach changes value; the thread that queues
-// it appends it to the work ring, so a sweep touches exactly the queued set and the work
-// follows the front outwards.  Large sets are swept by the whole grid with one grid barrier per
-// sweep.  The tail of a march -- a few dozen voxels per sweep chasing dependency chains along
-// the interface -- is swept by CTA 0 alone with block barriers.  If the ring overflows, the
-// next sweep finds its work by scanning the candidate list for epoch == sweep.
+// it appends it to the work ring (next sweep) or, when last rebuild's hint says its value
+// settles later, to the parking bucket of that sweep.  The work set of sweep s is the ring
+// window filled during sweep s-1 plus bucket s.  Large sets are swept by the whole grid with one
+// grid barrier per sweep.  Small ones -- a few dozen voxels per sweep chasing dependency chains
+// along the interface -- are swept by CTA 0 alone with block barriers.  If the ring overflows,
+// the next sweep finds its work by scanning the candidate list for epoch == sweep.
 template <int NDIM>
 __global__ void __launch_bounds__(FMM_THREADS, FMM_MIN_BLOCKS)
 fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i64* list, i64 cap,
-                 FmmGeom g, double band, FmmCounters* ctr, Ring ring) {
+                 FmmGeom g, double band, FmmCounters* ctr, Ring ring, i64* park) {
     cg::grid_group grid = cg::this_grid();
     __shared__ i64 queue[FMM_WARPS][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 nthreads = (i64)gridDim.x * blockDim.x;
     const i64 gwarp = tid >> 5, nwarps = nthreads >> 5;
-    volatile i64* vtail = &ctr->tail;
+    volatile i64* vtail = ctr->tail3;
     volatile i64* vovf = ctr->overflow;
     volatile i64* vpub = &ctr->pub_begin;
+    volatile i64* vfill = ctr->fill;
+    volatile i64* vlast = &ctr->last_bucket;
+    const bool hints = ctr->use_hints != 0;
+    const unsigned gen_tag = (unsigned)((ctr->gen & 0xff) << 8);
+    const unsigned hint_tag = hints ? (unsigned)(((ctr->gen - 1) & 0xff) << 8) : 0xffffffffu;
     unsigned sweep = 1u;               // epoch of the work set being consumed
+    unsigned rix = 1u;                 // executed-sweep counter (rotation index of tail3)
     int barriers = 0, tail_sweeps = 0;
     bool converged = false;
-    i64 begin = 0, end = *vtail;
-    bool scan = vovf[2] != 0;          // the seed kernel reports into slot 2
+    i64 begin = 0, end = vtail[1];     // the seed kernel queued sweep 1
+    bool scan = vovf[2] != 0;          // ... and reports overflow into slot 2
     i64 nreplay = 0;
     while (barriers < FMM_MAX_SWEEPS) {
-        if (end == begin && !scan) { converged = true; break; }
+        i64 nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;       // bucket of this sweep
+        if (end == begin && nbk == 0 && !scan) {
+            if (!hints || (i64)sweep >= *vlast) { converged = true; break; }
+            ++sweep;                    // nothing queued for this sweep, something parked later
+            continue;
+        }
         const int slot = barriers % 3;
         if (tid == 0) {
             vovf[(barriers + 1) % 3] = 0;
+            vtail[(rix + 2u) % 3u] = 0;
             if (barriers < 32) {
-                ctr->sizes[barriers] = scan ? -1 : end - begin;
+                ctr->sizes[barriers] = scan ? -1 : end - begin + nbk;
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 ctr->stamps[barriers] = (i64)now;
             }
         }
-        if (!scan && end - begin <= FMM_TAIL_MAX) {
+        if (!scan && end - begin + nbk <= FMM_TAIL_MAX) {
             // ---- a run of small sweeps on CTA 0; everybody else waits at the barrier
             if (blockIdx.x == 0) {
                 i64 b = begin, e = end;
                 int inner = 0;
-                while (e > b && e - b <= FMM_TAIL_MAX && inner < 4096) {
-                    const Sched sc{aux, ring, ctr, b, sweep + 1u, slot};
-                    for (i64 t = b + threadIdx.x; t < e; t += FMM_THREADS) {
-                        process_candidate<NDIM>(ring.slots[t & (ring.cap - 1)], u, T, mask, list,
-                                                cap, g, band, sc);
+                while (inner < 4096) {
+                    nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;
+                    const i64 work = e - b + nbk;
+                    if (work == 0) {
+                        if (!hints || (i64)sweep >= *vlast) break;
+                        ++sweep;
+                        continue;
+                    }
+                    if (work > FMM_TAIL_MAX) break;
+                    if (threadIdx.x == 0 && inner > 0) vtail[(rix + 2u) % 3u] = 0;
+                    const Sched sc{aux, ring, park, ctr, b, e, sweep + 1u, (int)((rix + 1u) % 3u),
+                                   hint_tag, slot};
+                    const i64 pbase = nbk ? ctr->offs[sweep] : 0;
+                    for (i64 k = threadIdx.x; k < work; k += FMM_THREADS) {
+                        const i64 ent = k < e - b ? ring.slots[(b + k) & (ring.cap - 1)]
+                                                  : park[pbase + k - (e - b)];
+                        process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag);
                         ++nreplay;
                     }
                     __threadfence();
                     __syncthreads();
                     b = e;
-                    e = *vtail;
+                    e = b + vtail[(rix + 1u) % 3u];
                     ++sweep;
+                    ++rix;
                     ++inner;
+                    const bool dropped = vovf[slot] != 0;      // (never seen: the ring is >= 64 Ki)
                     __syncthreads();
+                    if (dropped) break;
                 }
                 if (threadIdx.x == 0) {
-                    vpub[0] = b; vpub[1] = e; vpub[2] = (i64)sweep;
+                    vpub[0] = b; vpub[1] = e; vpub[2] = (i64)sweep; vpub[3] = (i64)rix;
                     ctr->tail_sweeps += inner;
                 }
                 tail_sweeps += inner;
@@ -747,24 +915,30 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             begin = vpub[0];
             end = vpub[1];
             sweep = (unsigned)vpub[2];
+            rix = (unsigned)vpub[3];
             scan = vovf[slot] != 0;
             ++barriers;
             continue;
         }
         if (!scan) {
-            const Sched sc{aux, ring, ctr, begin, sweep + 1u, slot};
-            // entry k of the window goes to warp k % nwarps, lane k / nwarps: a small work set
-            // is spread one entry per warp (a lone lane runs its own path, not the union of 32
+            const Sched sc{aux, ring, park, ctr, begin, end, sweep + 1u, (int)((rix + 1u) % 3u),
+                           hint_tag, slot};
+            const i64 work = end - begin + nbk;
+            const i64 pbase = nbk ? ctr->offs[sweep] : 0;
+            // entry k of the work set goes to warp k % nwarps, lane k / nwarps: a small set is
+            // spread one entry per warp (a lone lane runs its own path, not the union of 32
             // divergent ones), a large one fills the warps evenly
-            for (i64 k = (i64)lane * nwarps + gwarp; k < end - begin; k += nthreads) {
-                process_candidate<NDIM>(ring.slots[(begin + k) & (ring.cap - 1)], u, T, mask, list,
-                                        cap, g, band, sc);
+            for (i64 k = (i64)lane * nwarps + gwarp; k < work; k += nthreads) {
+                const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
+                                                : park[pbase + k - (end - begin)];
+                process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag);
                 ++nreplay;
             }
         } else {
             // ---- fallback: scan the candidate list; a warp collects its queued entries in
             // shared memory and evaluates them 32 at a time
-            const Sched sc{aux, ring, ctr, end, sweep + 1u, slot};
+            const Sched sc{aux, ring, park, ctr, end, end, sweep + 1u, (int)((rix + 1u) % 3u),
+                           hint_tag, slot};
             const i64 nc = *reinterpret_cast<volatile i64*>(&ctr->n_cand);
             int qn = 0;
             for (i64 base = gwarp * 32; base < nc; base += nwarps * 32) {
@@ -784,12 +958,12 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                     const i64 e2 = queue[warp][qn - 32 + lane];
                     qn -= 32;
                     __syncwarp();
-                    process_candidate<NDIM>(e2, u, T, mask, list, cap, g, band, sc);
+                    process_candidate<NDIM>(e2, u, T, mask, list, cap, g, band, sc, gen_tag);
                     ++nreplay;
                 }
             }
             if (lane < qn) {
-                process_candidate<NDIM>(queue[warp][lane], u, T, mask, list, cap, g, band, sc);
+                process_candidate<NDIM>(queue[warp][lane], u, T, mask, list, cap, g, band, sc, gen_tag);
                 ++nreplay;
             }
             __syncwarp();
@@ -799,9 +973,10 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
         // ring entries behind `end` are complete unless this sweep overflowed, in which case the
         // next sweep scans instead
         begin = end;
-        end = *vtail;
+        end = begin + vtail[(rix + 1u) % 3u];
         scan = vovf[slot] != 0;
         ++sweep;
+        ++rix;
         ++barriers;
     }
     // final mask: candidates frozen by the marcher are those with |d| <= band
@@ -841,17 +1016,18 @@ __global__ void __launch_bounds__(256)
 fill_aux_kernel(Aux* __restrict__ aux, i64 total) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (i64)gridDim.x * blockDim.x)
-        aux[i] = Aux{0u, __int_as_float(0x7f800000)};
+        aux[i] = Aux{0u, (unsigned short)REACH16_INF, (unsigned short)0};
 }
 
 // ---------------------------------------------------------------------------------- host side
 // workspace layout: T (total f64) | aux (total x 8 B) | list (total i64) | ring (ring_cap i64)
-// | counters
+// | parking array (ring_cap i64) | counters
 struct FmmWorkspace {
     double* T;
     Aux* aux;
     i64* list;
     Ring ring;
+    i64* park;
     FmmCounters* ctr;
 };
 
@@ -872,6 +1048,7 @@ static FmmWorkspace carve(void* workspace, i64 total) {
     w.list = reinterpret_cast<i64*>(p); p += total * sizeof(i64);
     w.ring.slots = reinterpret_cast<i64*>(p); w.ring.cap = ring_capacity(total);
     p += w.ring.cap * sizeof(i64);
+    w.park = reinterpret_cast<i64*>(p); p += w.ring.cap * sizeof(i64);
     w.ctr = reinterpret_cast<FmmCounters*>(p);
     return w;
 }
@@ -892,8 +1069,9 @@ static int march_launch(const double* u, const FmmWorkspace& w, u8* mask, i64 ca
     }
     double* T = w.T; Aux* aux = w.aux; i64* list = w.list; FmmCounters* ctr = w.ctr;
     Ring ring = w.ring;
+    i64* park = w.park;
     void* args[] = {(void*)&u, (void*)&T, (void*)&aux, (void*)&mask, (void*)&list, (void*)&cap,
-                    (void*)&fg, (void*)&band, (void*)&ctr, (void*)&ring};
+                    (void*)&fg, (void*)&band, (void*)&ctr, (void*)&ring, (void*)&park};
     LSML_CUDA(cudaLaunchCooperativeKernel((void*)fmm_march_kernel<NDIM>, dim3(g_march_blocks[NDIM]),
                                           dim3(FMM_THREADS), args, 0, s));
     count_launch();
@@ -902,7 +1080,7 @@ static int march_launch(const double* u, const FmmWorkspace& w, u8* mask, i64 ca
 
 i64 fmm_workspace_bytes(i64 total) {
     return total * (i64)(sizeof(double) + sizeof(Aux) + sizeof(i64)) +
-           ring_capacity(total) * (i64)sizeof(i64) +
+           2 * ring_capacity(total) * (i64)sizeof(i64) +
            (i64)sizeof(FmmCounters);
 }
 
@@ -936,7 +1114,8 @@ static int rebuild_nd(const Geom& g, const FmmGeom& fg, const double* u, double 
         fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr);
         LSML_LAUNCH_CHECK("fmm_init_kernel");
     }
-    fmm_seed_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(mask, w.aux, w.list, total, fg, w.ctr, w.ring);
+    fmm_seed_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(mask, w.aux, w.list, total, fg, w.ctr, w.ring,
+                                                     w.park);
     LSML_LAUNCH_CHECK("fmm_seed_kernel");
     return march_launch<NDIM>(u, w, mask, total, fg, eff_band, s);
 }
@@ -959,8 +1138,10 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
 
     fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
     LSML_LAUNCH_CHECK("fmm_clear_kernel");
-    fmm_reset_counters_kernel<<<1, 1, 0, s>>>(w.ctr);
-    LSML_LAUNCH_CHECK("fmm_reset_counters_kernel");
+    static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
+    fmm_prepare_kernel<<<1, 256, 0, s>>>(w.ctr, (prev_band_idx != nullptr && !no_hints) ? 1 : 0,
+                                         w.ring.cap);
+    LSML_LAUNCH_CHECK("fmm_prepare_kernel");
 
     int st = 0;
     if (g.ndim == 3) st = rebuild_nd<3>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
