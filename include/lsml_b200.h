@@ -156,6 +156,13 @@ int lsml_band_update(int ndim, const int *shape, long long batch, const double *
                      const double *vel, const long long *band_idx, const long long *n_band,
                      double step, double *new_u, double *gmag_out, int apply, void *stream);
 
+/* Same with apply, and the lsml_global_stats record of u (stats, device) brought up to date from
+ * the voxels whose sign class changed -- exactly what a dense recount of the new u would give. */
+int lsml_band_update_stats(int ndim, const int *shape, long long batch, const double *dx, double *u,
+                           const double *vel, const long long *band_idx, const long long *n_band,
+                           double step, double *new_u, double *gmag_out,
+                           unsigned long long *stats, void *stream);
+
 /* ---- band rebuild: distance_transform(u, band, dx) (lsml/util/distance_transform.py:5-59) --- */
 long long lsml_fmm_workspace_bytes(long long total);
 int lsml_fmm_workspace_init(long long total, void *workspace, void *stream);

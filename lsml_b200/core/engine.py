@@ -389,11 +389,13 @@ class BandEngine:
                     reg.n_features, self.program.nfeat))
             self.compute_features()
             reg.predict_into(self.X, self.n_band_dev, self.vel)
-            _lib.check(_lib.lib.lsml_band_update(
+            # u[mask] += step*v*|Du| and, in the same scatter, the exact {u > 0} statistics of the
+            # new u (no dense recount)
+            _lib.check(_lib.lib.lsml_band_update_stats(
                 ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
                 _lib.ptr(self.u), _lib.ptr(self.vel), _lib.ptr(self.band_idx),
                 _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)), _lib.ptr(self.new_u),
-                _lib.c_p(0), ctypes.c_int(1), self._stream()), "band_update")
+                _lib.c_p(0), _lib.ptr(self.stats), self._stream()), "band_update")
             # band indices of THIS iteration (the rebuild below overwrites band_idx); together
             # with new_u[:nb] this is the sparse record `segment` rebuilds the iterates from
             self._last_idx = self.band_idx[:nb].clone()
@@ -402,7 +404,6 @@ class BandEngine:
                     self.history = []
                 self.history.append((self._last_idx, self.new_u[:nb].clone()))
             self.band_voxel_iterations += nb
-            self._global_stats()
             if rebuild:
                 self._rebuild_band(from_band=True)
             else:

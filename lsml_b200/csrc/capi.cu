@@ -285,7 +285,16 @@ int lsml_band_update(int ndim, const int* shape, long long batch, const double* 
                      const double* vel, const long long* band_idx, const long long* n_band,
                      double step, double* new_u, double* gmag_out, int apply, void* stream) {
     GEOM(g);
-    return band_update(g, u, vel, band_idx, n_band, step, new_u, gmag_out, apply, (cudaStream_t)stream);
+    return band_update(g, u, vel, band_idx, n_band, step, new_u, gmag_out, apply, nullptr,
+                       (cudaStream_t)stream);
+}
+int lsml_band_update_stats(int ndim, const int* shape, long long batch, const double* dx, double* u,
+                           const double* vel, const long long* band_idx, const long long* n_band,
+                           double step, double* new_u, double* gmag_out,
+                           unsigned long long* stats, void* stream) {
+    GEOM(g);
+    return band_update(g, u, vel, band_idx, n_band, step, new_u, gmag_out, 1, stats,
+                       (cudaStream_t)stream);
 }
 long long lsml_fmm_workspace_bytes(long long total) { return fmm_workspace_bytes(total); }
 int lsml_fmm_workspace_init(long long total, void* workspace, void* stream) {

@@ -62,7 +62,7 @@ int mlp_predict(const double* X, const i64* n_band, const double* mean, const do
 // update.cu
 int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx,
                 const i64* n_band, double step, double* new_u, double* gmag_out, int apply,
-                cudaStream_t s);
+                u64* stats, cudaStream_t s);
 
 // fmm.cu
 i64 fmm_workspace_bytes(i64 total);

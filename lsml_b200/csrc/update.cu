@@ -72,18 +72,46 @@ band_update_kernel(const double* __restrict__ u, const double* __restrict__ vel,
     }
 }
 
+// Scatter of the new values.  u changes only here, so the exact {u > 0} statistics that Size /
+// Moments / centre of mass need (features.cu:global_stats_kernel -- integer sums, hence
+// order-independent) are kept up to date from the voxels that change sign class instead of a
+// dense pass over the grid every iteration: stats[item*8 + {0 count, 1..3 sum idx, 4..6 sum
+// idx^2, 7 zeros}].
 __global__ void __launch_bounds__(256)
 band_apply_kernel(double* __restrict__ u, const double* __restrict__ new_u,
-                  const i64* __restrict__ band_idx, const i64* __restrict__ n_band) {
+                  const i64* __restrict__ band_idx, const i64* __restrict__ n_band, BandGeom g,
+                  u64* __restrict__ stats) {
     const i64 nb = *n_band;
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
-         b += (i64)gridDim.x * blockDim.x)
-        u[__ldg(band_idx + b)] = __ldg(new_u + b);
+         b += (i64)gridDim.x * blockDim.x) {
+        const i64 l = __ldg(band_idx + b);
+        const double nv = __ldg(new_u + b);
+        if (stats != nullptr) {
+            const double ov = u[l];
+            const int pos = (nv > 0.0) - (ov > 0.0), zer = (nv == 0.0) - (ov == 0.0);
+            if (pos | zer) {
+                const i64 item = l / g.voxels, loc = l - item * g.voxels;
+                u64* st = stats + item * 8;
+                if (pos) {
+                    const u64 k = (u64)(loc % g.n2);
+                    const i64 r = loc / g.n2;
+                    const u64 j = (u64)(r % g.n1), i = (u64)(r / g.n1);
+                    const u64 sgn = pos > 0 ? (u64)1 : ~(u64)0;            // +1 / -1 (mod 2^64)
+                    atomicAdd(st + 0, sgn);
+                    atomicAdd(st + 1, sgn * i); atomicAdd(st + 2, sgn * j); atomicAdd(st + 3, sgn * k);
+                    atomicAdd(st + 4, sgn * i * i); atomicAdd(st + 5, sgn * j * j);
+                    atomicAdd(st + 6, sgn * k * k);
+                }
+                if (zer) atomicAdd(st + 7, zer > 0 ? (u64)1 : ~(u64)0);
+            }
+        }
+        u[l] = nv;
+    }
 }
 
 int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx,
                 const i64* n_band, double step, double* new_u, double* gmag_out, int apply,
-                cudaStream_t s) {
+                u64* stats, cudaStream_t s) {
     BandGeom bg;
     bg.ndim = g.ndim; bg.n0 = g.n[0]; bg.n1 = g.n[1]; bg.n2 = g.n[2]; bg.voxels = g.voxels;
     bg.dx0 = g.dx[0]; bg.dx1 = g.dx[1]; bg.dx2 = g.dx[2];
@@ -91,7 +119,7 @@ int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx
     band_update_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, vel, band_idx, n_band, bg, step, new_u, gmag_out);
     LSML_LAUNCH_CHECK("band_update_kernel");
     if (apply) {
-        band_apply_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, new_u, band_idx, n_band);
+        band_apply_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, new_u, band_idx, n_band, bg, stats);
         LSML_LAUNCH_CHECK("band_apply_kernel");
     }
     return 0;

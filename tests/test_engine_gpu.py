@@ -226,3 +226,37 @@ def test_full_step_against_oracle(oracle, shape, dx):
             assert np.array_equal(m_g[b], m_o[b]), (it, b, (m_g[b] != m_o[b]).sum())
             assert np.allclose(u_g[b], u_o[b], rtol=1e-12, atol=1e-12), \
                 np.abs(u_g[b] - u_o[b]).max()
+
+
+@pytest.mark.parametrize("shape,dx", [((61, 47), (1.0, 1.0)), ((26, 31, 28), (1.0, 1.0, 1.0))])
+def test_incremental_statistics_and_sparse_rebuild_match_dense(shape, dx):
+    """After several iterations the {u>0} statistics maintained from sign changes in the scatter
+    kernel equal a dense recount, and the band found from the previous band (sparse interface
+    search, hinted schedule) equals the band of a from-scratch dense rebuild of the same u."""
+    from sklearn.linear_model import LinearRegression
+    specs = [("image_sample", 0.0), ("size",)]
+    eng, imgs, us = build_engine(shape, 3, dx, specs, normalize=True, seed=5)
+    reg = LinearRegression().fit(np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]),
+                                 np.array([0.3, 1.3, 0.3]))          # v = img + 0.3
+    for it in range(6):
+        eng.step(reg, 0.45)
+        stats_inc = eng.stats.cpu().numpy().copy()
+        mask_inc = eng.mask.cpu().numpy().copy()
+        idx_inc = eng.band_idx[:eng.n_band].cpu().numpy().copy()
+        u_now = eng.u.cpu().numpy()
+        want = np.zeros_like(stats_inc)
+        for b in range(3):
+            pos = u_now[b] > 0
+            coords = np.nonzero(pos)
+            want[b, 0] = pos.sum()
+            for a in range(len(shape)):
+                want[b, 1 + 3 - len(shape) + a] = coords[a].sum()
+                want[b, 4 + 3 - len(shape) + a] = (coords[a].astype(np.int64) ** 2).sum()
+            want[b, 7] = (u_now[b] == 0).sum()
+        assert np.array_equal(stats_inc, want), (it, stats_inc, want)
+        # dense rebuild of the same u on a fresh engine
+        from lsml_b200.core.engine import BandEngine
+        ref = BandEngine(shape, 3, dx=dx, band=eng.band, specs=[])
+        ref.set_level_sets(u_now)
+        assert np.array_equal(ref.mask.cpu().numpy(), mask_inc), it
+        assert np.array_equal(ref.band_idx[:ref.n_band].cpu().numpy(), idx_inc), it
