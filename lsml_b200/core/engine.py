@@ -126,6 +126,24 @@ class FeatureProgram:
         return self.planes.index(key)
 
 
+class _Phase:
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.timers is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.eng.timers is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.eng.timers.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
 class BandEngine:
     def __init__(self, shape, batch, dx=None, band=3.0, specs=(), device="cuda"):
         _lib.require_cuda()
@@ -155,6 +173,7 @@ class BandEngine:
             self.n_band_dev = torch.zeros(1, dtype=i64, device=d)
             self.item_offsets = torch.zeros(self.batch + 1, dtype=i64, device=d)
             self.band_idx = torch.zeros(1, dtype=i64, device=d)
+            self._band_idx_prev = torch.zeros(1, dtype=i64, device=d)
             npl = max(len(self.program.planes), 1)
             self.band_mean = torch.zeros((self.batch, npl), dtype=f64, device=d)
             self.band_std = torch.zeros((self.batch, npl), dtype=f64, device=d)
@@ -182,10 +201,22 @@ class BandEngine:
         self.history = None           # list of (band_idx, new_u) per iteration when recording
         self.last_fmm_counters = None
         self._band_is_rebuilt = False
+        self.timers = None            # dict while bench.py collects per-phase device times
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return _lib.current_stream()
+
+    def _phase(self, name):
+        """CUDA-event bracket around one phase of an iteration, active only while
+        ``self.timers`` is a dict (bench.py's per-kernel evidence pass); a no-op otherwise."""
+        return _Phase(self, name)
+
+    def phase_times_ms(self):
+        """{phase: (launch groups, total ms)} of the brackets recorded so far (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        return {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v)))
+                for k, v in (self.timers or {}).items()}
 
     def _ensure_capacity(self, n):
         if n <= self._cap:
@@ -302,13 +333,14 @@ class BandEngine:
             self.mask.zero_()
             _lib.check(_lib.lib.lsml_fmm_workspace_init(
                 _lib.c_i64(self.total), _lib.ptr(self._ws_fmm), self._stream()), "fmm_init")
-        _lib.check(_lib.lib.lsml_fmm_rebuild_from_band(
-            ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
-            _lib.ptr(self.u), ctypes.c_double(self.band), _lib.ptr(self.stats),
-            _lib.ptr(self.mask), _lib.ptr(dist_out), _lib.ptr(self._ws_fmm),
-            _lib.ptr(self.band_idx if from_band else None),
-            _lib.ptr(self.n_band_dev if from_band else None), self._stream()),
-            "fmm_rebuild")
+        with self._phase("rebuild"):
+            _lib.check(_lib.lib.lsml_fmm_rebuild_from_band(
+                ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
+                _lib.ptr(self.u), ctypes.c_double(self.band), _lib.ptr(self.stats),
+                _lib.ptr(self.mask), _lib.ptr(dist_out), _lib.ptr(self._ws_fmm),
+                _lib.ptr(self.band_idx if from_band else None),
+                _lib.ptr(self.n_band_dev if from_band else None), self._stream()),
+                "fmm_rebuild")
         self._compact()
         self._band_is_rebuilt = True
 
@@ -333,15 +365,22 @@ class BandEngine:
         return dist
 
     def _compact(self):
+        # two index buffers, swapped on every compaction: the previous band's indices stay valid
+        # (they are the sparse record of the iteration that just ran) without a copy
+        self.band_idx, self._band_idx_prev = self._band_idx_prev, self.band_idx
         if self.band_idx.numel() < self.total:
             # capacity: the band can be the whole grid (band == 0 or u == 0 everywhere)
             self.band_idx = torch.empty(self.total, dtype=torch.int64, device=self.device)
+        with self._phase("compact"):
+            self._compact_launch()
+        self.n_band = int(self.n_band_dev.item())      # one host sync per iteration (capacity)
+        self._ensure_capacity(self.n_band)
+
+    def _compact_launch(self):
         _lib.check(_lib.lib.lsml_compact_mask(
             _lib.c_i64(self.total), _lib.c_i64(self.voxels), _lib.ptr(self.mask),
             _lib.ptr(self.band_idx), _lib.ptr(self.n_band_dev), _lib.ptr(self.item_offsets),
             _lib.ptr(self._ws_compact), self._stream()), "compact_mask")
-        self.n_band = int(self.n_band_dev.item())      # one host sync per iteration (capacity)
-        self._ensure_capacity(self.n_band)
 
     # ------------------------------------------------------------------ features
     def compute_features(self):
@@ -387,22 +426,27 @@ class BandEngine:
             if reg.n_features != self.program.nfeat:
                 raise ValueError("regressor expects {} features, feature map has {}".format(
                     reg.n_features, self.program.nfeat))
-            self.compute_features()
-            reg.predict_into(self.X, self.n_band_dev, self.vel)
+            with self._phase("features"):
+                self.compute_features()
+            with self._phase("predict"):
+                reg.predict_into(self.X, self.n_band_dev, self.vel)
             # u[mask] += step*v*|Du| and, in the same scatter, the exact {u > 0} statistics of the
             # new u (no dense recount)
-            _lib.check(_lib.lib.lsml_band_update_stats(
-                ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
-                _lib.ptr(self.u), _lib.ptr(self.vel), _lib.ptr(self.band_idx),
-                _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)), _lib.ptr(self.new_u),
-                _lib.c_p(0), _lib.ptr(self.stats), self._stream()), "band_update")
-            # band indices of THIS iteration (the rebuild below overwrites band_idx); together
-            # with new_u[:nb] this is the sparse record `segment` rebuilds the iterates from
-            self._last_idx = self.band_idx[:nb].clone()
+            with self._phase("update"):
+                _lib.check(_lib.lib.lsml_band_update_stats(
+                    ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
+                    _lib.ptr(self.u), _lib.ptr(self.vel), _lib.ptr(self.band_idx),
+                    _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)),
+                    _lib.ptr(self.new_u), _lib.c_p(0), _lib.ptr(self.stats), self._stream()),
+                    "band_update")
+            # band indices of THIS iteration; together with new_u[:nb] this is the sparse record
+            # `segment` rebuilds the iterates from.  The rebuild below compacts into the OTHER
+            # index buffer, so this view stays valid until the next iteration's rebuild.
+            self._last_idx = self.band_idx[:nb]
             if record:
                 if self.history is None:
                     self.history = []
-                self.history.append((self._last_idx, self.new_u[:nb].clone()))
+                self.history.append((self._last_idx.clone(), self.new_u[:nb].clone()))
             self.band_voxel_iterations += nb
             if rebuild:
                 self._rebuild_band(from_band=True)
