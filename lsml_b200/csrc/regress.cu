@@ -21,7 +21,9 @@
 // tree by tree with the current tree staged in shared memory and 4 voxels per thread was 2x
 // SLOWER (738 us vs 388 us): the plain kernel runs at full occupancy (64 warps/SM) and is bound
 // by L1 tag throughput on divergent node fetches, which the staged version only replaces by
-// shared-memory bank conflicts at a quarter of the occupancy.
+// shared-memory bank conflicts at a quarter of the occupancy.  Walking 2 or 4 trees per thread
+// at once (independent chains for latency hiding) was also slower (578 / 543 us): the limit is
+// the number of divergent L1 sectors per warp-load, not the latency of a single chain.
 #include "lsml_internal.h"
 
 namespace lsml {

@@ -77,35 +77,61 @@ band_update_kernel(const double* __restrict__ u, const double* __restrict__ vel,
 // order-independent) are kept up to date from the voxels that change sign class instead of a
 // dense pass over the grid every iteration: stats[item*8 + {0 count, 1..3 sum idx, 4..6 sum
 // idx^2, 7 zeros}].
-__global__ void __launch_bounds__(256)
+// The per-thread deltas are reduced over the CTA before they touch the counters (same-address
+// atomics serialise in L2: one atomic per flipped voxel cost 90 us at 256^3).  Band indices are
+// ascending, so a CTA's contiguous chunk of the band belongs to one item except at item
+// boundaries, where the partial sums are flushed early.
+constexpr int APPLY_THREADS = 256;
+
+__device__ __forceinline__ void flush_stats(u64 (&d)[8], i64 item, u64* __restrict__ stats) {
+    __shared__ u64 red[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const u64 t = block_sum<u64>(d[q], red);
+        if (threadIdx.x == 0 && t) atomicAdd(stats + item * 8 + q, t);
+        d[q] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(APPLY_THREADS)
 band_apply_kernel(double* __restrict__ u, const double* __restrict__ new_u,
                   const i64* __restrict__ band_idx, const i64* __restrict__ n_band, BandGeom g,
                   u64* __restrict__ stats) {
     const i64 nb = *n_band;
-    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
-         b += (i64)gridDim.x * blockDim.x) {
-        const i64 l = __ldg(band_idx + b);
-        const double nv = __ldg(new_u + b);
-        if (stats != nullptr) {
-            const double ov = u[l];
+    if (stats == nullptr) {
+        for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
+             b += (i64)gridDim.x * blockDim.x)
+            u[__ldg(band_idx + b)] = __ldg(new_u + b);
+        return;
+    }
+    // contiguous chunk of the band per CTA
+    const i64 per = (nb + gridDim.x - 1) / gridDim.x;
+    const i64 lo = min(nb, (i64)blockIdx.x * per), hi = min(nb, lo + per);
+    if (lo >= hi) return;
+    const i64 first_item = __ldg(band_idx + lo) / g.voxels;
+    const i64 last_item = __ldg(band_idx + hi - 1) / g.voxels;
+    for (i64 item = first_item; item <= last_item; ++item) {      // one pass in all but edge cases
+        u64 d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const i64 ibase = item * g.voxels;
+        for (i64 b = lo + threadIdx.x; b < hi; b += APPLY_THREADS) {
+            const i64 l = __ldg(band_idx + b);
+            const i64 loc = l - ibase;
+            if (loc < 0 || loc >= g.voxels) continue;             // another item's voxel
+            const double nv = __ldg(new_u + b), ov = u[l];
             const int pos = (nv > 0.0) - (ov > 0.0), zer = (nv == 0.0) - (ov == 0.0);
-            if (pos | zer) {
-                const i64 item = l / g.voxels, loc = l - item * g.voxels;
-                u64* st = stats + item * 8;
-                if (pos) {
-                    const u64 k = (u64)(loc % g.n2);
-                    const i64 r = loc / g.n2;
-                    const u64 j = (u64)(r % g.n1), i = (u64)(r / g.n1);
-                    const u64 sgn = pos > 0 ? (u64)1 : ~(u64)0;            // +1 / -1 (mod 2^64)
-                    atomicAdd(st + 0, sgn);
-                    atomicAdd(st + 1, sgn * i); atomicAdd(st + 2, sgn * j); atomicAdd(st + 3, sgn * k);
-                    atomicAdd(st + 4, sgn * i * i); atomicAdd(st + 5, sgn * j * j);
-                    atomicAdd(st + 6, sgn * k * k);
-                }
-                if (zer) atomicAdd(st + 7, zer > 0 ? (u64)1 : ~(u64)0);
+            if (pos) {
+                const u64 k = (u64)(loc % g.n2);
+                const i64 r = loc / g.n2;
+                const u64 j = (u64)(r % g.n1), i = (u64)(r / g.n1);
+                const u64 sgn = pos > 0 ? (u64)1 : ~(u64)0;        // +1 / -1 (mod 2^64)
+                d[0] += sgn;
+                d[1] += sgn * i; d[2] += sgn * j; d[3] += sgn * k;
+                d[4] += sgn * i * i; d[5] += sgn * j * j; d[6] += sgn * k * k;
             }
+            if (zer) d[7] += zer > 0 ? (u64)1 : ~(u64)0;
+            u[l] = nv;
         }
-        u[l] = nv;
+        flush_stats(d, item, stats);
     }
 }
 
@@ -119,7 +145,7 @@ int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx
     band_update_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, vel, band_idx, n_band, bg, step, new_u, gmag_out);
     LSML_LAUNCH_CHECK("band_update_kernel");
     if (apply) {
-        band_apply_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, new_u, band_idx, n_band, bg, stats);
+        band_apply_kernel<<<LSML_SMS * 4, APPLY_THREADS, 0, s>>>(u, new_u, band_idx, n_band, bg, stats);
         LSML_LAUNCH_CHECK("band_apply_kernel");
     }
     return 0;
