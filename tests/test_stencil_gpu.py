@@ -129,3 +129,51 @@ def test_band_compaction_matches_numpy_order(shape, batch, density):
     assert np.array_equal(idx.cpu().numpy(), want)
     per_item = mask.reshape(batch, -1).sum(axis=1)
     assert np.array_equal(offsets.cpu().numpy(), np.r_[0, np.cumsum(per_item)])
+
+
+@pytest.mark.parametrize("shape,dx", [((20, 17, 64), None), ((19, 24, 128), (1.0, 1.0, 1.0)),
+                                      ((18, 9, 96), (0.5, 2.0, 4.0)), ((21, 16, 72), (0.7, 1.3, 1.1)),
+                                      ((35, 8, 64), None), ((2, 2, 64), None)])
+def test_vectorised_march_kernel_bit_exact_all_inputs(oracle, shape, dx):
+    """The 16-byte vectorised 3-D kernel (even last axis >= 64) evaluates the upwind sum in a
+    scaled form; it must still be bit-identical to the reference for ordinary values, with and
+    without masks, and for the values where the scaled form is not exact by itself (subnormal
+    squares, infinities, NaNs, exact zeros), which take the kernel's exact slow path."""
+    import torch
+    from lsml_b200.gradient import masked_gradient as mg
+    rs = np.random.RandomState(11)
+    arr = rs.randn(*shape)
+    nu = rs.randn(*shape)
+    dxa = None if dx is None else np.asarray(dx)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for mask in (None, rs.rand(*shape) > 0.3, rs.rand(*shape) > 0.97):
+        got = mg.gradient_magnitude_osher_sethian(t(arr), t(nu), mask=None if mask is None else t(mask),
+                                                  dx=dxa).cpu().numpy()
+        want = oracle.gmag_os(arr, nu, mask, dxa, use_reference=oracle.reference_lib() is not None)
+        assert np.array_equal(got, want), np.abs(got - want).max()
+    # special values
+    sp = arr.copy()
+    flat = sp.ravel()
+    idx = rs.choice(flat.size, size=400, replace=flat.size < 400)
+    flat[idx[:80]] *= 1e-170                  # squares underflow / are subnormal
+    flat[idx[80:160]] *= 1e-200
+    flat[idx[160:200]] = 0.0
+    flat[idx[200:240]] = np.inf
+    flat[idx[240:280]] = -np.inf
+    flat[idx[280:320]] = np.nan
+    flat[idx[320:360]] *= 1e160               # squares overflow
+    sp[..., :8] = 3.0                         # flat region: exact zeros of the gradient
+    tiny = arr * 1e-165                       # everything tiny: sum in the subnormal range
+    for a in (sp, tiny):
+        with np.errstate(all="ignore"):
+            got = mg.gradient_magnitude_osher_sethian(t(a), t(nu), dx=dxa).cpu().numpy()
+            want = oracle.gmag_os(a, nu, None, dxa, use_reference=oracle.reference_lib() is not None)
+        assert np.array_equal(got, want, equal_nan=True), \
+            np.flatnonzero(~((got == want) | (np.isnan(got) & np.isnan(want))).ravel())[:10]
+    # float32 build of the same kernel (last axis % 4 == 0 and >= 128 takes the vector path)
+    if shape[2] % 4 == 0:
+        a32 = np.tile(arr, (1, 1, 2)).astype(np.float32)
+        n32 = np.tile(nu, (1, 1, 2)).astype(np.float32)
+        got = mg.gradient_magnitude_osher_sethian(t(a32), t(n32), dx=dxa).cpu().numpy()
+        want = oracle.gmag_os(a32.astype(np.float64), n32.astype(np.float64), None, dxa)
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-6)
