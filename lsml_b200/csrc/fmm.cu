@@ -53,6 +53,10 @@ struct FmmGeom {
     // list entries are "packed coordinates" (item, i, j, k) in bit fields: k at bit 0, j at sh1,
     // i at sh0, item at shb -- decoding is shifts and masks, never a 64-bit division
     int sh1, sh0, shb;
+    // slab decomposition: this rank OWNS the planes [own_lo, own_hi) of (padded) axis 0 and only
+    // ever freezes / queues / evaluates voxels there; the other planes of the local grid are
+    // halo copies of the neighbour ranks' voxels (whole grid = [0, n0) for a single GPU)
+    int own_lo, own_hi;
 };
 
 static int bits_for(i64 n) { int b = 0; while (((i64)1 << b) < n) ++b; return b; }
@@ -64,6 +68,7 @@ static int make_fmm_geom(const Geom& g, FmmGeom& fg) {
     fg.sh0 = fg.sh1 + bits_for(g.n[1]);
     fg.shb = fg.sh0 + bits_for(g.n[0]);
     if (fg.shb + bits_for(g.batch) > 62) { set_error("grid too large for packed band entries"); return 1; }
+    fg.own_lo = 0; fg.own_hi = g.n[0];
     return 0;
 }
 
@@ -81,6 +86,8 @@ struct FmmCounters {      // device-resident
                           // during the one after (no reader can race a writer, no extra barrier)
     i64 pub_begin, pub_end;     // window published by CTA 0 after a run of single-CTA sweeps
     i64 pub_sweep, pub_rix;     // ... and the sweep number / executed-sweep count reached
+    i64 resume_sweep, resume_rix, resume_begin;   // where the next march launch of this rebuild
+                                // continues (slab decomposition: several launches per rebuild)
     i64 overflow[3];      // rotating "a push was dropped" flags => next sweep scans the list
     // ---- schedule hints carried from one rebuild to the next (see Aux::lvl)
     i64 gen;              // rebuild counter (low 8 bits tag the hints)
@@ -177,6 +184,7 @@ fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap) {
     if (t == 0) {
         ctr->n_init = 0; ctr->n_cand = 0; ctr->tail_sweeps = 0; ctr->sweeps = 0; ctr->converged = 0;
         ctr->replays = 0; ctr->tail3[0] = 0; ctr->tail3[1] = 0; ctr->tail3[2] = 0; ctr->pub_begin = 0; ctr->pub_end = 0; ctr->pub_sweep = 0; ctr->pub_rix = 0;
+        ctr->resume_sweep = 1; ctr->resume_rix = 1; ctr->resume_begin = 0;
         ctr->overflow[0] = 0; ctr->overflow[1] = 0; ctr->overflow[2] = 0;
         ctr->last_bucket = 0;
         ctr->gen = ctr->gen + 1;
@@ -236,29 +244,32 @@ __device__ __forceinline__ bool init_distance(const double* __restrict__ u, i64 
 // are left untouched => empty mask.  stats[item*8+0] = #(u>0), stats[item*8+7] = #(u==0).
 __device__ __forceinline__ bool item_has_contour(const u64* __restrict__ stats, i64 item,
                                                  const FmmGeom& g) {
+    if (stats == nullptr) return true;            // the caller decided (slab decomposition)
     const u64 npos = stats[item * 8 + 0], nzero = stats[item * 8 + 7];
     return nzero == (u64)g.voxels || !(npos == 0 || npos == (u64)g.voxels);
 }
 
-// Dense pass over u (first rebuild of a level set): 8 B/voxel read, HBM-bound.
+// Dense pass over the planes [p_lo, p_hi) of u (first rebuild of a level set, and the two
+// boundary planes of a slab on every rebuild): 8 B/voxel read, HBM-bound.
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 fmm_init_kernel(const double* __restrict__ u, double* __restrict__ T, u8* __restrict__ mask,
                 i64* __restrict__ list, FmmGeom g, const u64* __restrict__ stats,
-                FmmCounters* ctr) {
-    // blockIdx.x = item*n0 + i, blockIdx.y = j tile, blockIdx.z = k tile (no per-thread division)
+                FmmCounters* ctr, int p_lo, int p_hi) {
+    // blockIdx.x = item*(p_hi-p_lo) + (i-p_lo), blockIdx.y = j tile, blockIdx.z = k tile
     const int k = blockIdx.z * blockDim.x + threadIdx.x;
     const int cj = blockIdx.y * blockDim.y + threadIdx.y;
     if (k >= g.n2 || cj >= g.n1) return;
-    const i64 item = blockIdx.x / (unsigned)g.n0;
-    const int ci = (int)(blockIdx.x % (unsigned)g.n0);
+    const unsigned np = (unsigned)(p_hi - p_lo);
+    const i64 item = blockIdx.x / np;
+    const int ci = p_lo + (int)(blockIdx.x % np);
     if (!item_has_contour(stats, item, g)) return;
-    const i64 l = ((i64)blockIdx.x * g.n1 + cj) * g.n2 + k;
+    const i64 l = (((i64)item * g.n0 + ci) * g.n1 + cj) * g.n2 + k;
     const int coord[3] = {ci, cj, k};
     double d;
     if (!init_distance<NDIM>(u, l, coord, g, d)) return;
+    if (!claim(mask, l, ST_INIT)) return;
     T[l] = d;
-    mask[l] = ST_INIT;
     const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_init), (u64)1);
     list[pos] = encode(item, ci, cj, k, g);
 }
@@ -301,6 +312,7 @@ fmm_init_band_kernel(const double* __restrict__ u, double* __restrict__ T, u8* _
             for (int j = -1; j < 2; j += 2) {
                 const int cc = coord[ax] + j;
                 if (cc < 0 || cc >= ext[ax]) continue;
+                if (ax == 0 && (cc < g.own_lo || cc >= g.own_hi)) continue;   // the owner does it
                 const i64 n = l + j * st[ax];
                 if (!(c * __ldg(u + n) < 0)) continue;
                 if (__ldcg(mask + n) != 0) continue;             // already claimed
@@ -408,6 +420,7 @@ __device__ __forceinline__ void expose_neighbours(i64 e, i64 l, const int (&coor
         for (int j = -1; j < 2; j += 2) {
             const int cc = coord[ax] + j;
             if (cc < 0 || cc >= ext[ax]) continue;
+            if (ax == 0 && (cc < g.own_lo || cc >= g.own_hi)) continue;       // a halo copy
             const i64 n = l + j * st[ax];
             if (__ldcg(mask + n) == 0 && claim(mask, n, ST_CAND)) {
                 const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)1);
@@ -721,7 +734,10 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const int cc = coord[ax] + j;
         s[k] = 0xff;
-        if (cc >= 0 && cc < ext[ax]) { valid |= 1u << k; s[k] = __ldcg(mask + l + j * st[ax]); }
+        if (cc >= 0 && cc < ext[ax] && (ax != 0 || (cc >= g.own_lo && cc < g.own_hi))) {
+            valid |= 1u << k;                     // (halo copies are neither queued nor claimed)
+            s[k] = __ldcg(mask + l + j * st[ax]);
+        }
     }
     // phase 2: scheduling records of the candidates; claims of far direct neighbours
     uint2 a[NS];
@@ -829,7 +845,7 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
 template <int NDIM>
 __global__ void __launch_bounds__(FMM_THREADS, FMM_MIN_BLOCKS)
 fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i64* list, i64 cap,
-                 FmmGeom g, double band, FmmCounters* ctr, Ring ring, i64* park) {
+                 FmmGeom g, double band, FmmCounters* ctr, Ring ring, i64* park, int finalize) {
     cg::grid_group grid = cg::this_grid();
     __shared__ i64 queue[FMM_WARPS][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -844,12 +860,14 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     const bool hints = ctr->use_hints != 0;
     const unsigned gen_tag = (unsigned)((ctr->gen & 0xff) << 8);
     const unsigned hint_tag = hints ? (unsigned)(((ctr->gen - 1) & 0xff) << 8) : 0xffffffffu;
-    unsigned sweep = 1u;               // epoch of the work set being consumed
-    unsigned rix = 1u;                 // executed-sweep counter (rotation index of tail3)
+    // (a rebuild is one launch on a single GPU; a slab-decomposed rebuild launches again after
+    // every halo exchange and continues where the previous launch stopped)
+    unsigned sweep = (unsigned)ctr->resume_sweep;      // epoch of the work set being consumed
+    unsigned rix = (unsigned)ctr->resume_rix;          // executed-sweep counter (rotation of tail3)
     int barriers = 0, tail_sweeps = 0;
     bool converged = false;
-    i64 begin = 0, end = vtail[1];     // the seed kernel queued sweep 1
-    bool scan = vovf[2] != 0;          // ... and reports overflow into slot 2
+    i64 begin = ctr->resume_begin, end = begin + vtail[rix % 3u];   // queued by seed / requeue
+    bool scan = vovf[2] != 0;          // ... which report overflow into slot 2
     i64 nreplay = 0;
     while (barriers < FMM_MAX_SWEEPS) {
         i64 nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;       // bucket of this sweep
@@ -981,11 +999,13 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     }
     // final mask: candidates frozen by the marcher are those with |d| <= band
     const i64 nc = *reinterpret_cast<volatile i64*>(&ctr->n_cand);
-    for (i64 t = tid; t < nc; t += nthreads) {
-        int coord[3];
-        const i64 l = decode(list[cap - 1 - t], g, coord);
-        if (fabs(__ldcg(T + l)) <= band) mask[l] = 1;
-        else { mask[l] = 0; T[l] = pos_inf(); }
+    if (finalize) {
+        for (i64 t = tid; t < nc; t += nthreads) {
+            int coord[3];
+            const i64 l = decode(list[cap - 1 - t], g, coord);
+            if (fabs(__ldcg(T + l)) <= band) mask[l] = 1;
+            else { mask[l] = 0; T[l] = pos_inf(); }
+        }
     }
     if (nreplay) atomicAdd(reinterpret_cast<u64*>(&ctr->replays), (u64)nreplay);
     if (tid == 0) {
@@ -993,7 +1013,83 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
         ctr->converged = converged ? 1 : 0;
         ctr->prev_init = ctr->n_init;
         ctr->prev_cand = nc;
+        ctr->resume_sweep = (i64)sweep;
+        ctr->resume_rix = (i64)rix;
+        ctr->resume_begin = begin;
     }
+}
+
+// ---- slab decomposition helpers ----------------------------------------------------------------
+// After the halo planes were refreshed from the neighbour ranks: every owned candidate within two
+// planes of a cut looks again, and far owned voxels next to a (possibly remote) frozen or in-band
+// voxel become candidates -- exactly what the remote voxel's own thread does for neighbours it
+// owns.  Entries are queued for the sweep the next march launch starts with.
+template <int NDIM>
+__global__ void __launch_bounds__(256)
+fmm_requeue_kernel(const double* T, Aux* aux, u8* mask, i64* list, i64 cap, FmmGeom g,
+                   double band, FmmCounters* ctr, Ring ring, i64* park) {
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const int cj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= g.n2 || cj >= g.n1) return;
+    // blockIdx.x enumerates the (up to) four boundary planes: lo, lo+1, hi-2, hi-1
+    const int own = g.own_hi - g.own_lo;
+    int ci;
+    if (blockIdx.x == 0) ci = g.own_lo;
+    else if (blockIdx.x == 1) ci = g.own_lo + 1;
+    else if (blockIdx.x == 2) ci = g.own_hi - 2;
+    else ci = g.own_hi - 1;
+    if (ci < g.own_lo || ci >= g.own_hi) return;
+    if (blockIdx.x >= 2 && ci < g.own_lo + 2) return;           // thin slab: planes already done
+    if (own <= 0) return;
+    const bool near_lo = g.own_lo > 0 && ci < g.own_lo + 2;      // a cut, not the end of the grid
+    const bool near_hi = g.own_hi < g.n0 && ci >= g.own_hi - 2;
+    if (!near_lo && !near_hi) return;
+    const i64 l = ((i64)ci * g.n1 + cj) * g.n2 + k;
+    const int coord[3] = {ci, cj, k};
+    const i64 e = encode(0, ci, cj, k, g);
+    const unsigned rix = (unsigned)ctr->resume_rix;
+    const Sched sc{aux, ring, park, ctr, ctr->resume_begin, ctr->resume_begin,
+                   (unsigned)ctr->resume_sweep, (int)(rix % 3u), 0xffffffffu, 2};
+    const u8 st = __ldcg(mask + l);
+    if (st & ST_CAND) { enqueue(sc, l, e); return; }
+    if (st != 0) return;
+    const int ext[3] = {g.n0, g.n1, g.n2};
+    const i64 stv[3] = {(i64)g.n1 * g.n2, (i64)g.n2, 1};
+    bool exposed = false;
+#pragma unroll
+    for (int ax = 3 - NDIM; ax < 3; ++ax)
+#pragma unroll
+        for (int j = -1; j < 2; j += 2) {
+            const int cc = coord[ax] + j;
+            if (cc < 0 || cc >= ext[ax]) continue;
+            const i64 n = l + j * stv[ax];
+            const u8 sn = __ldcg(mask + n);
+            if (sn == ST_INIT || ((sn & ST_CAND) && fabs(__ldcg(T + n)) <= band)) exposed = true;
+        }
+    if (exposed && claim(mask, l, ST_CAND)) {
+        const i64 pos = (i64)atomicAdd(reinterpret_cast<u64*>(&ctr->n_cand), (u64)1);
+        list[cap - 1 - pos] = e;
+        enqueue(sc, l, e);
+    }
+}
+
+// the final mask of a slab-decomposed rebuild (the single-GPU march does this itself)
+__global__ void __launch_bounds__(256)
+fmm_finalize_kernel(double* T, u8* mask, const i64* __restrict__ list, i64 cap, FmmGeom g,
+                    double band, const FmmCounters* ctr) {
+    const i64 nc = ctr->n_cand;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < nc;
+         t += (i64)gridDim.x * blockDim.x) {
+        int coord[3];
+        const i64 l = decode(list[cap - 1 - t], g, coord);
+        if (fabs(T[l]) <= band) mask[l] = 1;
+        else { mask[l] = 0; T[l] = pos_inf(); }
+    }
+}
+
+// number of entries waiting for the next march launch -> a device int64 (for the all-reduce)
+__global__ void fmm_pending_kernel(const FmmCounters* ctr, i64* out) {
+    *out = ctr->tail3[ctr->resume_rix % 3] + (ctr->overflow[2] ? 1 : 0);
 }
 
 // dist_out = T where mask else 0  (skfmm masked data after post-processing)
@@ -1057,7 +1153,7 @@ static int g_march_blocks[4] = {0, 0, 0, 0};
 
 template <int NDIM>
 static int march_launch(const double* u, const FmmWorkspace& w, u8* mask, i64 cap, FmmGeom fg,
-                        double band, cudaStream_t s) {
+                        double band, int finalize, cudaStream_t s) {
     if (g_march_blocks[NDIM] == 0) {
         int per_sm = 0, dev = 0, sms = 0;
         LSML_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmm_march_kernel<NDIM>,
@@ -1071,7 +1167,8 @@ static int march_launch(const double* u, const FmmWorkspace& w, u8* mask, i64 ca
     Ring ring = w.ring;
     i64* park = w.park;
     void* args[] = {(void*)&u, (void*)&T, (void*)&aux, (void*)&mask, (void*)&list, (void*)&cap,
-                    (void*)&fg, (void*)&band, (void*)&ctr, (void*)&ring, (void*)&park};
+                    (void*)&fg, (void*)&band, (void*)&ctr, (void*)&ring, (void*)&park,
+                    (void*)&finalize};
     LSML_CUDA(cudaLaunchCooperativeKernel((void*)fmm_march_kernel<NDIM>, dim3(g_march_blocks[NDIM]),
                                           dim3(FMM_THREADS), args, 0, s));
     count_launch();
@@ -1095,30 +1192,59 @@ int fmm_workspace_init(i64 total, void* workspace, cudaStream_t s) {
     return 0;
 }
 
+static void plane_launch_shape(const Geom& g, int planes, dim3& grid, dim3& block) {
+    int bx = 32;
+    while (bx < 256 && bx < g.n[2]) bx <<= 1;
+    int by = 256 / bx;
+    if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
+    block = dim3(bx, by);
+    grid = dim3((unsigned)(g.batch * planes), (unsigned)((g.n[1] + by - 1) / by),
+                (unsigned)((g.n[2] + bx - 1) / bx));
+}
+
+// clear + prepare + initial frozen set + seeds
 template <int NDIM>
-static int rebuild_nd(const Geom& g, const FmmGeom& fg, const double* u, double eff_band,
-                      const u64* stats, u8* mask, const FmmWorkspace& w, i64 total,
-                      const i64* prev_band_idx, const i64* prev_n_band, cudaStream_t s) {
+static int begin_nd(const Geom& g, const FmmGeom& fg, const double* u, const u64* stats, u8* mask,
+                    const FmmWorkspace& w, i64 total, const i64* prev_band_idx,
+                    const i64* prev_n_band, cudaStream_t s) {
+    static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
+    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
+    LSML_LAUNCH_CHECK("fmm_clear_kernel");
+    fmm_prepare_kernel<<<1, 256, 0, s>>>(w.ctr, (prev_band_idx != nullptr && !no_hints) ? 1 : 0,
+                                         w.ring.cap);
+    LSML_LAUNCH_CHECK("fmm_prepare_kernel");
+    dim3 grid, block;
+    const bool slab = fg.own_lo > 0 || fg.own_hi < fg.n0;
     if (prev_band_idx != nullptr) {
         fmm_init_band_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(u, w.T, mask, w.list, fg, stats,
                                                               prev_band_idx, prev_n_band, w.ctr);
         LSML_LAUNCH_CHECK("fmm_init_band_kernel");
+        // a slab's boundary planes can be frozen by a sign change on the neighbour's side
+        if (slab && fg.own_lo > 0) {
+            plane_launch_shape(g, 1, grid, block);
+            fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr,
+                                                        fg.own_lo, fg.own_lo + 1);
+            LSML_LAUNCH_CHECK("fmm_init_kernel");
+        }
+        if (slab && fg.own_hi < fg.n0) {                  // (claims make a repeated plane harmless)
+            plane_launch_shape(g, 1, grid, block);
+            fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr,
+                                                        fg.own_hi - 1, fg.own_hi);
+            LSML_LAUNCH_CHECK("fmm_init_kernel");
+        }
     } else {
-        int bx = 32;
-        while (bx < 256 && bx < g.n[2]) bx <<= 1;
-        int by = 256 / bx;
-        if (by > g.n[1]) { by = 1; while (by < g.n[1]) by <<= 1; }
-        const dim3 block(bx, by), grid((unsigned)(g.batch * g.n[0]),
-                                       (unsigned)((g.n[1] + by - 1) / by),
-                                       (unsigned)((g.n[2] + bx - 1) / bx));
-        fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr);
+        plane_launch_shape(g, fg.own_hi - fg.own_lo, grid, block);
+        fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr,
+                                                    fg.own_lo, fg.own_hi);
         LSML_LAUNCH_CHECK("fmm_init_kernel");
     }
     fmm_seed_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(mask, w.aux, w.list, total, fg, w.ctr, w.ring,
                                                      w.park);
     LSML_LAUNCH_CHECK("fmm_seed_kernel");
-    return march_launch<NDIM>(u, w, mask, total, fg, eff_band, s);
+    return 0;
 }
+
+#define LSML_ND(call3, call2, call1) (g.ndim == 3 ? (call3) : g.ndim == 2 ? (call2) : (call1))
 
 // Rebuild the band of every item from u.  mask must be all-zero on first use of the workspace
 // and is thereafter maintained by this function.  band == 0 => whole grid (no narrow band).
@@ -1135,18 +1261,13 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
     FmmGeom fg;
     if (make_fmm_geom(g, fg)) return 1;
     const double eff_band = band != 0.0 ? band : DBL_MAX;
-
-    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
-    LSML_LAUNCH_CHECK("fmm_clear_kernel");
-    static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
-    fmm_prepare_kernel<<<1, 256, 0, s>>>(w.ctr, (prev_band_idx != nullptr && !no_hints) ? 1 : 0,
-                                         w.ring.cap);
-    LSML_LAUNCH_CHECK("fmm_prepare_kernel");
-
-    int st = 0;
-    if (g.ndim == 3) st = rebuild_nd<3>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
-    else if (g.ndim == 2) st = rebuild_nd<2>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
-    else st = rebuild_nd<1>(g, fg, u, eff_band, stats, mask, w, total, prev_band_idx, prev_n_band, s);
+    int st = LSML_ND(begin_nd<3>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s),
+                     begin_nd<2>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s),
+                     begin_nd<1>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s));
+    if (st) return st;
+    st = LSML_ND(march_launch<3>(u, w, mask, total, fg, eff_band, 1, s),
+                 march_launch<2>(u, w, mask, total, fg, eff_band, 1, s),
+                 march_launch<1>(u, w, mask, total, fg, eff_band, 1, s));
     if (st) return st;
     if (dist_out != nullptr) {
         fmm_export_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, mask, dist_out, total);
@@ -1154,6 +1275,83 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
     }
     return 0;
 }
+
+// ---- slab-decomposed rebuild: the same kernels, driven in phases by the host layer ----------
+// (lsml_b200/core/slab.py): begin -> [march -> halo exchange of T/state -> requeue]* -> finish.
+// The local grid is the rank's owned planes [own_lo, own_hi) plus halo planes; batch must be 1.
+static int slab_geom(const Geom& g, int own_lo, int own_hi, FmmGeom& fg) {
+    if (g.batch != 1) { set_error("slab decomposition: one volume per rank"); return 1; }
+    if (make_fmm_geom(g, fg)) return 1;
+    if (own_lo < 0 || own_hi > g.n[0] || own_lo >= own_hi) {
+        set_error("slab decomposition: bad owned plane range [%d, %d)", own_lo, own_hi);
+        return 1;
+    }
+    fg.own_lo = own_lo; fg.own_hi = own_hi;
+    return 0;
+}
+
+int fmm_slab_begin(const Geom& g, int own_lo, int own_hi, const double* u, u8* mask,
+                   void* workspace, const i64* prev_band_idx, const i64* prev_n_band,
+                   cudaStream_t s) {
+    const i64 total = g.voxels * g.batch;
+    const FmmWorkspace w = carve(workspace, total);
+    FmmGeom fg;
+    if (slab_geom(g, own_lo, own_hi, fg)) return 1;
+    return LSML_ND(begin_nd<3>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s),
+                   begin_nd<2>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s),
+                   begin_nd<1>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s));
+}
+
+int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, double band, u8* mask,
+                   void* workspace, cudaStream_t s) {
+    const i64 total = g.voxels * g.batch;
+    const FmmWorkspace w = carve(workspace, total);
+    FmmGeom fg;
+    if (slab_geom(g, own_lo, own_hi, fg)) return 1;
+    const double eff_band = band != 0.0 ? band : DBL_MAX;
+    return LSML_ND(march_launch<3>(u, w, mask, total, fg, eff_band, 0, s),
+                   march_launch<2>(u, w, mask, total, fg, eff_band, 0, s),
+                   march_launch<1>(u, w, mask, total, fg, eff_band, 0, s));
+}
+
+int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, u8* mask, void* workspace,
+                     i64* pending_out, cudaStream_t s) {
+    const i64 total = g.voxels * g.batch;
+    const FmmWorkspace w = carve(workspace, total);
+    FmmGeom fg;
+    if (slab_geom(g, own_lo, own_hi, fg)) return 1;
+    const double eff_band = band != 0.0 ? band : DBL_MAX;
+    dim3 grid, block;
+    plane_launch_shape(g, 4, grid, block);
+    if (g.ndim == 3) fmm_requeue_kernel<3><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park);
+    else if (g.ndim == 2) fmm_requeue_kernel<2><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park);
+    else fmm_requeue_kernel<1><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park);
+    LSML_LAUNCH_CHECK("fmm_requeue_kernel");
+    if (pending_out != nullptr) {
+        fmm_pending_kernel<<<1, 1, 0, s>>>(w.ctr, pending_out);
+        LSML_LAUNCH_CHECK("fmm_pending_kernel");
+    }
+    return 0;
+}
+
+int fmm_slab_finish(const Geom& g, int own_lo, int own_hi, double band, u8* mask, double* dist_out,
+                    void* workspace, cudaStream_t s) {
+    const i64 total = g.voxels * g.batch;
+    const FmmWorkspace w = carve(workspace, total);
+    FmmGeom fg;
+    if (slab_geom(g, own_lo, own_hi, fg)) return 1;
+    const double eff_band = band != 0.0 ? band : DBL_MAX;
+    fmm_finalize_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, mask, w.list, total, fg, eff_band, w.ctr);
+    LSML_LAUNCH_CHECK("fmm_finalize_kernel");
+    if (dist_out != nullptr) {
+        fmm_export_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, mask, dist_out, total);
+        LSML_LAUNCH_CHECK("fmm_export_kernel");
+    }
+    return 0;
+}
+
+// device address of T (total float64) inside a workspace: the host layer exchanges its halo planes
+double* fmm_distance_ptr(void* workspace) { return static_cast<double*>(workspace); }
 
 // device address of the counters {n_init, n_cand, tail_sweeps, sweeps, converged, prev_init,
 // prev_cand, replays, ...} of the last rebuild
