@@ -179,6 +179,44 @@ int lsml_fmm_rebuild_from_band(int ndim, const int *shape, long long batch, cons
                                uint8_t *mask, double *dist_out, void *workspace,
                                const long long *prev_band_idx, const long long *prev_n_band,
                                void *stream);
+/* ---- slab decomposition of ONE large volume along axis 0 (host side:
+ * lsml_b200/core/slab.py).  The local grid `shape` is the rank's owned planes [own_lo, own_hi)
+ * plus halo planes that hold copies of the neighbour ranks' voxels.  A rebuild is
+ *   begin -> { march -> exchange the halo planes of T (first 8*total bytes of the workspace) and
+ *   of mask -> requeue } until no rank has pending work -> finish.
+ * The fixed point is the same as the single-GPU one, so masks and distances are identical. */
+int lsml_fmm_slab_begin(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
+                        const double *u, uint8_t *mask, void *workspace,
+                        const long long *prev_band_idx, const long long *prev_n_band,
+                        void *stream);
+int lsml_fmm_slab_march(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
+                        const double *u, double band, uint8_t *mask, void *workspace,
+                        void *stream);
+/* sides: bit 0 / bit 1 = the halo below / above the owned planes changed in the exchange;
+ * pending_out: DEVICE int64, number of voxels queued for the next march (0 = this rank is done) */
+int lsml_fmm_slab_requeue(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
+                          double band, int sides, uint8_t *mask, void *workspace,
+                          long long *pending_out, void *stream);
+int lsml_fmm_slab_finish(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
+                         double band, uint8_t *mask, double *dist_out, void *workspace,
+                         void *stream);
+/* compaction of a sub-range of a grid: indices are written with index_offset added */
+int lsml_compact_mask_range(long long total, const uint8_t *mask, long long *band_idx,
+                            long long *n_band, long long index_offset, void *workspace,
+                            void *stream);
+/* raw band sums per item and plane: mode 0 sum x, mode 1 sum (x - mean)^2 (mean: [batch][nplanes]) */
+int lsml_band_sums(long long voxels, long long batch, const double *planes,
+                   long long plane_stride, int nplanes, const long long *band_idx,
+                   const long long *item_offsets, int mode, const double *mean, double *sums,
+                   void *workspace, void *stream);
+/* lsml_assemble_features for a local grid whose first axis-0 plane is plane origin0 of the volume */
+int lsml_assemble_features_origin(int nfeat, const int *kind, const int *a, const int *b, int ndim,
+                                  const int *shape, long long batch, const double *dx,
+                                  const long long *band_idx, const long long *n_band,
+                                  const double *planes, long long plane_stride,
+                                  const double *item_feat, const double *com, double *X,
+                                  int origin0, void *stream);
+
 /* synchronous: copies the 8 int64 counters of the last rebuild to HOST out
  * {n_init, n_cand, single-CTA sweeps, sweeps, converged, prev_init, prev_cand, replays} */
 int lsml_fmm_counters(long long total, void *workspace, long long *out, void *stream);

@@ -191,12 +191,17 @@ int lsml_compact_mask(long long total, long long voxels_per_item, const uint8_t*
                       long long* band_idx, long long* n_band, long long* item_offsets_out,
                       void* workspace, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    int st = compact_mask(total, mask, band_idx, n_band, workspace, s);
+    int st = compact_mask(total, mask, band_idx, n_band, workspace, 0, s);
     if (st) return st;
     if (item_offsets_out != nullptr && voxels_per_item > 0)
         return item_offsets(band_idx, n_band, voxels_per_item, total / voxels_per_item,
                             item_offsets_out, s);
     return 0;
+}
+int lsml_compact_mask_range(long long total, const uint8_t* mask, long long* band_idx,
+                            long long* n_band, long long index_offset, void* workspace,
+                            void* stream) {
+    return compact_mask(total, mask, band_idx, n_band, workspace, index_offset, (cudaStream_t)stream);
 }
 
 #define GEOM(g) Geom g; if (make_geom(g, ndim, shape, batch, dx)) return 1
@@ -261,7 +266,24 @@ int lsml_assemble_features(int nfeat, const int* kind, const int* a, const int* 
                            const double* item_feat, const double* com, double* X, void* stream) {
     GEOM(g);
     return assemble_features_c(nfeat, kind, a, b, g, band_idx, n_band, planes, plane_stride,
-                               item_feat, com, X, (cudaStream_t)stream);
+                               item_feat, com, X, 0, (cudaStream_t)stream);
+}
+int lsml_assemble_features_origin(int nfeat, const int* kind, const int* a, const int* b, int ndim,
+                                  const int* shape, long long batch, const double* dx,
+                                  const long long* band_idx, const long long* n_band,
+                                  const double* planes, long long plane_stride,
+                                  const double* item_feat, const double* com, double* X,
+                                  int origin0, void* stream) {
+    GEOM(g);
+    return assemble_features_c(nfeat, kind, a, b, g, band_idx, n_band, planes, plane_stride,
+                               item_feat, com, X, origin0, (cudaStream_t)stream);
+}
+int lsml_band_sums(long long voxels, long long batch, const double* planes,
+                   long long plane_stride, int nplanes, const long long* band_idx,
+                   const long long* item_offsets, int mode, const double* mean, double* sums,
+                   void* workspace, void* stream) {
+    return band_sums(voxels, batch, planes, plane_stride, nplanes, band_idx, item_offsets, mode,
+                     mean, sums, workspace, (cudaStream_t)stream);
 }
 int lsml_linear_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
                         const double* scale, const double* coef, double intercept, double* out,
@@ -315,6 +337,38 @@ int lsml_fmm_rebuild_from_band(int ndim, const int* shape, long long batch, cons
     GEOM(g);
     return fmm_rebuild(g, u, band, stats, mask, dist_out, workspace, prev_band_idx, prev_n_band,
                        (cudaStream_t)stream);
+}
+int lsml_fmm_slab_begin(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
+                        const double* u, uint8_t* mask, void* workspace,
+                        const long long* prev_band_idx, const long long* prev_n_band,
+                        void* stream) {
+    const long long batch = 1;
+    GEOM(g);
+    return fmm_slab_begin(g, own_lo, own_hi, u, mask, workspace, prev_band_idx, prev_n_band,
+                          (cudaStream_t)stream);
+}
+int lsml_fmm_slab_march(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
+                        const double* u, double band, uint8_t* mask, void* workspace,
+                        void* stream) {
+    const long long batch = 1;
+    GEOM(g);
+    return fmm_slab_march(g, own_lo, own_hi, u, band, mask, workspace, (cudaStream_t)stream);
+}
+int lsml_fmm_slab_requeue(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
+                          double band, int sides, uint8_t* mask, void* workspace,
+                          long long* pending_out, void* stream) {
+    const long long batch = 1;
+    GEOM(g);
+    return fmm_slab_requeue(g, own_lo, own_hi, band, sides, mask, workspace, pending_out,
+                            (cudaStream_t)stream);
+}
+int lsml_fmm_slab_finish(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
+                         double band, uint8_t* mask, double* dist_out, void* workspace,
+                         void* stream) {
+    const long long batch = 1;
+    GEOM(g);
+    return fmm_slab_finish(g, own_lo, own_hi, band, mask, dist_out, workspace,
+                           (cudaStream_t)stream);
 }
 int lsml_fmm_counters(long long total, void* workspace, long long* out, void* stream) {
     const i64* dev = nullptr;

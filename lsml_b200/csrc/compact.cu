@@ -92,7 +92,7 @@ compact_scan_kernel(i64* __restrict__ tile_counts, i64 n, i64* __restrict__ n_ba
 __global__ void __launch_bounds__(CT_THREADS)
 compact_scatter_kernel(const u8* __restrict__ mask, i64 total,
                        const i64* __restrict__ tile_offsets, i64* __restrict__ band_idx,
-                       bool aligned) {
+                       bool aligned, i64 index_offset) {
     __shared__ int warp_tot[CT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 start = ((i64)blockIdx.x * CT_THREADS + tid) * CT_BYTES_PER_THREAD;
@@ -113,7 +113,7 @@ compact_scatter_kernel(const u8* __restrict__ mask, i64 total,
     while (bits) {
         const int b = __ffs(bits) - 1;
         bits &= bits - 1;
-        band_idx[pos++] = start + b;
+        band_idx[pos++] = start + b + index_offset;
     }
 }
 
@@ -137,8 +137,10 @@ i64 compact_workspace_bytes(i64 total) {
     return (tiles + 1) * (i64)sizeof(i64);
 }
 
+// index_offset is added to every index written (the mask may be a sub-range of a larger grid:
+// the owned planes of a slab)
 int compact_mask(i64 total, const u8* mask, i64* band_idx, i64* n_band, void* workspace,
-                 cudaStream_t s) {
+                 i64 index_offset, cudaStream_t s) {
     if (total <= 0) {
         LSML_CUDA(cudaMemsetAsync(n_band, 0, sizeof(i64), s));
         return 0;
@@ -150,7 +152,8 @@ int compact_mask(i64 total, const u8* mask, i64* band_idx, i64* n_band, void* wo
     LSML_LAUNCH_CHECK("compact_count_kernel");
     compact_scan_kernel<<<1, 1024, 0, s>>>(tile_counts, tiles, n_band);
     LSML_LAUNCH_CHECK("compact_scan_kernel");
-    compact_scatter_kernel<<<(unsigned)tiles, CT_THREADS, 0, s>>>(mask, total, tile_counts, band_idx, aligned);
+    compact_scatter_kernel<<<(unsigned)tiles, CT_THREADS, 0, s>>>(mask, total, tile_counts, band_idx, aligned,
+                                                                  index_offset);
     LSML_LAUNCH_CHECK("compact_scatter_kernel");
     return 0;
 }

@@ -216,7 +216,8 @@ band_sum_partial_kernel(const double* __restrict__ planes, i64 plane_stride, int
     }
 }
 
-// out[item][p] = op(sum_s partial / n_item) ; op 0 mean, op 1 sqrt (population std, ddof=0)
+// out[item][p] = op(sum_s partial / n_item) ; op 0 mean, op 1 sqrt (population std, ddof=0),
+// op 2 the raw sum (slab decomposition: the ranks' sums are all-reduced first)
 __global__ void band_sum_final_kernel(const double* __restrict__ partial, int nplanes, int slices,
                                       const i64* __restrict__ item_offsets, i64 batch, int op,
                                       double* __restrict__ out) {
@@ -229,7 +230,7 @@ __global__ void band_sum_final_kernel(const double* __restrict__ partial, int np
     acc = warp_sum(acc);
     if (lane == 0) {
         const double n = (double)(item_offsets[item + 1] - item_offsets[item]);
-        out[w] = op == 0 ? acc / n : sqrt(acc / n);
+        out[w] = op == 2 ? acc : (op == 0 ? acc / n : sqrt(acc / n));
     }
 }
 
@@ -310,6 +311,7 @@ struct ItemGeom {
     int pad;           // 3 - ndim
     double dx[3];      // padded
     double pdx;        // prod(dx) over real axes, multiplied left to right
+    int origin0;       // index of the local grid's first axis-0 plane in the whole volume (slabs)
 };
 
 // moment of `order` along padded axis ax from the exact integer sums
@@ -392,7 +394,7 @@ assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
             const double* c = com + item * 3;
             // numpy.linalg.norm(mesh - com, axis=0): ((d0^2 + d1^2) + d2^2) over the real axes
             double acc = 0.0;
-            if (geo.ndim == 3) { const double d = i * geo.dx[0] - c[0]; acc = d * d; }
+            if (geo.ndim == 3) { const double d = (i + geo.origin0) * geo.dx[0] - c[0]; acc = d * d; }
             if (geo.ndim >= 2) { const double d = j * geo.dx[1] - c[1]; acc = geo.ndim == 2 ? d * d : acc + d * d; }
             { const double d = k * geo.dx[2] - c[2]; acc = geo.ndim == 1 ? d * d : acc + d * d; }
             v = sqrt(acc);
@@ -515,6 +517,24 @@ int band_stats(i64 voxels, i64 batch, const double* planes, i64 plane_stride, in
     return 0;
 }
 
+// raw per-item band sums of every plane: mode 0 sum x, mode 1 sum (x - mean)^2 with the given mean
+int band_sums(i64 voxels, i64 batch, const double* planes, i64 plane_stride, int nplanes,
+              const i64* band_idx, const i64* item_offsets, int mode, const double* mean,
+              double* sums, void* workspace, cudaStream_t s) {
+    if (nplanes > MAX_PLANES) { set_error("at most %d image planes", MAX_PLANES); return 1; }
+    if (nplanes == 0) return 0;
+    const int slices = band_slices(voxels);
+    double* partial = static_cast<double*>(workspace);
+    const dim3 grid(slices, (unsigned)batch);
+    const int fin_blocks = (int)((batch * nplanes + 7) / 8);
+    band_sum_partial_kernel<<<grid, RS_THREADS, 0, s>>>(planes, plane_stride, nplanes, band_idx,
+                                                        item_offsets, slices, mode, mean, partial);
+    LSML_LAUNCH_CHECK("band_sum_partial_kernel");
+    band_sum_final_kernel<<<fin_blocks, 256, 0, s>>>(partial, nplanes, slices, item_offsets, batch, 2, sums);
+    LSML_LAUNCH_CHECK("band_sum_final_kernel");
+    return 0;
+}
+
 constexpr int CL_CELLS_PER_CTA = 8192;
 
 i64 contour_workspace_bytes(int m, int n, i64 batch) {
@@ -549,7 +569,7 @@ int item_features(const FeatProgram& prog, const Geom& g, int nplanes, const u64
     double pdx = 1.0;
     for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
     for (int a = geo.pad; a < 3; ++a) pdx = (a == geo.pad) ? g.dx[a] : pdx * g.dx[a];
-    geo.pdx = pdx;
+    geo.pdx = pdx; geo.origin0 = 0;
     item_features_kernel<<<(unsigned)((g.batch + 127) / 128), 128, 0, s>>>(
         prog, geo, g.batch, nplanes, stats, band_mean, band_std, boundary, item_feat, com);
     LSML_LAUNCH_CHECK("item_features_kernel");
@@ -558,11 +578,12 @@ int item_features(const FeatProgram& prog, const Geom& g, int nplanes, const u64
 
 int assemble_features(const FeatProgram& prog, const Geom& g, const i64* band_idx,
                       const i64* n_band, const double* planes, i64 plane_stride,
-                      const double* item_feat, const double* com, double* X, cudaStream_t s) {
+                      const double* item_feat, const double* com, double* X, int origin0,
+                      cudaStream_t s) {
     ItemGeom geo;
     geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
     for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
-    geo.pdx = 1.0;
+    geo.pdx = 1.0; geo.origin0 = origin0;
     assemble_kernel<<<LSML_SMS * 8, 256, 0, s>>>(prog, geo, g.n[1], g.n[2], g.voxels, band_idx,
                                                   n_band, planes, plane_stride, item_feat, com, X);
     LSML_LAUNCH_CHECK("assemble_kernel");
@@ -598,10 +619,11 @@ int item_features_c(int nfeat, const int* kind, const int* a, const int* b, cons
 int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
                         const i64* band_idx, const i64* n_band, const double* planes,
                         i64 plane_stride, const double* item_feat, const double* com, double* X,
-                        cudaStream_t s) {
+                        int origin0, cudaStream_t s) {
     FeatProgram p;
     if (fill_program(p, nfeat, kind, a, b)) return 1;
-    return assemble_features(p, g, band_idx, n_band, planes, plane_stride, item_feat, com, X, s);
+    return assemble_features(p, g, band_idx, n_band, planes, plane_stride, item_feat, com, X,
+                             origin0, s);
 }
 
 }  // namespace lsml

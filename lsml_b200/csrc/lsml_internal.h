@@ -14,7 +14,7 @@ int gradient_centered_dense(const Geom& g, const T* A, const u8* mask, T* grads,
 // compact.cu
 i64 compact_workspace_bytes(i64 total);
 int compact_mask(i64 total, const u8* mask, i64* band_idx, i64* n_band, void* workspace,
-                 cudaStream_t s);
+                 i64 index_offset, cudaStream_t s);
 int item_offsets(const i64* band_idx, const i64* n_band, i64 voxels, i64 batch, i64* offsets,
                  cudaStream_t s);
 
@@ -45,7 +45,10 @@ int item_features_c(int nfeat, const int* kind, const int* a, const int* b, cons
 int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, const Geom& g,
                         const i64* band_idx, const i64* n_band, const double* planes,
                         i64 plane_stride, const double* item_feat, const double* com, double* X,
-                        cudaStream_t s);
+                        int origin0, cudaStream_t s);
+int band_sums(i64 voxels, i64 batch, const double* planes, i64 plane_stride, int nplanes,
+              const i64* band_idx, const i64* item_offsets, int mode, const double* mean,
+              double* sums, void* workspace, cudaStream_t s);
 
 // regress.cu
 int linear_predict(const double* X, const i64* n_band, int F, const double* mean,
@@ -70,6 +73,15 @@ int fmm_workspace_init(i64 total, void* workspace, cudaStream_t s);
 int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u8* mask,
                 double* dist_out, void* workspace, const i64* prev_band_idx,
                 const i64* prev_n_band, cudaStream_t s);
+int fmm_slab_begin(const Geom& g, int own_lo, int own_hi, const double* u, u8* mask,
+                   void* workspace, const i64* prev_band_idx, const i64* prev_n_band,
+                   cudaStream_t s);
+int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, double band, u8* mask,
+                   void* workspace, cudaStream_t s);
+int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, int sides, u8* mask,
+                     void* workspace, i64* pending_out, cudaStream_t s);
+int fmm_slab_finish(const Geom& g, int own_lo, int own_hi, double band, u8* mask, double* dist_out,
+                    void* workspace, cudaStream_t s);
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
 i64 fmm_counters_sizes_offset();
 i64 fmm_counters_stamps_offset();
