@@ -192,11 +192,12 @@ int lsml_fmm_slab_begin(int ndim, const int *shape, const double *dx, int own_lo
 int lsml_fmm_slab_march(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
                         const double *u, double band, uint8_t *mask, void *workspace,
                         void *stream);
-/* sides: bit 0 / bit 1 = the halo below / above the owned planes changed in the exchange;
+/* sides_dev: DEVICE int64[2], non-zero = the halo below / above the owned planes changed in the
+ * exchange (kept on the device so that a round needs a single host read);
  * pending_out: DEVICE int64, number of voxels queued for the next march (0 = this rank is done) */
 int lsml_fmm_slab_requeue(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
-                          double band, int sides, uint8_t *mask, void *workspace,
-                          long long *pending_out, void *stream);
+                          double band, const long long *sides_dev, uint8_t *mask,
+                          void *workspace, long long *pending_out, void *stream);
 int lsml_fmm_slab_finish(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
                          double band, uint8_t *mask, double *dist_out, void *workspace,
                          void *stream);

@@ -54,13 +54,17 @@ class LocalCollective:
         return [total.to(p.device) for p in parts]
 
     def exchange(self, sends):
-        """sends[r] = (to_lower, to_upper) tensors (or None at the ends of the volume);
-        returns recvs[r] = (from_lower, from_upper)."""
+        """sends[r] = list over arrays of (to_lower, to_upper) tensors (None at the ends of the
+        volume); returns recvs[r] = list over arrays of (from_lower, from_upper)."""
         out = []
         for r in range(self.world):
-            lo = sends[r - 1][1] if r > 0 else None
-            hi = sends[r + 1][0] if r + 1 < self.world else None
-            out.append((None if lo is None else lo.clone(), None if hi is None else hi.clone()))
+            per_array = []
+            for a in range(len(sends[r])):
+                lo = sends[r - 1][a][1] if r > 0 else None
+                hi = sends[r + 1][a][0] if r + 1 < self.world else None
+                per_array.append((None if lo is None else lo.clone(),
+                                  None if hi is None else hi.clone()))
+            out.append(per_array)
         return out
 
 
@@ -80,20 +84,23 @@ class TorchCollective:
         return [t]
 
     def exchange(self, sends):
-        to_lo, to_hi = sends[0]
-        ops, from_lo, from_hi = [], None, None
-        if self.rank > 0:
-            from_lo = torch.empty_like(to_lo)
-            ops.append(self.dist.P2POp(self.dist.isend, to_lo.contiguous(), self.rank - 1))
-            ops.append(self.dist.P2POp(self.dist.irecv, from_lo, self.rank - 1))
-        if self.rank + 1 < self.world:
-            from_hi = torch.empty_like(to_hi)
-            ops.append(self.dist.P2POp(self.dist.isend, to_hi.contiguous(), self.rank + 1))
-            ops.append(self.dist.P2POp(self.dist.irecv, from_hi, self.rank + 1))
+        """All arrays' halo planes in ONE batch of point-to-point operations."""
+        ops, out = [], []
+        for to_lo, to_hi in sends[0]:
+            from_lo = from_hi = None
+            if self.rank > 0:
+                from_lo = torch.empty_like(to_lo)
+                ops.append(self.dist.P2POp(self.dist.isend, to_lo.contiguous(), self.rank - 1))
+                ops.append(self.dist.P2POp(self.dist.irecv, from_lo, self.rank - 1))
+            if self.rank + 1 < self.world:
+                from_hi = torch.empty_like(to_hi)
+                ops.append(self.dist.P2POp(self.dist.isend, to_hi.contiguous(), self.rank + 1))
+                ops.append(self.dist.P2POp(self.dist.irecv, from_hi, self.rank + 1))
+            out.append((from_lo, from_hi))
         if ops:
             for req in self.dist.batch_isend_irecv(ops):
                 req.wait()
-        return [(from_lo, from_hi)]
+        return [out]
 
 
 class SlabRank:
@@ -210,10 +217,10 @@ class SlabRank:
             _lib.ptr(e._ws_fmm), e._stream()), "fmm_slab_march")
 
     def rebuild_requeue(self, sides):
-        """sides: bit 0 = the lower halo changed, bit 1 = the upper halo changed."""
+        """sides: device int64[2], non-zero = the lower / upper halo changed."""
         e = self.eng
         _lib.check(_lib.lib.lsml_fmm_slab_requeue(
-            *self._fmm_args(), ctypes.c_double(e.band), ctypes.c_int(int(sides)),
+            *self._fmm_args(), ctypes.c_double(e.band), _lib.ptr(sides),
             _lib.ptr(e.mask), _lib.ptr(e._ws_fmm), _lib.ptr(self.pending), e._stream()),
             "fmm_slab_requeue")
 
@@ -331,11 +338,17 @@ class SlabVolume:
     def _global_stats(self):
         return self.coll.allreduce_sum([r.global_frame_stats() for r in self.ranks])
 
-    def _exchange(self, getter):
-        """Halo exchange of one local array per rank; returns per-rank 'changed' flags."""
-        arrs = [getter(r) for r in self.ranks]
-        recvs = self.coll.exchange([r._halo_sends(a) for r, a in zip(self.ranks, arrs)])
-        return [r._halo_store(a, rc) for r, a, rc in zip(self.ranks, arrs, recvs)]
+    def _exchange(self, *getters):
+        """Halo exchange of one or more local arrays per rank in a single round of messages;
+        returns, per rank, the sum over arrays of the (lower, upper) 'changed' flags."""
+        arrs = [[g(r) for g in getters] for r in self.ranks]
+        recvs = self.coll.exchange([[r._halo_sends(a) for a in al]
+                                    for r, al in zip(self.ranks, arrs)])
+        out = []
+        for r, al, rc in zip(self.ranks, arrs, recvs):
+            flags = [r._halo_store(a, c) for a, c in zip(al, rc)]
+            out.append(sum(flags[1:], flags[0]))
+        return out
 
     def _rebuild(self, from_band):
         gstats = self._global_stats()
@@ -354,12 +367,10 @@ class SlabVolume:
         while True:
             for r in self.ranks:
                 r.rebuild_march()
-            changed = self._exchange(lambda r: r.T_view())
-            changed2 = self._exchange(lambda r: r.eng.mask[0])
-            for r, c, c2 in zip(self.ranks, changed, changed2):
-                lo_hi = (c + c2).tolist()             # one small host read per rank and round
-                r.rebuild_requeue((1 if lo_hi[0] else 0) | (2 if lo_hi[1] else 0))
-            rounds += 1
+            changed = self._exchange(lambda r: r.T_view(), lambda r: r.eng.mask[0])
+            for r, c in zip(self.ranks, changed):
+                r.rebuild_requeue(c)
+            rounds += 1                               # (one host read per round: the line below)
             if int(self.coll.allreduce_sum([r.pending for r in self.ranks])[0].item()) == 0:
                 break
             if rounds > 10000:

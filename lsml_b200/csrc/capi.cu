@@ -355,11 +355,11 @@ int lsml_fmm_slab_march(int ndim, const int* shape, const double* dx, int own_lo
     return fmm_slab_march(g, own_lo, own_hi, u, band, mask, workspace, (cudaStream_t)stream);
 }
 int lsml_fmm_slab_requeue(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
-                          double band, int sides, uint8_t* mask, void* workspace,
-                          long long* pending_out, void* stream) {
+                          double band, const long long* sides_dev, uint8_t* mask,
+                          void* workspace, long long* pending_out, void* stream) {
     const long long batch = 1;
     GEOM(g);
-    return fmm_slab_requeue(g, own_lo, own_hi, band, sides, mask, workspace, pending_out,
+    return fmm_slab_requeue(g, own_lo, own_hi, band, sides_dev, mask, workspace, pending_out,
                             (cudaStream_t)stream);
 }
 int lsml_fmm_slab_finish(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,

@@ -1027,7 +1027,8 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
 template <int NDIM>
 __global__ void __launch_bounds__(256)
 fmm_requeue_kernel(const double* T, Aux* aux, u8* mask, i64* list, i64 cap, FmmGeom g,
-                   double band, FmmCounters* ctr, Ring ring, i64* park, int sides) {
+                   double band, FmmCounters* ctr, Ring ring, i64* park,
+                   const i64* __restrict__ sides_dev) {
     const int k = blockIdx.z * blockDim.x + threadIdx.x;
     const int cj = blockIdx.y * blockDim.y + threadIdx.y;
     if (k >= g.n2 || cj >= g.n1) return;
@@ -1041,9 +1042,9 @@ fmm_requeue_kernel(const double* T, Aux* aux, u8* mask, i64* list, i64 cap, FmmG
     if (ci < g.own_lo || ci >= g.own_hi) return;
     if (blockIdx.x >= 2 && ci < g.own_lo + 2) return;           // thin slab: planes already done
     if (own <= 0) return;
-    // sides: bit 0 / bit 1 = the halo below / above the owned planes changed in this exchange
-    const bool near_lo = (sides & 1) && g.own_lo > 0 && ci < g.own_lo + 2;
-    const bool near_hi = (sides & 2) && g.own_hi < g.n0 && ci >= g.own_hi - 2;
+    // sides_dev[0] / [1] != 0: the halo below / above the owned planes changed in this exchange
+    const bool near_lo = sides_dev[0] != 0 && g.own_lo > 0 && ci < g.own_lo + 2;
+    const bool near_hi = sides_dev[1] != 0 && g.own_hi < g.n0 && ci >= g.own_hi - 2;
     if (!near_lo && !near_hi) return;
     const i64 l = ((i64)ci * g.n1 + cj) * g.n2 + k;
     const int coord[3] = {ci, cj, k};
@@ -1315,8 +1316,8 @@ int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, doubl
                    march_launch<1>(u, w, mask, total, fg, eff_band, 0, s));
 }
 
-int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, int sides, u8* mask,
-                     void* workspace, i64* pending_out, cudaStream_t s) {
+int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, const i64* sides_dev,
+                     u8* mask, void* workspace, i64* pending_out, cudaStream_t s) {
     const i64 total = g.voxels * g.batch;
     const FmmWorkspace w = carve(workspace, total);
     FmmGeom fg;
@@ -1324,12 +1325,10 @@ int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, int sid
     const double eff_band = band != 0.0 ? band : DBL_MAX;
     dim3 grid, block;
     plane_launch_shape(g, 4, grid, block);
-    if (sides) {
-        if (g.ndim == 3) fmm_requeue_kernel<3><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides);
-        else if (g.ndim == 2) fmm_requeue_kernel<2><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides);
-        else fmm_requeue_kernel<1><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides);
-        LSML_LAUNCH_CHECK("fmm_requeue_kernel");
-    }
+    if (g.ndim == 3) fmm_requeue_kernel<3><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides_dev);
+    else if (g.ndim == 2) fmm_requeue_kernel<2><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides_dev);
+    else fmm_requeue_kernel<1><<<grid, block, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, eff_band, w.ctr, w.ring, w.park, sides_dev);
+    LSML_LAUNCH_CHECK("fmm_requeue_kernel");
     if (pending_out != nullptr) {
         fmm_pending_kernel<<<1, 1, 0, s>>>(w.ctr, pending_out);
         LSML_LAUNCH_CHECK("fmm_pending_kernel");

@@ -78,8 +78,8 @@ int fmm_slab_begin(const Geom& g, int own_lo, int own_hi, const double* u, u8* m
                    cudaStream_t s);
 int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, double band, u8* mask,
                    void* workspace, cudaStream_t s);
-int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, int sides, u8* mask,
-                     void* workspace, i64* pending_out, cudaStream_t s);
+int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, const i64* sides_dev,
+                     u8* mask, void* workspace, i64* pending_out, cudaStream_t s);
 int fmm_slab_finish(const Geom& g, int own_lo, int own_hi, double band, u8* mask, double* dist_out,
                     void* workspace, cudaStream_t s);
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
