@@ -33,6 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ITERS = 50
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures
+NCU_TRAFFIC_MARCH_BYTES = 16.951296e6 + 5.875200e6
+NCU_TRAFFIC_STENCIL_BYTES = 354.348800e6 + 122.087424e6
 BAND = 3.0
 STEP = 0.35
 INIT_RADIUS = 40.0
@@ -431,8 +434,10 @@ def main():
                          "kernel": "band rebuild: fmm_march_kernel<3> (+ clear/prepare/init/seed), "
                                    "the dominant kernel of the step",
                          "achieved": rebuild_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": rebuild_gbs / peak, "traffic": None, "peak_source": peak_src,
-                         "ms": rebuild_avg_ms, "share_of_step": rebuild_ms / max(phase_total, 1e-9),
+                         "frac": rebuild_gbs / peak, "traffic": NCU_TRAFFIC_MARCH_BYTES,
+                         "traffic_source": "profiles/r1_ncu_fmm_march_r1.txt (one ncu --set full "
+                                           "capture of iteration 12 of tools/iter_probe.py)",
+                         "peak_source": peak_src, "ms": rebuild_avg_ms, "share_of_step": rebuild_ms / max(phase_total, 1e-9),
                          "algorithmic_bytes_per_launch": rebuild_bytes,
                          "candidates_per_launch": avg_cand,
                          "sweeps_per_launch": sweeps_sum / max(1, n_sampled),
@@ -440,10 +445,12 @@ def main():
                          "note": "latency-bound (dependency depth of the fast-marching order x "
                                  "replay latency), not HBM-bound: DESIGN.md 4.6"},
             "roofline_stencil": {"bound": "hbm",
-                                 "kernel": "gmag_os_march3d_kernel<double> (dense %d^3, full mask, "
+                                 "kernel": "gmag_os_marchv_kernel<double> (dense %d^3, full mask, "
                                            "L2 flushed between launches)" % n,
                                  "achieved": stencil_gbs, "peak": peak, "unit": "GB/s",
-                                 "frac": stencil_gbs / peak, "traffic": None,
+                                 "frac": stencil_gbs / peak, "traffic": NCU_TRAFFIC_STENCIL_BYTES,
+                                 "traffic_source": "profiles/r1_ncu_stencil_r1.txt",
+                                 "algorithmic_bytes_per_launch": stencil_bytes,
                                  "peak_source": peak_src, "ms": st_ms},
             "phases_ms_per_step": {k: v[1] for k, v in phases.items()},
         }
