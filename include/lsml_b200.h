@@ -185,10 +185,13 @@ int lsml_fmm_rebuild_from_band(int ndim, const int *shape, long long batch, cons
  *   begin -> { march -> exchange the halo planes of T (first 8*total bytes of the workspace) and
  *   of mask -> requeue } until no rank has pending work -> finish.
  * The fixed point is the same as the single-GPU one, so masks and distances are identical. */
+/* [own_lo, own_hi) here is the range of planes the rank EVALUATES (its owned planes plus the
+ * ghost planes it solves redundantly); dense_planes = HOST int[4] {a0, b0, a1, b1}: plane ranges
+ * searched densely for the interface besides the previous band (prev_band_idx != NULL only). */
 int lsml_fmm_slab_begin(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
                         const double *u, uint8_t *mask, void *workspace,
                         const long long *prev_band_idx, const long long *prev_n_band,
-                        void *stream);
+                        const int *dense_planes, void *stream);
 int lsml_fmm_slab_march(int ndim, const int *shape, const double *dx, int own_lo, int own_hi,
                         const double *u, double band, uint8_t *mask, void *workspace,
                         void *stream);

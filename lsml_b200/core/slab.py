@@ -17,6 +17,14 @@ band rebuild          the single-GPU sweeps (csrc/fmm.cu) restricted to the owne
 compaction            of the owned planes; global band order = rank order x local order
 ====================  =========================================================================
 
+Overlap (alternating Schwarz): a rebuild needs one exchange round every time a dependency chain
+of the marcher crosses a cut, and those chains run ALONG the interface.  Each rank therefore also
+evaluates ``overlap`` ghost planes beyond its cuts; the Dirichlet data it receives are the two
+planes just outside that evaluated range, taken from the neighbour's solution.  On the overlap
+both ranks solve the same strip problem with the same boundary data, whose fixed point is unique,
+so at convergence they agree there and the owned parts glue to the global solution -- but a chain
+now has to leave the overlap before it costs another round.
+
 Communication goes through a small ``Collective`` interface with two implementations:
 ``TorchCollective`` (one process per GPU, ``torch.distributed``: NCCL over NVLink on a B200 box,
 gloo in CPU-side tests of the bookkeeping) and ``LocalCollective`` (all ranks emulated in ONE
@@ -32,7 +40,8 @@ from .. import _lib
 from .engine import BandEngine, gaussian_weights
 from .regressors import export_regressor
 
-HALO_STATE = 2          # planes of T / state / u exchanged at every cut (replay stencil reach)
+HALO_STATE = 2          # planes of T / state exchanged per cut (replay stencil reach)
+OVERLAP = 8             # default ghost planes evaluated redundantly beyond every cut
 
 
 def plane_ranges(n0, world):
@@ -106,7 +115,7 @@ class TorchCollective:
 class SlabRank:
     """One rank's share of the volume: a BandEngine over the local (owned + halo) grid."""
 
-    def __init__(self, shape, rank, world, dx, band, specs, device):
+    def __init__(self, shape, rank, world, dx, band, specs, device, overlap=OVERLAP):
         if len(shape) != 3:
             raise ValueError("slab decomposition is for 3-D volumes")
         self.gshape = tuple(int(s) for s in shape)
@@ -117,15 +126,24 @@ class SlabRank:
         dx = np.ones(3) if dx is None else np.asarray(dx, dtype=np.float64)
         # halo wide enough for the axis-0 Gaussians of the image planes (one-time) and the
         # two-plane stencil reach of the band rebuild (every iteration)
-        hw = HALO_STATE
+        thick = min(b - a for a, b in plane_ranges(self.gshape[0], world))
+        self.W = max(0, min(int(overlap), thick - HALO_STATE - 1)) if world > 1 else 0
+        hw = self.W + HALO_STATE + 1          # ghost planes + Dirichlet planes + one more of u
         for spec in specs:
             if spec[0] in ("image_sample", "image_edge", "band_mean", "band_std") and spec[1] > 0:
                 hw = max(hw, gaussian_weights(float(spec[1]) / dx[0], 0)[1])
+        if world > 1 and thick < hw:
+            raise ValueError("slabs of %d planes are thinner than the %d-plane halo they have to "
+                             "supply to their neighbours: use fewer ranks" % (thick, hw))
+        self.hw = hw
         self.hlo = min(hw, self.A) if world > 1 else 0
         self.hhi = min(hw, self.gshape[0] - self.B) if world > 1 else 0
         self.lo, self.hi = self.hlo, self.hlo + (self.B - self.A)       # owned planes, local
         self.origin0 = self.A - self.hlo                                # local plane 0 in the volume
         lshape = (self.hi + self.hhi,) + self.gshape[1:]
+        # planes this rank EVALUATES in the band rebuild: owned + W ghost planes beyond each cut
+        self.elo = self.lo - self.W if rank > 0 else 0
+        self.ehi = self.hi + self.W if rank + 1 < world else lshape[0]
         self.eng = BandEngine(lshape, 1, dx=dx, band=band, specs=specs, device=device)
         self.plane = self.gshape[1] * self.gshape[2]
         self.device = self.eng.device
@@ -141,19 +159,26 @@ class SlabRank:
         e = self.eng
         return e._ws_fmm[:e.total * 8].view(torch.float64).view(e.shape)
 
-    def _halo_sends(self, arr):
-        """(planes for the lower neighbour, planes for the upper neighbour) of a local array."""
-        lo = arr[self.lo:self.lo + HALO_STATE] if self.rank > 0 else None
-        hi = arr[self.hi - HALO_STATE:self.hi] if self.rank + 1 < self.world else None
+    def _halo_sends(self, arr, wide=False):
+        """(planes for the lower neighbour, planes for the upper neighbour) of a local array.
+        ``wide``: the whole halo width (u); otherwise the two Dirichlet planes just outside the
+        neighbour's evaluated range, which lie ``W`` planes inside this rank's owned range."""
+        n, off = (self.hw, 0) if wide else (HALO_STATE, self.W)     # (every slab is >= hw thick)
+        lo = arr[self.lo + off:self.lo + off + n] if self.rank > 0 else None
+        hi = arr[self.hi - off - n:self.hi - off] if self.rank + 1 < self.world else None
         return (lo, hi)
 
-    def _halo_store(self, arr, recv):
+    def _halo_store(self, arr, recv, wide=False):
         """Write received planes into the halo; returns an int64 tensor [2] = (lower halo
         changed, upper halo changed)."""
         changed = torch.zeros(2, dtype=torch.int64, device=self.device)
         bits = torch.uint8 if arr.dtype == torch.uint8 else torch.int64      # bitwise compare
-        for side, src, dst in ((0, recv[0], arr[self.lo - HALO_STATE:self.lo]),
-                               (1, recv[1], arr[self.hi:self.hi + HALO_STATE])):
+        if wide:
+            dsts = (arr[0:self.lo], arr[self.hi:])
+        else:
+            dsts = (arr[self.elo - HALO_STATE:self.elo] if self.rank > 0 else None,
+                    arr[self.ehi:self.ehi + HALO_STATE] if self.rank + 1 < self.world else None)
+        for side, src, dst in ((0, recv[0], dsts[0]), (1, recv[1], dsts[1])):
             if src is None:
                 continue
             src = src.to(self.device)
@@ -188,7 +213,7 @@ class SlabRank:
     # -------------------------------------------------------------------------------- rebuild
     def _fmm_args(self):
         e = self.eng
-        return (ctypes.c_int(3), e._shape_c, e._dx_c, ctypes.c_int(self.lo), ctypes.c_int(self.hi))
+        return (ctypes.c_int(3), e._shape_c, e._dx_c, ctypes.c_int(self.elo), ctypes.c_int(self.ehi))
 
     def rebuild_begin(self, from_band):
         e = self.eng
@@ -199,16 +224,21 @@ class SlabRank:
             _lib.check(_lib.lib.lsml_fmm_workspace_init(
                 _lib.c_i64(e.total), _lib.ptr(e._ws_fmm), e._stream()), "fmm_init")
         from_band = from_band and self._band_is_rebuilt
-        # halo copies of the previous rebuild are stale: far until the first exchange says otherwise
+        # Dirichlet copies of the previous rebuild are stale: far until the first exchange says
+        # otherwise (the ghost planes inside the evaluated range are cleared by the kernels)
         T, m = self.T_view(), e.mask[0]
-        if self.hlo:
-            T[:self.lo].fill_(float("inf")); m[:self.lo].zero_()
-        if self.hhi:
-            T[self.hi:].fill_(float("inf")); m[self.hi:].zero_()
+        if self.elo:
+            T[:self.elo].fill_(float("inf")); m[:self.elo].zero_()
+        if self.ehi < e.shape[0]:
+            T[self.ehi:].fill_(float("inf")); m[self.ehi:].zero_()
+        # u moved on the owned band (searched from the band) and, through the exchange, anywhere
+        # in the ghost planes and next to them (searched densely)
+        dense = _lib.int_array((self.elo, self.lo + 1 if self.rank > 0 else self.elo,
+                                self.hi - 1 if self.rank + 1 < self.world else self.ehi, self.ehi))
         _lib.check(_lib.lib.lsml_fmm_slab_begin(
             *self._fmm_args(), _lib.ptr(e.u), _lib.ptr(e.mask), _lib.ptr(e._ws_fmm),
             _lib.ptr(e.band_idx if from_band else None),
-            _lib.ptr(e.n_band_dev if from_band else None), e._stream()), "fmm_slab_begin")
+            _lib.ptr(e.n_band_dev if from_band else None), dense, e._stream()), "fmm_slab_begin")
 
     def rebuild_march(self):
         e = self.eng
@@ -297,13 +327,13 @@ class SlabVolume:
     process on ``device`` (LocalCollective); pass a TorchCollective under torchrun."""
 
     def __init__(self, shape, world=None, dx=None, band=3.0, specs=(), device="cuda",
-                 collective=None):
+                 collective=None, overlap=OVERLAP):
         self.coll = collective if collective is not None else LocalCollective(int(world))
         self.world = self.coll.world
         self.shape = tuple(int(s) for s in shape)
         self.specs = [tuple(s) for s in specs]
         self.band = float(band)
-        self.ranks = [SlabRank(self.shape, r, self.world, dx, band, self.specs, device)
+        self.ranks = [SlabRank(self.shape, r, self.world, dx, band, self.specs, device, overlap)
                       for r in self.coll.local_ranks]
         self.n_band = 0
         self.rebuild_rounds = 0
@@ -338,15 +368,15 @@ class SlabVolume:
     def _global_stats(self):
         return self.coll.allreduce_sum([r.global_frame_stats() for r in self.ranks])
 
-    def _exchange(self, *getters):
+    def _exchange(self, *getters, wide=False):
         """Halo exchange of one or more local arrays per rank in a single round of messages;
         returns, per rank, the sum over arrays of the (lower, upper) 'changed' flags."""
         arrs = [[g(r) for g in getters] for r in self.ranks]
-        recvs = self.coll.exchange([[r._halo_sends(a) for a in al]
+        recvs = self.coll.exchange([[r._halo_sends(a, wide) for a in al]
                                     for r, al in zip(self.ranks, arrs)])
         out = []
         for r, al, rc in zip(self.ranks, arrs, recvs):
-            flags = [r._halo_store(a, c) for a, c in zip(al, rc)]
+            flags = [r._halo_store(a, c, wide) for a, c in zip(al, rc)]
             out.append(sum(flags[1:], flags[0]))
         return out
 
@@ -401,7 +431,7 @@ class SlabVolume:
         for r, gs in zip(self.ranks, gstats):
             r.assemble(gs.to(r.device))
             r.predict_and_update(regressor, step)
-        self._exchange(lambda r: r.eng.u[0])
+        self._exchange(lambda r: r.eng.u[0], wide=True)
         self._rebuild(from_band=True)
         return nb
 

@@ -341,11 +341,11 @@ int lsml_fmm_rebuild_from_band(int ndim, const int* shape, long long batch, cons
 int lsml_fmm_slab_begin(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
                         const double* u, uint8_t* mask, void* workspace,
                         const long long* prev_band_idx, const long long* prev_n_band,
-                        void* stream) {
+                        const int* dense_planes, void* stream) {
     const long long batch = 1;
     GEOM(g);
     return fmm_slab_begin(g, own_lo, own_hi, u, mask, workspace, prev_band_idx, prev_n_band,
-                          (cudaStream_t)stream);
+                          dense_planes, (cudaStream_t)stream);
 }
 int lsml_fmm_slab_march(int ndim, const int* shape, const double* dx, int own_lo, int own_hi,
                         const double* u, double band, uint8_t* mask, void* workspace,

@@ -1208,7 +1208,7 @@ static void plane_launch_shape(const Geom& g, int planes, dim3& grid, dim3& bloc
 template <int NDIM>
 static int begin_nd(const Geom& g, const FmmGeom& fg, const double* u, const u64* stats, u8* mask,
                     const FmmWorkspace& w, i64 total, const i64* prev_band_idx,
-                    const i64* prev_n_band, cudaStream_t s) {
+                    const i64* prev_n_band, const int (&dense)[4], cudaStream_t s) {
     static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
     fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
     LSML_LAUNCH_CHECK("fmm_clear_kernel");
@@ -1216,22 +1216,19 @@ static int begin_nd(const Geom& g, const FmmGeom& fg, const double* u, const u64
                                          w.ring.cap);
     LSML_LAUNCH_CHECK("fmm_prepare_kernel");
     dim3 grid, block;
-    const bool slab = fg.own_lo > 0 || fg.own_hi < fg.n0;
     if (prev_band_idx != nullptr) {
         fmm_init_band_kernel<NDIM><<<LSML_SMS * 8, 256, 0, s>>>(u, w.T, mask, w.list, fg, stats,
                                                               prev_band_idx, prev_n_band, w.ctr);
         LSML_LAUNCH_CHECK("fmm_init_band_kernel");
-        // a slab's boundary planes can be frozen by a sign change on the neighbour's side
-        if (slab && fg.own_lo > 0) {
-            plane_launch_shape(g, 1, grid, block);
-            fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr,
-                                                        fg.own_lo, fg.own_lo + 1);
-            LSML_LAUNCH_CHECK("fmm_init_kernel");
-        }
-        if (slab && fg.own_hi < fg.n0) {                  // (claims make a repeated plane harmless)
-            plane_launch_shape(g, 1, grid, block);
-            fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr,
-                                                        fg.own_hi - 1, fg.own_hi);
+        // slab decomposition: planes whose interface status can change from the neighbour's side
+        // (the ghost planes a rank evaluates redundantly, and its first/last owned plane) are
+        // searched densely; claims make overlaps with the sparse search harmless
+        for (int q = 0; q < 2; ++q) {
+            const int a = dense[2 * q] < fg.own_lo ? fg.own_lo : dense[2 * q];
+            const int b = dense[2 * q + 1] > fg.own_hi ? fg.own_hi : dense[2 * q + 1];
+            if (b <= a) continue;
+            plane_launch_shape(g, b - a, grid, block);
+            fmm_init_kernel<NDIM><<<grid, block, 0, s>>>(u, w.T, mask, w.list, fg, stats, w.ctr, a, b);
             LSML_LAUNCH_CHECK("fmm_init_kernel");
         }
     } else {
@@ -1263,9 +1260,10 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
     FmmGeom fg;
     if (make_fmm_geom(g, fg)) return 1;
     const double eff_band = band != 0.0 ? band : DBL_MAX;
-    int st = LSML_ND(begin_nd<3>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s),
-                     begin_nd<2>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s),
-                     begin_nd<1>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, s));
+    const int none[4] = {0, 0, 0, 0};
+    int st = LSML_ND(begin_nd<3>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, none, s),
+                     begin_nd<2>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, none, s),
+                     begin_nd<1>(g, fg, u, stats, mask, w, total, prev_band_idx, prev_n_band, none, s));
     if (st) return st;
     st = LSML_ND(march_launch<3>(u, w, mask, total, fg, eff_band, 1, s),
                  march_launch<2>(u, w, mask, total, fg, eff_band, 1, s),
@@ -1292,16 +1290,19 @@ static int slab_geom(const Geom& g, int own_lo, int own_hi, FmmGeom& fg) {
     return 0;
 }
 
+// dense_planes: {a0, b0, a1, b1} -- plane ranges searched densely for the interface in addition
+// to the previous band (ignored on a first rebuild, which searches every evaluated plane)
 int fmm_slab_begin(const Geom& g, int own_lo, int own_hi, const double* u, u8* mask,
                    void* workspace, const i64* prev_band_idx, const i64* prev_n_band,
-                   cudaStream_t s) {
+                   const int* dense_planes, cudaStream_t s) {
     const i64 total = g.voxels * g.batch;
     const FmmWorkspace w = carve(workspace, total);
     FmmGeom fg;
     if (slab_geom(g, own_lo, own_hi, fg)) return 1;
-    return LSML_ND(begin_nd<3>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s),
-                   begin_nd<2>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s),
-                   begin_nd<1>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, s));
+    const int dense[4] = {dense_planes[0], dense_planes[1], dense_planes[2], dense_planes[3]};
+    return LSML_ND(begin_nd<3>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, dense, s),
+                   begin_nd<2>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, dense, s),
+                   begin_nd<1>(g, fg, u, nullptr, mask, w, total, prev_band_idx, prev_n_band, dense, s));
 }
 
 int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, double band, u8* mask,

@@ -75,7 +75,7 @@ int fmm_rebuild(const Geom& g, const double* u, double band, const u64* stats, u
                 const i64* prev_n_band, cudaStream_t s);
 int fmm_slab_begin(const Geom& g, int own_lo, int own_hi, const double* u, u8* mask,
                    void* workspace, const i64* prev_band_idx, const i64* prev_n_band,
-                   cudaStream_t s);
+                   const int* dense_planes, cudaStream_t s);
 int fmm_slab_march(const Geom& g, int own_lo, int own_hi, const double* u, double band, u8* mask,
                    void* workspace, cudaStream_t s);
 int fmm_slab_requeue(const Geom& g, int own_lo, int own_hi, double band, const i64* sides_dev,
