@@ -18,6 +18,13 @@ the final mask inside the timed region).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size 256]
 N > 1: torchrun, one volume per rank (independent items, no data-path collective; weak scaling).
+
+Other BASELINE.json configurations (parity-test cases; measured for DESIGN.md / profiles/, not
+the bench line the driver reads) run with --workload:
+  c4   64^3 crops, 2048 per GPU in one engine (configs[3]; weak scaling, no collective)
+  c2   101^2 images, 1024 in total sharded over the GPUs (configs[1]; strong scaling)
+  c5   ONE --size^3 volume slab-decomposed over the GPUs (configs[4]; NCCL halo exchange +
+       all-reduce, strong scaling; default size 512, 1024 for the full configuration)
 """
 import argparse
 import json
@@ -250,6 +257,185 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------
+# other configurations (--workload c2 | c4 | c5): same metric, same JSON line, shorter evidence
+# --------------------------------------------------------------------------------------------
+def _blob_items(count, shape, seed, r_lo, r_hi, jitter):
+    """`count` items of `shape`: a noisy ball (radius in [r_lo, r_hi] voxels, jittered centre)."""
+    rs = np.random.RandomState(seed)
+    nd = len(shape)
+    ax = [np.arange(s, dtype=np.float64) for s in shape]
+    imgs = np.empty((count,) + tuple(shape))
+    for b in range(count):
+        c = np.array(shape) / 2.0 + rs.uniform(-jitter, jitter, size=nd)
+        rad = rs.uniform(r_lo, r_hi)
+        r2 = 0.0
+        for a in range(nd):
+            sl = [None] * nd
+            sl[a] = slice(None)
+            r2 = r2 + (ax[a][tuple(sl)] - c[a]) ** 2
+        imgs[b] = (r2 < rad * rad).astype(np.float64) + 0.2 * rs.standard_normal(shape)
+    return imgs
+
+
+def _fit_forest(X, y, seed):
+    import warnings
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    rs = np.random.RandomState(seed)
+    sub = rs.choice(X.shape[0], size=min(X.shape[0], 20000), replace=False)
+    reg = Pipeline([("standardscaler", StandardScaler()),
+                    ("regressor", RandomForestRegressor(n_estimators=100, max_samples=300,
+                                                        random_state=rs))])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        reg.fit(X[sub], y[sub])
+    return reg
+
+
+def run_other_workload(args):
+    """c2 / c4: a batch of independent items per rank in ONE engine; c5: one volume over all
+    ranks.  One step = `iters` evolution iterations from the initial level sets."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1 or args.workload == "c5":
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29577")
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    from lsml_b200 import _lib
+    from lsml_b200.core.engine import BandEngine
+    from lsml_b200.core.regressors import export_regressor
+    from lsml_b200.core.sharding import shard_range
+    wl = args.workload
+    if wl == "c5":
+        from sklearn.linear_model import LinearRegression
+        from lsml_b200.core.slab import SlabVolume, TorchCollective
+        n = args.size or 512
+        iters = 20
+        shape = (n, n, n)
+        specs = ([("image_sample", 0.0), ("image_sample", 2.0), ("image_edge", 0.0),
+                  ("image_edge", 2.0), ("band_mean", 2.0), ("band_std", 2.0), ("dist_to_com",),
+                  ("moments", (0, 1, 2), (1, 2)), ("size",)])
+        ax = np.arange(n, dtype=np.float64) - n / 2.0
+        vol = SlabVolume(shape, specs=specs, device=device, collective=TorchCollective())
+        # every rank only materialises the planes it holds (owned + halo); the noise of a plane
+        # depends on the plane's index only, so that halo planes equal the neighbour's planes
+        sl = vol.ranks[0].local_slice()
+        a0 = ax[sl]
+        r = np.sqrt((a0[:, None, None] / 0.30) ** 2 + (ax[None, :, None] / 0.26) ** 2 +
+                    (ax[None, None, :] / 0.22) ** 2) / n          # ellipsoid 300/260/220 at 1024
+        part = (r < 1.0).astype(np.float64)
+        for q, plane in enumerate(range(sl.start, sl.stop)):
+            part[q] += 0.25 * np.random.RandomState(7000 + plane).standard_normal((n, n))
+        u0_part = np.where(np.sqrt(a0[:, None, None] ** 2 + ax[None, :, None] ** 2 +
+                                   ax[None, None, :] ** 2) < 0.146 * n, 1.0, -1.0)
+        del r
+        vol.load_image_parts([part], normalize=True)
+        X = np.random.RandomState(0).randn(64, 14)
+        w = np.zeros(14); w[1] = 0.8
+        reg = export_regressor(LinearRegression().fit(X, X @ w + 0.15), device)
+        u0_t = torch.from_numpy(u0_part).to(device)
+
+        def one_pass():
+            vol.set_level_sets_parts([u0_t])
+            tot = 0
+            for _ in range(iters):
+                tot += vol.step(reg, 0.4)
+            return tot
+        units_are_global = True
+        desc = ("C5: ONE synthetic %d^3 ellipsoid volume slab-decomposed over %d GPU(s) along axis "
+                "0, linear velocity, F=14, band=3, %d iterations per step; NCCL: 2 P2P halo "
+                "exchanges per round, ~3 rounds per rebuild, 3 small all-reduces per iteration"
+                % (n, world, iters))
+        scaling = "strong"
+    else:
+        if wl == "c4":
+            shape, per_rank, iters = (64, 64, 64), args.items or 2048, 30
+            lo, hi = rank * per_rank, (rank + 1) * per_rank
+            imgs = _blob_items(per_rank, shape, 10000 + rank, 6, 18, 8)
+            r_init, scaling = 5.0, "weak"
+            specs = SPECS
+            total_items = per_rank * world
+        else:
+            shape, total_items, iters = (101, 101), args.items or 1024, 10
+            lo, hi = shard_range(total_items, rank, world)
+            imgs = _blob_items(hi - lo, shape, 20000 + rank, 15, 35, 10)
+            r_init, scaling = 10.0, "strong"
+            specs = ([("image_sample", 0.0), ("image_sample", 2.0), ("image_edge", 0.0),
+                      ("image_edge", 2.0), ("band_mean", 0.0), ("band_mean", 2.0),
+                      ("band_std", 0.0), ("band_std", 2.0), ("dist_to_com",),
+                      ("moments", (0, 1), (1, 2)), ("size",), ("boundary_size",),
+                      ("isoperimetric",)])
+        nd = len(shape)
+        eng = BandEngine(shape, hi - lo, dx=np.ones(nd), band=BAND, specs=specs, device=device)
+        eng.load_images(imgs, normalize=True)
+        g = np.indices(shape).astype(np.float64)
+        rc = np.sqrt(sum((g[a] - shape[a] / 2.0) ** 2 for a in range(nd)))
+        u0 = torch.from_numpy(np.where(rc < r_init, 1.0, -1.0)).to(device).expand(
+            (hi - lo,) + tuple(shape)).contiguous()
+        eng.set_level_sets(u0)
+        X = eng.compute_features().cpu().numpy()
+        y = X[:, 1] + 0.2 * np.random.RandomState(1).standard_normal(X.shape[0])
+        reg = export_regressor(_fit_forest(X, y, 5), device)     # one forest reused every iteration
+
+        def one_pass():
+            eng.set_level_sets(u0)
+            tot = 0
+            for _ in range(iters):
+                tot += eng.step(reg, 0.4)
+            return tot
+        units_are_global = False
+        desc = ("%s: %d synthetic %s items (%d on this rank, one engine per GPU), RF-100 velocity, "
+                "F=%d, band=3, %d iterations per step; no data-path collective"
+                % (wl.upper(), total_items, "x".join(map(str, shape)), hi - lo, len(X[0]), iters))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(1, args.warmup)):
+        one_pass()
+    barrier()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    units = 0
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            units += one_pass()
+        ev1.record()
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    cnt = torch.tensor([units, _lib.launch_count() - l0], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if units_are_global:
+            dist.all_reduce(cnt[1:], op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(t[0])
+        print(json.dumps({
+            "metric": "narrow-band voxel-iterations/sec (feat+velocity+update+band rebuild)",
+            "value": int(cnt[0]) / (ms * 1e-3), "unit": "band-voxel-iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc,
+                       "band_voxel_iterations_per_step": int(cnt[0]) // max(1, args.steps)},
+            "gpu_launches": int(cnt[1]), "clocks": clocks.summary()}))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def main():
@@ -258,10 +444,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--size", type=int, default=None, help="volume edge (c3: 256, c5: 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
+    ap.add_argument("--items", type=int, default=0, help="c2: total images, c4: crops per GPU")
     args = ap.parse_args()
+    if args.workload != "c3" and args.impl != "reference":
+        return run_other_workload(args)
+    args.size = args.size or 256
     if args.impl == "reference":
         return run_reference_arm(args)
 

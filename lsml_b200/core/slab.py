@@ -344,7 +344,13 @@ class SlabVolume:
         least its own ``local_slice()`` planes filled in).  Normalisation uses the mean and
         population std of the WHOLE image (model.py:328-329), formed from all-reduced sums."""
         img_t = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img))
-        parts = [img_t[r.local_slice()].to(r.device, dtype=torch.float64) for r in self.ranks]
+        self.load_image_parts([img_t[r.local_slice()] for r in self.ranks], normalize)
+
+    def load_image_parts(self, parts, normalize=True):
+        """Same, from the planes each local rank holds (``SlabRank.local_slice()``), so that no
+        process ever has to materialise the whole volume."""
+        parts = [(p if torch.is_tensor(p) else torch.from_numpy(np.ascontiguousarray(p))).to(
+            r.device, dtype=torch.float64) for p, r in zip(parts, self.ranks)]
         if normalize:
             n = float(np.prod(self.shape))
             own = [p[r.lo:r.hi] for p, r in zip(parts, self.ranks)]
@@ -357,9 +363,13 @@ class SlabVolume:
 
     def set_level_sets(self, u0):
         u_t = u0 if torch.is_tensor(u0) else torch.from_numpy(np.ascontiguousarray(u0))
-        for r in self.ranks:
+        self.set_level_sets_parts([u_t[r.local_slice()] for r in self.ranks])
+
+    def set_level_sets_parts(self, parts):
+        for r, p in zip(self.ranks, parts):
             e = r.eng
-            e.u[0].copy_(u_t[r.local_slice()].to(r.device, dtype=torch.float64))
+            p = p if torch.is_tensor(p) else torch.from_numpy(np.ascontiguousarray(p))
+            e.u[0].copy_(p.to(r.device, dtype=torch.float64))
             r.count_owned()
             r._band_is_rebuilt = False
         self._rebuild(from_band=False)
