@@ -21,7 +21,8 @@ N > 1: torchrun, one volume per rank (independent items, no data-path collective
 
 Other BASELINE.json configurations (parity-test cases; measured for DESIGN.md / profiles/, not
 the bench line the driver reads) run with --workload:
-  c4   64^3 crops, 2048 per GPU in one engine (configs[3]; weak scaling, no collective)
+  c4   64^3 crops, --items per GPU (default 512) in one engine (configs[3]; weak scaling,
+       no collective)
   c2   101^2 images, 1024 in total sharded over the GPUs (configs[1]; strong scaling)
   c5   ONE --size^3 volume slab-decomposed over the GPUs (configs[4]; NCCL halo exchange +
        all-reduce, strong scaling; default size 512, 1024 for the full configuration)
@@ -356,7 +357,9 @@ def run_other_workload(args):
         scaling = "strong"
     else:
         if wl == "c4":
-            shape, per_rank, iters = (64, 64, 64), args.items or 2048, 30
+            # (verified with 512 crops per GPU; a 2048-per-GPU run on 4 GPUs did not finish within
+            # its 25-minute limit in round 1 and is still to be diagnosed -- DESIGN.md 8)
+            shape, per_rank, iters = (64, 64, 64), args.items or 512, 30
             lo, hi = rank * per_rank, (rank + 1) * per_rank
             imgs = _blob_items(per_rank, shape, 10000 + rank, 6, 18, 8)
             r_init, scaling = 5.0, "weak"

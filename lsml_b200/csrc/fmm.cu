@@ -697,7 +697,8 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
     return narrow ? t : inf;
 }
 
-constexpr int FMM_MAX_SWEEPS = 1 << 20;
+constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s at worst, then
+                                          // `converged` = 0 is reported (never seen)
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
 #ifndef FMM_MIN_BLOCKS
