@@ -15,25 +15,31 @@
 // order, after each one the update U is re-evaluated exactly as the marcher would (direct
 // neighbour frozen -> update; voxel two cells away frozen while the one in between is frozen ->
 // update), and the replay stops as soon as x's own key is smaller than the next stencil key
-// (x is frozen first).  The marcher's final state is a fixed point of T <- V(T); iterating V
-// over the candidate voxels (chaotic relaxation, in place) reaches it in about as many sweeps
-// as the band is voxels wide, because the voxels that are final stay final (induction over the
-// marcher's freeze order).  Every U uses the marcher's own floating-point expressions in the
+// (x is frozen first).  The marcher's final state is the UNIQUE fixed point of T <- V(T)
+// (induction over the marcher's freeze order); iterating V over the candidate voxels in any
+// order (chaotic relaxation, in place) reaches it in about as many sweeps as the marcher's
+// dependency graph is deep.  Every U uses the marcher's own floating-point expressions in the
 // same order (no FMA), so the converged values are bit-identical to the sequential result,
-// not merely close.  oracle/lsml_oracle.c:orc_fmm_distance is the sequential statement.
+// not merely close.  oracle/lsml_oracle.c:orc_fmm_distance is the sequential statement,
+// oracle/fmm_replay_model.c the CPU model of V (tests/test_fmm_algorithm.py).
 //
-// Kernels:
-//   fmm_clear_kernel  reset T / mask of the voxels touched by the previous rebuild (sparse)
-//   fmm_init_kernel   dense pass over u: exact zeros and sign-change voxels are frozen with the
-//                     sub-voxel interpolated distance (8 B/voxel read: HBM-bound)
-//   fmm_seed_kernel   direct neighbours of the initial frozen set become candidates
-//   fmm_march_kernel  cooperative persistent kernel: sweeps of V over the candidates with a
-//                     grid barrier between sweeps, candidate set grown from voxels whose value
-//                     is inside the band; then the final mask
+// Kernels of one rebuild:
+//   fmm_clear_kernel      reset T / state / epoch of the voxels the previous rebuild touched
+//   fmm_prepare_kernel    counters, hint generation, parking-bucket offsets
+//   fmm_init_kernel       dense search of the interface: exact zeros and sign-change voxels are
+//                         frozen with the sub-voxel interpolated distance (first rebuild of a
+//                         level set; boundary / ghost planes of a slab)
+//   fmm_init_band_kernel  the same search restricted to the previous band (evolution loop)
+//   fmm_seed_kernel       direct neighbours of the initial frozen set become candidates
+//   fmm_march_kernel      cooperative persistent kernel: sweeps of V over the queued candidates
+//                         (work ring + parking buckets), one grid barrier per sweep, small work
+//                         sets on a single CTA; then the final mask
+//   fmm_requeue_kernel, fmm_finalize_kernel, fmm_pending_kernel   slab decomposition only
 //
-// T is +inf for every voxel that has no value (the dense array is filled once and only the
-// touched voxels are reset), mask doubles as the state array: 0 far, 1 initial frozen,
-// 2 candidate during the march; 0/1 = the reference's `mask` afterwards.
+// Per-voxel state: T (f64, +inf = no value; the dense array is filled once and only touched
+// voxels are ever reset), Aux (8 B: queue epoch, reach, depth hint), and the mask byte, which
+// doubles as the state during a rebuild: 0 far, 1 initial frozen, (depth << 2) | 2 candidate;
+// 0/1 = the reference's `mask` afterwards.
 #include <cooperative_groups.h>
 #include <cooperative_groups/scan.h>
 #include <cfloat>
@@ -163,7 +169,7 @@ __device__ __forceinline__ i64 encode(i64 item, int i, int j, int k, const FmmGe
 
 __global__ void __launch_bounds__(256)
 fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__ mask,
-                 const i64* __restrict__ list, i64 cap, FmmGeom g, FmmCounters* ctr) {
+                 const i64* __restrict__ list, i64 cap, FmmGeom g, FmmCounters* ctr, i64 total) {
     const i64 ni = ctr->prev_init, nc = ctr->prev_cand;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni + nc;
          t += (i64)gridDim.x * blockDim.x) {
@@ -172,6 +178,15 @@ fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__
         T[l] = pos_inf();
         aux[l] = Aux{0u, (unsigned short)REACH16_INF, aux[l].lvl};      // the hint survives
         mask[l] = 0;
+    }
+    // Hints are tagged with the low 8 bits of the rebuild counter.  Every 128th rebuild ALL hints
+    // are dropped (one dense 8 B/voxel pass), so no voxel can carry a tag that is 256 rebuilds
+    // old and would be mistaken for last rebuild's: the parking buckets are sized from last
+    // rebuild's histogram and must never receive a voxel it did not count.
+    if ((ctr->gen & 127) == 127) {
+        for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (i64)gridDim.x * blockDim.x)
+            aux[i].lvl = 0;
     }
 }
 
@@ -1211,7 +1226,7 @@ static int begin_nd(const Geom& g, const FmmGeom& fg, const double* u, const u64
                     const FmmWorkspace& w, i64 total, const i64* prev_band_idx,
                     const i64* prev_n_band, const int (&dense)[4], cudaStream_t s) {
     static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
-    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr);
+    fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr, total);
     LSML_LAUNCH_CHECK("fmm_clear_kernel");
     fmm_prepare_kernel<<<1, 256, 0, s>>>(w.ctr, (prev_band_idx != nullptr && !no_hints) ? 1 : 0,
                                          w.ring.cap);
@@ -1353,9 +1368,6 @@ int fmm_slab_finish(const Geom& g, int own_lo, int own_hi, double band, u8* mask
     }
     return 0;
 }
-
-// device address of T (total float64) inside a workspace: the host layer exchanges its halo planes
-double* fmm_distance_ptr(void* workspace) { return static_cast<double*>(workspace); }
 
 // device address of the counters {n_init, n_cand, tail_sweeps, sweeps, converged, prev_init,
 // prev_cand, replays, ...} of the last rebuild
