@@ -49,6 +49,54 @@ def plane_ranges(n0, world):
     return [(r * n0 // world, (r + 1) * n0 // world) for r in range(world)]
 
 
+class SlabLayout:
+    """Index bookkeeping of one rank's local grid (pure integers; tested on the CPU).
+
+    Local plane q of rank r is plane ``origin0 + q`` of the volume.  ``[lo, hi)`` are the owned
+    planes, ``[elo, ehi)`` the planes the band rebuild evaluates (owned + ``W`` ghost planes
+    beyond each cut), ``hw`` the halo width kept on each side of an interior cut."""
+
+    def __init__(self, n0, rank, world, halo_needed=0, overlap=8):
+        self.n0, self.rank, self.world = int(n0), int(rank), int(world)
+        ranges = plane_ranges(self.n0, self.world)
+        self.A, self.B = ranges[rank]
+        thick = min(b - a for a, b in ranges)
+        if world > 1 and thick < HALO_STATE:
+            raise ValueError("every slab needs at least %d planes" % HALO_STATE)
+        self.W = max(0, min(int(overlap), thick - HALO_STATE - 1)) if world > 1 else 0
+        # ghost planes + Dirichlet planes + one more plane of u, or the widest axis-0 Gaussian
+        self.hw = max(self.W + HALO_STATE + 1, int(halo_needed)) if world > 1 else 0
+        if world > 1 and thick < self.hw:
+            raise ValueError("slabs of %d planes are thinner than the %d-plane halo they have to "
+                             "supply to their neighbours: use fewer ranks" % (thick, self.hw))
+        self.hlo = min(self.hw, self.A)
+        self.hhi = min(self.hw, self.n0 - self.B)
+        self.lo, self.hi = self.hlo, self.hlo + (self.B - self.A)
+        self.origin0 = self.A - self.hlo
+        self.nloc = self.hi + self.hhi
+        self.elo = self.lo - self.W if rank > 0 else 0
+        self.ehi = self.hi + self.W if rank + 1 < world else self.nloc
+
+    def send_slices(self, wide):
+        """(slice sent to the lower neighbour, slice sent to the upper neighbour), local planes.
+        ``wide``: the whole halo width (u); otherwise the two Dirichlet planes just outside the
+        neighbour's evaluated range, which lie ``W`` planes inside this rank's owned range."""
+        n, off = (self.hw, 0) if wide else (HALO_STATE, self.W)
+        lo = slice(self.lo + off, self.lo + off + n) if self.rank > 0 else None
+        hi = slice(self.hi - off - n, self.hi - off) if self.rank + 1 < self.world else None
+        return lo, hi
+
+    def recv_slices(self, wide):
+        """(slice filled from the lower neighbour, slice filled from the upper neighbour)."""
+        if wide:
+            lo = slice(0, self.lo) if self.rank > 0 else None
+            hi = slice(self.hi, self.nloc) if self.rank + 1 < self.world else None
+        else:
+            lo = slice(self.elo - HALO_STATE, self.elo) if self.rank > 0 else None
+            hi = slice(self.ehi, self.ehi + HALO_STATE) if self.rank + 1 < self.world else None
+        return lo, hi
+
+
 class LocalCollective:
     """All ranks live in this process: ``parts`` arguments are lists with one entry per rank."""
 
@@ -120,30 +168,18 @@ class SlabRank:
             raise ValueError("slab decomposition is for 3-D volumes")
         self.gshape = tuple(int(s) for s in shape)
         self.rank, self.world = rank, world
-        self.A, self.B = plane_ranges(self.gshape[0], world)[rank]
-        if self.B - self.A < HALO_STATE and world > 1:
-            raise ValueError("every slab needs at least %d planes" % HALO_STATE)
         dx = np.ones(3) if dx is None else np.asarray(dx, dtype=np.float64)
-        # halo wide enough for the axis-0 Gaussians of the image planes (one-time) and the
-        # two-plane stencil reach of the band rebuild (every iteration)
-        thick = min(b - a for a, b in plane_ranges(self.gshape[0], world))
-        self.W = max(0, min(int(overlap), thick - HALO_STATE - 1)) if world > 1 else 0
-        hw = self.W + HALO_STATE + 1          # ghost planes + Dirichlet planes + one more of u
+        # halo wide enough for the axis-0 Gaussians of the image planes (one-time) and for the
+        # ghost + Dirichlet planes of the band rebuild (every iteration)
+        gauss = 0
         for spec in specs:
             if spec[0] in ("image_sample", "image_edge", "band_mean", "band_std") and spec[1] > 0:
-                hw = max(hw, gaussian_weights(float(spec[1]) / dx[0], 0)[1])
-        if world > 1 and thick < hw:
-            raise ValueError("slabs of %d planes are thinner than the %d-plane halo they have to "
-                             "supply to their neighbours: use fewer ranks" % (thick, hw))
-        self.hw = hw
-        self.hlo = min(hw, self.A) if world > 1 else 0
-        self.hhi = min(hw, self.gshape[0] - self.B) if world > 1 else 0
-        self.lo, self.hi = self.hlo, self.hlo + (self.B - self.A)       # owned planes, local
-        self.origin0 = self.A - self.hlo                                # local plane 0 in the volume
-        lshape = (self.hi + self.hhi,) + self.gshape[1:]
-        # planes this rank EVALUATES in the band rebuild: owned + W ghost planes beyond each cut
-        self.elo = self.lo - self.W if rank > 0 else 0
-        self.ehi = self.hi + self.W if rank + 1 < world else lshape[0]
+                gauss = max(gauss, gaussian_weights(float(spec[1]) / dx[0], 0)[1])
+        self.layout = lay = SlabLayout(self.gshape[0], rank, world, gauss, overlap)
+        self.A, self.B, self.W, self.hw = lay.A, lay.B, lay.W, lay.hw
+        self.hlo, self.hhi, self.lo, self.hi = lay.hlo, lay.hhi, lay.lo, lay.hi
+        self.origin0, self.elo, self.ehi = lay.origin0, lay.elo, lay.ehi
+        lshape = (lay.nloc,) + self.gshape[1:]
         self.eng = BandEngine(lshape, 1, dx=dx, band=band, specs=specs, device=device)
         self.plane = self.gshape[1] * self.gshape[2]
         self.device = self.eng.device
@@ -160,27 +196,19 @@ class SlabRank:
         return e._ws_fmm[:e.total * 8].view(torch.float64).view(e.shape)
 
     def _halo_sends(self, arr, wide=False):
-        """(planes for the lower neighbour, planes for the upper neighbour) of a local array.
-        ``wide``: the whole halo width (u); otherwise the two Dirichlet planes just outside the
-        neighbour's evaluated range, which lie ``W`` planes inside this rank's owned range."""
-        n, off = (self.hw, 0) if wide else (HALO_STATE, self.W)     # (every slab is >= hw thick)
-        lo = arr[self.lo + off:self.lo + off + n] if self.rank > 0 else None
-        hi = arr[self.hi - off - n:self.hi - off] if self.rank + 1 < self.world else None
-        return (lo, hi)
+        """(planes for the lower neighbour, planes for the upper neighbour) of a local array."""
+        lo, hi = self.layout.send_slices(wide)
+        return (None if lo is None else arr[lo], None if hi is None else arr[hi])
 
     def _halo_store(self, arr, recv, wide=False):
         """Write received planes into the halo; returns an int64 tensor [2] = (lower halo
         changed, upper halo changed)."""
         changed = torch.zeros(2, dtype=torch.int64, device=self.device)
         bits = torch.uint8 if arr.dtype == torch.uint8 else torch.int64      # bitwise compare
-        if wide:
-            dsts = (arr[0:self.lo], arr[self.hi:])
-        else:
-            dsts = (arr[self.elo - HALO_STATE:self.elo] if self.rank > 0 else None,
-                    arr[self.ehi:self.ehi + HALO_STATE] if self.rank + 1 < self.world else None)
-        for side, src, dst in ((0, recv[0], dsts[0]), (1, recv[1], dsts[1])):
-            if src is None:
+        for side, src, sl in zip((0, 1), recv, self.layout.recv_slices(wide)):
+            if src is None or sl is None:
                 continue
+            dst = arr[sl]
             src = src.to(self.device)
             changed[side] = (dst.view(bits) != src.view(bits)).any().to(torch.int64)
             dst.copy_(src)

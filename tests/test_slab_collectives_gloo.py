@@ -67,3 +67,55 @@ def test_torch_collective_matches_local_collective():
                     assert np.array_equal(got[a][side], w.numpy()), (r, a, side)
     # rank 1 received rank 0's "to upper" planes from below and rank 2's "to lower" from above
     assert float(res[1][0][0][0][0, 0, 0]) == 0.5 and float(res[1][0][0][1][0, 0, 0]) == 2.25
+
+
+def test_slab_layout_halo_exchange_is_consistent():
+    """Pure index bookkeeping of the slab decomposition (no GPU): what a rank sends is exactly
+    what its neighbour expects, in volume coordinates; the Dirichlet planes sit just outside the
+    receiver's evaluated range; a simulated exchange fills every halo with the owner's planes."""
+    from lsml_b200.core.slab import HALO_STATE, LocalCollective, SlabLayout
+    for n0, world, gauss, overlap in [(40, 3, 6, 8), (37, 4, 6, 8), (24, 2, 0, 8), (1024, 8, 8, 8),
+                                      (128, 4, 12, 16), (64, 2, 0, 0), (30, 1, 8, 8), (96, 3, 0, 3)]:
+        lays = [SlabLayout(n0, r, world, gauss, overlap) for r in range(world)]
+        assert lays[0].A == 0 and lays[-1].B == n0
+        for r, L in enumerate(lays):
+            assert 0 <= L.elo <= L.lo < L.hi <= L.ehi <= L.nloc
+            assert L.origin0 + L.lo == L.A and L.origin0 + L.hi == L.B
+            if world > 1:
+                assert L.hw >= L.W + HALO_STATE + 1 and L.hw >= gauss
+            if r > 0:
+                assert L.lo - L.elo == L.W and L.elo >= HALO_STATE      # room for Dirichlet planes
+            if r + 1 < world:
+                assert L.ehi - L.hi == L.W and L.nloc - L.ehi >= HALO_STATE
+        for wide in (False, True):
+            for r in range(world - 1):
+                lo_rank, hi_rank = lays[r], lays[r + 1]
+                send_up = lo_rank.send_slices(wide)[1]          # r -> r+1
+                recv_lo = hi_rank.recv_slices(wide)[0]
+                send_dn = hi_rank.send_slices(wide)[0]          # r+1 -> r
+                recv_hi = lo_rank.recv_slices(wide)[1]
+                g = lambda L, s: (L.origin0 + s.start, L.origin0 + s.stop)
+                assert g(lo_rank, send_up) == g(hi_rank, recv_lo), (n0, world, wide, r)
+                assert g(hi_rank, send_dn) == g(lo_rank, recv_hi), (n0, world, wide, r)
+                # the sender owns what it sends
+                assert lo_rank.lo <= send_up.start and send_up.stop <= lo_rank.hi
+                assert hi_rank.lo <= send_dn.start and send_dn.stop <= hi_rank.hi
+                if not wide:
+                    assert recv_lo.stop == hi_rank.elo and recv_hi.start == lo_rank.ehi
+        # simulated exchange of a volume whose plane p holds the value p
+        coll = LocalCollective(world)
+        vol = torch.arange(n0, dtype=torch.float64)[:, None].repeat(1, 3)
+        local = []
+        for L in lays:
+            a = vol[L.origin0:L.origin0 + L.nloc].clone()
+            a[:L.lo] = -1.0
+            a[L.hi:] = -1.0                                     # halos unknown
+            local.append(a)
+        sends = [[tuple(None if s is None else a[s] for s in L.send_slices(True))]
+                 for L, a in zip(lays, local)]
+        recvs = coll.exchange(sends)
+        for L, a, rc in zip(lays, local, recvs):
+            for src, sl in zip(rc[0], L.recv_slices(True)):
+                if sl is not None:
+                    a[sl] = src
+            assert torch.equal(a, vol[L.origin0:L.origin0 + L.nloc]), (n0, world)
