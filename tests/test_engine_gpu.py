@@ -228,7 +228,8 @@ def test_full_step_against_oracle(oracle, shape, dx):
                 np.abs(u_g[b] - u_o[b]).max()
 
 
-@pytest.mark.parametrize("shape,dx", [((61, 47), (1.0, 1.0)), ((26, 31, 28), (1.0, 1.0, 1.0))])
+@pytest.mark.parametrize("shape,dx", [((61, 47), (1.0, 1.0)), ((26, 31, 28), (1.0, 1.0, 1.0)),
+                                      ((64, 72, 80), (1.0, 0.9, 1.1))])
 def test_incremental_statistics_and_sparse_rebuild_match_dense(shape, dx):
     """After several iterations the {u>0} statistics maintained from sign changes in the scatter
     kernel equal a dense recount, and the band found from the previous band (sparse interface
