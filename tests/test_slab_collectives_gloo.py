@@ -119,3 +119,52 @@ def test_slab_layout_halo_exchange_is_consistent():
                 if sl is not None:
                     a[sl] = src
             assert torch.equal(a, vol[L.origin0:L.origin0 + L.nloc]), (n0, world)
+
+
+def test_slab_volume_exchange_plumbing_with_stub_engine(monkeypatch):
+    """SlabVolume._exchange / SlabRank._halo_sends / _halo_store on CPU tensors: the engine (which
+    needs a GPU) is replaced by a stub that only owns the arrays, so that the exchange code the
+    GPU tests and torchrun jobs run is also exercised in the CPU tier."""
+    from lsml_b200.core import slab
+
+    class StubEngine:
+        def __init__(self, shape, batch, dx=None, band=3.0, specs=(), device="cpu"):
+            self.shape, self.device = tuple(shape), torch.device("cpu")
+            self.total = int(np.prod(shape))
+            self.u = torch.zeros((1,) + self.shape, dtype=torch.float64)
+            self.mask = torch.zeros((1,) + self.shape, dtype=torch.uint8)
+
+    monkeypatch.setattr(slab, "BandEngine", StubEngine)
+    shape, world = (48, 5, 6), 3
+    vol = slab.SlabVolume(shape, world=world, specs=[("image_sample", 2.0)], device="cpu")
+    full_u = torch.arange(48, dtype=torch.float64)[:, None, None].expand(shape).contiguous()
+    full_m = (torch.arange(48) % 7).to(torch.uint8)[:, None, None].expand(shape).contiguous()
+    for r in vol.ranks:
+        sl = r.local_slice()
+        r.eng.u[0].copy_(full_u[sl])
+        r.eng.mask[0].copy_(full_m[sl])
+        r.eng.u[0, :r.lo] = -1
+        r.eng.u[0, r.hi:] = -1                      # halos unknown
+    flags = vol._exchange(lambda r: r.eng.u[0], wide=True)
+    for r, f in zip(vol.ranks, flags):
+        assert torch.equal(r.eng.u[0], full_u[r.local_slice()])
+        assert f.tolist() == [1 if r.rank > 0 else 0, 1 if r.rank + 1 < world else 0]
+    # a second exchange changes nothing
+    assert all(f.tolist() == [0, 0] for f in vol._exchange(lambda r: r.eng.u[0], wide=True))
+    # Dirichlet planes of two arrays in one round: they land just outside the evaluated range
+    for r in vol.ranks:
+        r.eng.u[0, :r.elo] = -5
+        r.eng.u[0, r.ehi:] = -5
+        r.eng.mask[0, :r.elo] = 99
+        r.eng.mask[0, r.ehi:] = 99
+    vol._exchange(lambda r: r.eng.u[0], lambda r: r.eng.mask[0])
+    for r in vol.ranks:
+        g = r.local_slice()
+        if r.rank > 0:
+            assert torch.equal(r.eng.u[0, r.elo - 2:r.elo], full_u[g][r.elo - 2:r.elo])
+            assert torch.equal(r.eng.mask[0, r.elo - 2:r.elo], full_m[g][r.elo - 2:r.elo])
+            if r.elo > 2:
+                assert (r.eng.u[0, :r.elo - 2] == -5).all()       # nothing else was touched
+        if r.rank + 1 < world:
+            assert torch.equal(r.eng.u[0, r.ehi:r.ehi + 2], full_u[g][r.ehi:r.ehi + 2])
+            assert torch.equal(r.eng.mask[0, r.ehi:r.ehi + 2], full_m[g][r.ehi:r.ehi + 2])
