@@ -488,6 +488,19 @@ __device__ __forceinline__ bool second_order_ok(double d2, float q2, double v1, 
     return v1 == 0.0 || d2 * v1 < 0 || q2 <= k1;
 }
 
+// Candidate contributor rule for round 2 (DESIGN.md 4.6 "Known limit"), OFF unless the library is
+// built with -DLSML_FMM_RULE_R2 and the oracle runs with LSML_ORACLE_RULE_R2=1: a second
+// neighbour of opposite sign lies across the interface and is exempt from the causality test
+// and from eviction.
+__device__ __forceinline__ bool across(const AxisState& a) {
+#ifdef LSML_FMM_RULE_R2
+    return a.v2 * a.v1 < 0;
+#else
+    (void)a;
+    return false;
+#endif
+}
+
 // The quadratic of oracle/lsml_oracle.c:fmm_solve on the contributors in `ax` -- the same
 // expressions in the same order, including the causality rule: a root that is not larger in
 // magnitude than a value it was computed from (or a non-positive discriminant) removes the
@@ -531,7 +544,7 @@ __device__ __forceinline__ double solve_quadratic(const AxisState (&in)[3], cons
             for (int ax = 3 - NDIM; ax < 3; ++ax) {
                 if (!active[ax]) continue;
                 if (qr <= in[ax].k1) causal = false;
-                if (second[ax] && qr <= in[ax].k2) causal = false;
+                if (second[ax] && !across(in[ax]) && qr <= in[ax].k2) causal = false;
             }
             if (causal) return r;
         }
@@ -543,7 +556,7 @@ __device__ __forceinline__ double solve_quadratic(const AxisState (&in)[3], cons
 #pragma unroll
         for (int ax = 3 - NDIM; ax < 3; ++ax) {
             if (!active[ax]) continue;
-            if (second[ax] && in[ax].k2 > wv) { wv = in[ax].k2; worst = ax; worst_is_v2 = true; }
+            if (second[ax] && !across(in[ax]) && in[ax].k2 > wv) { wv = in[ax].k2; worst = ax; worst_is_v2 = true; }
             if (in[ax].k1 > wv) { wv = in[ax].k1; worst = ax; worst_is_v2 = false; }
         }
 #pragma unroll

@@ -27,6 +27,16 @@ typedef uint32_t u32;
 
 static inline float qmag(double d) { return (float)fabs(d); }
 
+/* Candidate contributor rule for round 2 (DESIGN.md 4.6 "Known limit"), OFF unless the
+ * environment says LSML_ORACLE_RULE_R2=1 (and liblsml_b200.so was built with
+ * -DLSML_FMM_RULE_R2): a second neighbour of opposite sign lies across the interface and is
+ * exempt from the causality test and from eviction. */
+static int across(double v1, double v2) {
+    static int rule = -1;
+    if (rule < 0) { const char *e = getenv("LSML_ORACLE_RULE_R2"); rule = (e && e[0] == '1') ? 1 : 0; }
+    return rule && v2 * v1 < 0;
+}
+
 typedef struct {
     int ndim, shape[3];
     long st[3], size;
@@ -76,14 +86,14 @@ static double sm_solve(int ndim, const double *idx2, const double *v1in, const d
             for (int ax = 0; ax < ndim; ++ax) {
                 if (!active[ax]) continue;
                 if (qmag(r) <= qmag(v1[ax])) causal = 0;
-                if (v2[ax] < DBL_MAX && qmag(r) <= qmag(v2[ax])) causal = 0;
+                if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && qmag(r) <= qmag(v2[ax])) causal = 0;
             }
             if (causal) return r;
         }
         int worst = -1, worst_is_v2 = 0; float wv = -1.0f;
         for (int ax = 0; ax < ndim; ++ax) {
             if (!active[ax]) continue;
-            if (v2[ax] < DBL_MAX && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = 1; }
+            if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = 1; }
             if (qmag(v1[ax]) > wv) { wv = qmag(v1[ax]); worst = ax; worst_is_v2 = 0; }
         }
         if (worst_is_v2) v2[worst] = DBL_MAX; else { active[worst] = 0; nactive--; }

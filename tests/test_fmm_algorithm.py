@@ -221,4 +221,7 @@ def test_known_limit_nonmonotone_freeze_order(oracle):
         d, m, sweeps = fixed_point(oracle, u, dx, band, jacobi)
         assert sweeps > 0 and np.array_equal(m, wm)
         assert np.abs(d - wd).max() < 1e-6
-        assert 0 < (d != wd).sum() < 100
+        if os.environ.get("LSML_ORACLE_RULE_R2") == "1":     # candidate rule: the limit is gone
+            assert np.array_equal(d, wd)
+        else:
+            assert 0 < (d != wd).sum() < 100
