@@ -118,7 +118,9 @@ int lsml_contour_length(int ndim, const int *shape, long long batch, const doubl
                         const double *dx, double *boundary, void *workspace, void *stream);
 /* Feature program: column f has kind[f] in {0 plane sample (a=plane), 1 distance to centre of
  * mass, 2 band mean (a=plane), 3 band std (a=plane), 4 size, 5 boundary size, 6 isoperimetric
- * ratio, 7 moment (a=axis, b=order)}.  kind/a/b are HOST int arrays of length nfeat (<= 64). */
+ * ratio, 7 moment (a=axis, b=order), 8 COMRaySample column (image.py:124-171; a=plane holding
+ * the raw image, b = sample index j | n_samples << 16; 2-D/3-D, not on slabs)}.  kind/a/b are
+ * HOST int arrays of length nfeat (<= 64). */
 int lsml_item_features(int nfeat, const int *kind, const int *a, const int *b, int ndim,
                        const int *shape, long long batch, const double *dx, int nplanes,
                        const unsigned long long *stats, const double *band_mean,

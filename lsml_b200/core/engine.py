@@ -31,6 +31,7 @@ from .regressors import export_regressor
 
 FK_PLANE, FK_DIST_COM, FK_BAND_MEAN, FK_BAND_STD = 0, 1, 2, 3
 FK_SIZE, FK_BOUNDARY, FK_ISOPERIMETRIC, FK_MOMENT = 4, 5, 6, 7
+FK_COM_RAY = 8
 
 
 def gaussian_kernel1d(sigma, order, radius):
@@ -104,6 +105,16 @@ class FeatureProgram:
                         kind.append(FK_MOMENT); a.append(int(axis)); b.append(int(order))
             elif k == "dist_to_com":
                 kind.append(FK_DIST_COM); a.append(0); b.append(0)
+            elif k == "com_ray":
+                # COMRaySample: 2*n_samples columns reading the RAW image (image.py:147-171)
+                n_samples = int(spec[1])
+                if ndim not in (2, 3):
+                    raise ValueError("`ndim` must be either 2 or 3")
+                if not 1 <= n_samples < 32768:
+                    raise ValueError("COMRaySample: n_samples must be in 1..32767")
+                plane = self._plane("sample", 0.0)
+                for j in range(2 * n_samples):
+                    kind.append(FK_COM_RAY); a.append(plane); b.append(j | (n_samples << 16))
             else:
                 raise NotImplementedError(
                     "no device kernel registered for feature spec %r (there is no CPU "

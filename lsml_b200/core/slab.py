@@ -173,6 +173,10 @@ class SlabRank:
         # ghost + Dirichlet planes of the band rebuild (every iteration)
         gauss = 0
         for spec in specs:
+            if spec[0] == "com_ray":
+                raise NotImplementedError(
+                    "COMRaySample reads the image along a ray through the whole volume and is "
+                    "not available on slab-decomposed volumes")
             if spec[0] in ("image_sample", "image_edge", "band_mean", "band_std") and spec[1] > 0:
                 gauss = max(gauss, gaussian_weights(float(spec[1]) / dx[0], 0)[1])
         self.layout = lay = SlabLayout(self.gshape[0], rank, world, gauss, overlap)

@@ -16,6 +16,7 @@
 //   item_features_kernel  turns the raw sums into the per-item ("global") feature values
 //   assemble_kernel       writes the (B, F) feature matrix in band order (feature_map.py:53-80)
 #include "lsml_internal.h"
+#include "com_ray.cuh"
 
 namespace lsml {
 
@@ -297,6 +298,7 @@ enum FeatKind {
     FK_BOUNDARY = 5,
     FK_ISOPERIMETRIC = 6,
     FK_MOMENT = 7,      // a = axis (0..ndim-1), b = order (1 or 2)
+    FK_COM_RAY = 8,     // a = plane index of the raw image, b = sample j | (n_samples << 16) (local)
 };
 
 struct FeatProgram {
@@ -312,6 +314,7 @@ struct ItemGeom {
     double dx[3];      // padded
     double pdx;        // prod(dx) over real axes, multiplied left to right
     int origin0;       // index of the local grid's first axis-0 plane in the whole volume (slabs)
+    int n0;            // extent of the (padded) first axis
 };
 
 // moment of `order` along padded axis ax from the exact integer sums
@@ -398,6 +401,15 @@ assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
             if (geo.ndim >= 2) { const double d = j * geo.dx[1] - c[1]; acc = geo.ndim == 2 ? d * d : acc + d * d; }
             { const double d = k * geo.dx[2] - c[2]; acc = geo.ndim == 1 ? d * d : acc + d * d; }
             v = sqrt(acc);
+        } else if (kind == FK_COM_RAY) {
+            // COMRaySample (image.py:147-171): the raw image along the voxel -> centroid ray
+            const i64 loc = g - item * voxels;
+            const i64 r = loc / n2;
+            const int idx[3] = {(int)(r / n1) + geo.origin0, (int)(r % n1), (int)(loc % n2)};
+            const int ext[3] = {geo.n0, n1, n2};
+            v = com_ray_sample(planes + (i64)prog.a[f] * plane_stride + item * voxels, geo.ndim,
+                               ext, geo.dx, com + item * 3, idx, prog.b[f] & 0xffff,
+                               prog.b[f] >> 16);
         } else {
             v = item_feat[item * prog.nfeat + f];
         }
@@ -569,7 +581,7 @@ int item_features(const FeatProgram& prog, const Geom& g, int nplanes, const u64
     double pdx = 1.0;
     for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
     for (int a = geo.pad; a < 3; ++a) pdx = (a == geo.pad) ? g.dx[a] : pdx * g.dx[a];
-    geo.pdx = pdx; geo.origin0 = 0;
+    geo.pdx = pdx; geo.origin0 = 0; geo.n0 = g.n[0];
     item_features_kernel<<<(unsigned)((g.batch + 127) / 128), 128, 0, s>>>(
         prog, geo, g.batch, nplanes, stats, band_mean, band_std, boundary, item_feat, com);
     LSML_LAUNCH_CHECK("item_features_kernel");
@@ -583,7 +595,7 @@ int assemble_features(const FeatProgram& prog, const Geom& g, const i64* band_id
     ItemGeom geo;
     geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
     for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
-    geo.pdx = 1.0; geo.origin0 = origin0;
+    geo.pdx = 1.0; geo.origin0 = origin0; geo.n0 = g.n[0];
     assemble_kernel<<<LSML_SMS * 8, 256, 0, s>>>(prog, geo, g.n[1], g.n[2], g.voxels, band_idx,
                                                   n_band, planes, plane_stride, item_feat, com, X);
     LSML_LAUNCH_CHECK("assemble_kernel");
@@ -601,6 +613,10 @@ static int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a
         p.kind[f] = kind[f]; p.a[f] = a[f]; p.b[f] = b[f];
         if (kind[f] == FK_MOMENT && (b[f] < 1 || b[f] > 2)) {
             set_error("Moments: only orders 1 and 2 are implemented on the device (got %d)", b[f]);
+            return 1;
+        }
+        if (kind[f] == FK_COM_RAY && ((b[f] >> 16) < 1 || (b[f] & 0xffff) >= 2 * (b[f] >> 16))) {
+            set_error("COMRaySample: sample %d of n_samples %d", b[f] & 0xffff, b[f] >> 16);
             return 1;
         }
     }
@@ -622,6 +638,14 @@ int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, 
                         int origin0, cudaStream_t s) {
     FeatProgram p;
     if (fill_program(p, nfeat, kind, a, b)) return 1;
+    for (int f = 0; f < nfeat; ++f) {
+        if (kind[f] != FK_COM_RAY) continue;
+        // the ray leaves the voxel's neighbourhood: the whole image must be local
+        if (origin0 != 0) { set_error("COMRaySample is not available on slab-decomposed volumes"); return 1; }
+        if (g.ndim < 2) { set_error("COMRaySample: `ndim` must be either 2 or 3"); return 1; }
+        for (int ax = 3 - g.ndim; ax < 3; ++ax)
+            if (g.n[ax] < 2) { set_error("COMRaySample: every axis needs at least 2 grid points"); return 1; }
+    }
     return assemble_features(p, g, band_idx, n_band, planes, plane_stride, item_feat, com, X,
                              origin0, s);
 }

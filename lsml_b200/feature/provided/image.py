@@ -52,8 +52,9 @@ class InteriorImageVariation(BaseImageFeature):
 
 
 class COMRaySample(BaseImageFeature):
-    """ Image samples along the voxel-to-centre-of-mass ray (:124-171).  Listed for API
-    completeness; it has no device kernel yet. """
+    """ The RAW image sampled along the segment from a voxel to the centre of mass of the
+    current iterate and symmetrically outwards (:124-171); ``sigma`` only enters the name, as
+    in the reference.  Device kernel: csrc/com_ray.cuh through ``assemble_kernel``. """
     locality = LOCAL_FEATURE_TYPE
 
     @property
@@ -69,6 +70,9 @@ class COMRaySample(BaseImageFeature):
             raise ValueError("`ndim` must be either 2 or 3")
         super().__init__(ndim, sigma)
         self.n_samples = n_samples
+
+    def spec(self):
+        return ("com_ray", int(self.n_samples))
 
 
 def get_basic_image_features(ndim=2, sigmas=[0, 2]):

@@ -1,6 +1,7 @@
 """Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 Run in the build container only (needs /root/reference):  python -m oracle.gen_golden
+(`python -m oracle.gen_golden com_ray` regenerates tests/golden/com_ray.npz alone.)
 
 Every array stored here is an output of the reference's own code imported through
 oracle/ref_shim.py (its compiled C kernels, its feature classes, its FeatureMap, its
@@ -27,7 +28,43 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
+def gen_com_ray():
+    """tests/golden/com_ray.npz: COMRaySample of the unmodified reference (image.py:124-171)."""
+    warnings.simplefilter("ignore")
+    from oracle import oracle as O
+    from oracle.ref_shim import import_reference
+    O.build()
+    import_reference(skfmm_distance=O.skfmm_distance)
+    from lsml.feature.provided.image import COMRaySample
+    from lsml.util.distance_transform import distance_transform as ref_dt
+    rs = np.random.RandomState(11)
+    f = {}
+    cases = [((41, 37), (1.0, 1.0), 3), ((41, 37), (0.5, 2.0), 10),
+             ((18, 21, 19), (1.0, 1.0, 1.0), 2), ((18, 21, 19), (2.0, 0.5, 1.0), 4)]
+    for c, (shape, dx, n_samples) in enumerate(cases):
+        ndim, dx = len(shape), np.asarray(dx)
+        gg = np.indices(shape).astype(float)
+        centre = np.asarray(shape) / 2.6          # off-centre: outward samples leave the grid
+        r = np.sqrt(sum(((gg[a] - centre[a]) * dx[a]) ** 2 for a in range(ndim)))
+        u = min(s * d for s, d in zip(shape, dx)) / 3.7 - r + 0.3 * rs.randn(*shape)
+        img = rs.randn(*shape)
+        dist, mask = ref_dt(u, band=3, dx=dx)
+        feat = COMRaySample(ndim=ndim, sigma=0, n_samples=n_samples)
+        X = feat(u=u, img=img, dist=dist, mask=mask, dx=dx)[mask]
+        f.update({"u%d" % c: u, "img%d" % c: img, "mask%d" % c: mask, "dx%d" % c: dx,
+                  "n_samples%d" % c: n_samples, "X%d" % c: X})
+    f["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "com_ray.npz"),
+                        notes="reference COMRaySample (scipy RegularGridInterpolator); band masks "
+                              "from the reference distance_transform wrapper with skfmm plugged "
+                              "by the oracle; dx are powers of two so that the centre of mass "
+                              "is exact in every summation order", **f)
+    print("com_ray.npz", os.path.getsize(os.path.join(OUT, "com_ray.npz")))
+
+
 def main():
+    if sys.argv[1:] == ["com_ray"]:       # regenerate that fixture only
+        return gen_com_ray()
     warnings.simplefilter("ignore")
     from oracle import oracle as O
     from oracle.ref_shim import import_reference
@@ -183,6 +220,7 @@ def main():
                               "LevelSetMachineLearning.segment (model.py:283-411) with skfmm "
                               "plugged by the oracle; regressors stored as exported parameters",
                         **seg_fix)
+    gen_com_ray()
     for name in sorted(os.listdir(OUT)):
         print(name, os.path.getsize(os.path.join(OUT, name)))
 

@@ -224,6 +224,25 @@ def dist_to_com_plane(u, dx):
     return np.linalg.norm(mesh - com[sl], axis=0)
 
 
+def com_ray_columns(u, img, mask, dx, n_samples):
+    """COMRaySample.compute_feature (image.py:147-171) on the band: (B, 2*n_samples).
+
+    Same expressions as the reference (numpy.linspace, ``t*com + (1-t)*(coord*dx)``, scipy's
+    RegularGridInterpolator with fill_value 0 on the RAW image); the only change of work
+    pattern is one interpolator call for all band voxels instead of one per voxel -- the
+    interpolation is elementwise, so the values are the same bit for bit
+    (tests/test_oracle_golden.py pins this against the reference's own output)."""
+    from scipy.interpolate import RegularGridInterpolator
+    com = center_of_mass(u, dx)
+    t = np.linspace(-1, 1, 2 * n_samples + 2)[1:-1, None]
+    interpolator = RegularGridInterpolator(
+        points=[np.arange(s, dtype=float) * delta for s, delta in zip(u.shape, dx)],
+        values=img, bounds_error=False, fill_value=0.0)
+    coords = np.array(np.where(mask)).T
+    points = t[None] * com[None, None] + (1 - t)[None] * (coords * dx)[:, None, :]
+    return interpolator(points.reshape(-1, u.ndim)).reshape(coords.shape[0], 2 * n_samples)
+
+
 def boundary_size(u, dx):
     """BoundarySize (shape.py:56-89).  2-D only here (3-D needs Lewiner marching cubes)."""
     if u.ndim != 2:
@@ -239,7 +258,10 @@ def boundary_size(u, dx):
 # feature classes (lsml_b200.feature.*.spec()).
 #   ("image_sample", sigma) ("image_edge", sigma) ("band_mean", sigma) ("band_std", sigma)
 #   ("size",) ("boundary_size",) ("isoperimetric",) ("moments", axes, orders) ("dist_to_com",)
+#   ("com_ray", n_samples)
 def spec_width(spec):
+    if spec[0] == "com_ray":
+        return 2 * int(spec[1])
     return len(spec[1]) * len(spec[2]) if spec[0] == "moments" else 1
 
 
@@ -271,6 +293,8 @@ def feature_columns(spec, u, img, dist, mask, dx):
         return np.tile(np.asarray(cols)[None, :], (nb, 1))
     if kind == "dist_to_com":
         return dist_to_com_plane(u, dx)[mask][:, None]
+    if kind == "com_ray":
+        return com_ray_columns(u, img, mask, dx, int(spec[1]))
     raise ValueError("unknown feature spec %r" % (spec,))
 
 

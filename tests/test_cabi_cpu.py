@@ -96,8 +96,11 @@ def test_feature_program_and_api_surface():
         FeatureProgram([BoundarySize(3).spec()], 3)          # Lewiner MC area not implemented
     with pytest.raises(NotImplementedError):
         FeatureProgram([Moments(2, orders=(3,)).spec()], 2)
-    with pytest.raises(NotImplementedError):
-        COMRaySample(2).spec()
+    ray = FeatureProgram([COMRaySample(2, n_samples=3).spec()], 2)      # 2N columns, raw image
+    assert ray.nfeat == 6 and ray.planes == [("sample", 0.0)]
+    assert [b & 0xffff for b in ray.b] == list(range(6)) and {b >> 16 for b in ray.b} == {3}
+    with pytest.raises(ValueError):
+        FeatureProgram([COMRaySample(2).spec()], 1)
     with pytest.raises(ValueError):
         Moments(2, axes=(2,))
     with pytest.raises(ValueError):
