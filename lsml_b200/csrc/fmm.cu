@@ -150,6 +150,13 @@ struct __align__(8) Aux {
     unsigned short lvl;
 };
 
+// Hint tag of rebuild `gen`, already shifted into the high byte of Aux::lvl: 1..255, never 0, so
+// that lvl == 0 (never evaluated, or wiped) carries no rebuild's tag.  The tags repeat every 255
+// rebuilds; all hints are wiped every 128 (fmm_clear_kernel), so a tag is never ambiguous.
+__device__ __forceinline__ unsigned hint_tag_of(i64 gen) {
+    return (unsigned)((gen % 255) + 1) << 8;
+}
+
 __device__ __forceinline__ unsigned short reach_up16(float r) {
     return (unsigned short)((__float_as_uint(r) + 0xffffu) >> 16);
 }
@@ -179,9 +186,9 @@ fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__
         aux[l] = Aux{0u, (unsigned short)REACH16_INF, aux[l].lvl};      // the hint survives
         mask[l] = 0;
     }
-    // Hints are tagged with the low 8 bits of the rebuild counter.  Every 128th rebuild ALL hints
-    // are dropped (one dense 8 B/voxel pass), so no voxel can carry a tag that is 256 rebuilds
-    // old and would be mistaken for last rebuild's: the parking buckets are sized from last
+    // Hints are tagged with hint_tag_of(rebuild counter), period 255.  Every 128th rebuild ALL
+    // hints are dropped (one dense 8 B/voxel pass), so no voxel can carry a tag that is 255
+    // rebuilds old and would be mistaken for last rebuild's: the parking buckets are sized from last
     // rebuild's histogram and must never receive a voxel it did not count.
     if ((ctr->gen & 127) == 127) {
         for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(256)
 fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* ctr, Ring ring,
                 i64* park) {
     const i64 ni = ctr->n_init;
-    const unsigned tag = ctr->use_hints ? (unsigned)(((ctr->gen - 1) & 0xff) << 8) : 0xffffffffu;
+    const unsigned tag = ctr->use_hints ? hint_tag_of(ctr->gen - 1) : 0xffffffffu;
     const Sched sc{aux, ring, park, ctr, 0, 0, 1u, 1, tag, 2};
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni;
          t += (i64)gridDim.x * blockDim.x) {
@@ -836,7 +843,8 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
 template <int NDIM>
 __device__ __forceinline__ void process_candidate(i64 e, const double* __restrict__ u, double* T,
                                                   u8* mask, i64* list, i64 cap, const FmmGeom& g,
-                                                  double band, const Sched& sc, unsigned gen_tag) {
+                                                  double band, const Sched& sc, unsigned gen_tag,
+                                                  i64* hist) {
     int coord[3];
     const i64 l = decode(e, g, coord);
     const double old = __ldcg(T + l);
@@ -849,7 +857,6 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     // this rebuild) as the hint for the next rebuild
     mask[l] = (u8)((level << 2) | ST_CAND);
     if (lvl != (gen_tag | level)) {
-        i64* hist = sc.ctr->hist[(gen_tag >> 8) & 1u];
         if ((lvl & 0xff00u) == gen_tag) warp_agg_add(hist, lvl & 0xffu, -1);
         warp_agg_add(hist, level, 1);
         lvl = gen_tag | level;
@@ -887,8 +894,9 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     volatile i64* vfill = ctr->fill;
     volatile i64* vlast = &ctr->last_bucket;
     const bool hints = ctr->use_hints != 0;
-    const unsigned gen_tag = (unsigned)((ctr->gen & 0xff) << 8);
-    const unsigned hint_tag = hints ? (unsigned)(((ctr->gen - 1) & 0xff) << 8) : 0xffffffffu;
+    const unsigned gen_tag = hint_tag_of(ctr->gen);
+    const unsigned hint_tag = hints ? hint_tag_of(ctr->gen - 1) : 0xffffffffu;
+    i64* const hist_cur = ctr->hist[ctr->gen & 1];
     // (a rebuild is one launch on a single GPU; a slab-decomposed rebuild launches again after
     // every halo exchange and continues where the previous launch stopped)
     unsigned sweep = (unsigned)ctr->resume_sweep;      // epoch of the work set being consumed
@@ -937,7 +945,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                     for (i64 k = threadIdx.x; k < work; k += FMM_THREADS) {
                         const i64 ent = k < e - b ? ring.slots[(b + k) & (ring.cap - 1)]
                                                   : park[pbase + k - (e - b)];
-                        process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag);
+                        process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
                         ++nreplay;
                     }
                     __threadfence();
@@ -978,7 +986,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             for (i64 k = (i64)lane * nwarps + gwarp; k < work; k += nthreads) {
                 const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
                                                 : park[pbase + k - (end - begin)];
-                process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag);
+                process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
                 ++nreplay;
             }
         } else {
@@ -1005,12 +1013,12 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                     const i64 e2 = queue[warp][qn - 32 + lane];
                     qn -= 32;
                     __syncwarp();
-                    process_candidate<NDIM>(e2, u, T, mask, list, cap, g, band, sc, gen_tag);
+                    process_candidate<NDIM>(e2, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
                     ++nreplay;
                 }
             }
             if (lane < qn) {
-                process_candidate<NDIM>(queue[warp][lane], u, T, mask, list, cap, g, band, sc, gen_tag);
+                process_candidate<NDIM>(queue[warp][lane], u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
                 ++nreplay;
             }
             __syncwarp();

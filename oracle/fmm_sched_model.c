@@ -287,6 +287,9 @@ static void publish_change(sched_t *s, long l, float q_min, int expose) {
  * filter; bit 2 (diagnostic): no hints.  counters: long[4] = {sweeps,
  * replays, parked entries, bucket overflows}.  Returns sweeps, or -1 without convergence.
  */
+/* fmm.cu:hint_tag_of -- tags 1..255, never 0: lvl == 0 (never evaluated / wiped) has no tag */
+static u32 hint_tag_of(long gen) { return (u32)((gen % 255) + 1) << 8; }
+
 long sm_rebuild(int ndim, const int *shape, const double *phi, const double *dx, double narrow,
                 u16 *lvl, long *hist, long *gen, const long *prev_band, long n_prev, int mode,
                 int max_sweeps, double *dist_out, u8 *frozen_out, long *counters) {
@@ -312,13 +315,13 @@ long sm_rebuild(int ndim, const int *shape, const double *phi, const double *dx,
     long *hist_cur = hist + 256 * cur, *hist_prev = hist + 256 * prev;
     for (int i = 0; i < 256; ++i) hist_cur[i] = 0;
     const int hints = prev_band != NULL && (gen[0] % 16) != 0 && !(mode & 4);
-    const u32 gen_tag = (u32)((gen[0] & 0xff) << 8);
+    const u32 gen_tag = hint_tag_of(gen[0]);
     vec_t ring_a = {0}, ring_b = {0}, cands = {0}, inits = {0};
     vec_t buckets[256];
     memset(buckets, 0, sizeof buckets);
     sched_t sc;
     sc.m = &m; sc.buckets = buckets; sc.cands = &cands; sc.last_bucket = 0;
-    sc.hint_tag = hints ? (u32)(((gen[0] - 1) & 0xff) << 8) : 0xffffffffu;
+    sc.hint_tag = hints ? hint_tag_of(gen[0] - 1) : 0xffffffffu;
     sc.hist_prev = hist_prev; sc.overflowed = 0; sc.no_reach = (mode & 2) != 0;
     /* initial frozen set */
     if (prev_band == NULL) {
@@ -403,6 +406,15 @@ long sm_rebuild(int ndim, const int *shape, const double *phi, const double *dx,
         int fr = m.state[i] == 1 || ((m.state[i] & 2) && m.state[i] != 1 && fabs(m.T[i]) <= m.band);
         frozen_out[i] = (u8)fr;
         dist_out[i] = fr ? m.T[i] : 0.0;
+    }
+    /* invariant the device's bucket offsets rest on: hist_cur[h] == #voxels hinted (this tag, h) */
+    {
+        long recount[256];
+        memset(recount, 0, sizeof recount);
+        for (long i = 0; i < m.size; ++i)
+            if ((lvl[i] & 0xff00u) == gen_tag) recount[lvl[i] & 0xff]++;
+        for (int h = 0; h < 256; ++h)
+            if (recount[h] != hist_cur[h]) sc.overflowed |= 2;
     }
     if (counters) { counters[0] = sweeps; counters[1] = replays; counters[2] = parked; counters[3] = sc.overflowed; }
     free(m.T); free(m.state); free(m.epoch); free(m.reach16);
