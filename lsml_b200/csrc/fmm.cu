@@ -178,19 +178,21 @@ __global__ void __launch_bounds__(256)
 fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__ mask,
                  const i64* __restrict__ list, i64 cap, FmmGeom g, FmmCounters* ctr, i64 total) {
     const i64 ni = ctr->prev_init, nc = ctr->prev_cand;
+    const bool wipe = (ctr->gen & 127) == 127;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < ni + nc;
          t += (i64)gridDim.x * blockDim.x) {
         int coord[3];
         const i64 l = decode(t < ni ? list[t] : list[cap - 1 - (t - ni)], g, coord);
         T[l] = pos_inf();
-        aux[l] = Aux{0u, (unsigned short)REACH16_INF, aux[l].lvl};      // the hint survives
+        // the hint survives (except in a wipe: both loops then store 0, in either order)
+        aux[l] = Aux{0u, (unsigned short)REACH16_INF, wipe ? (unsigned short)0 : aux[l].lvl};
         mask[l] = 0;
     }
     // Hints are tagged with hint_tag_of(rebuild counter), period 255.  Every 128th rebuild ALL
     // hints are dropped (one dense 8 B/voxel pass), so no voxel can carry a tag that is 255
     // rebuilds old and would be mistaken for last rebuild's: the parking buckets are sized from last
     // rebuild's histogram and must never receive a voxel it did not count.
-    if ((ctr->gen & 127) == 127) {
+    if (wipe) {
         for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < total;
              i += (i64)gridDim.x * blockDim.x)
             aux[i].lvl = 0;
@@ -734,6 +736,12 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
 
 constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s at worst, then
                                           // `converged` = 0 is reported (never seen)
+// Sweeps per REBUILD, counting the single-CTA ones (a grid-wide step can hold 4096 of those, so
+// FMM_MAX_SWEEPS alone does not bound the time).  Far above any dependency depth (a full 1024^3
+// distance map needs ~3 000); a march that gets here is cycling on an input for which the replay
+// operator has no fixed point (DESIGN.md 4.6 "Known limit") and ends with `converged` = 0 after
+// a fraction of a second instead of never.
+constexpr unsigned FMM_SWEEP_LIMIT = 1u << 16;
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
 #ifndef FMM_MIN_BLOCKS
@@ -906,7 +914,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     i64 begin = ctr->resume_begin, end = begin + vtail[rix % 3u];   // queued by seed / requeue
     bool scan = vovf[2] != 0;          // ... which report overflow into slot 2
     i64 nreplay = 0;
-    while (barriers < FMM_MAX_SWEEPS) {
+    while (barriers < FMM_MAX_SWEEPS && sweep < FMM_SWEEP_LIMIT) {
         i64 nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;       // bucket of this sweep
         if (end == begin && nbk == 0 && !scan) {
             if (!hints || (i64)sweep >= *vlast) { converged = true; break; }
@@ -929,7 +937,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             if (blockIdx.x == 0) {
                 i64 b = begin, e = end;
                 int inner = 0;
-                while (inner < 4096) {
+                while (inner < 4096 && sweep < FMM_SWEEP_LIMIT) {
                     nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;
                     const i64 work = e - b + nbk;
                     if (work == 0) {

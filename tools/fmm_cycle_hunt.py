@@ -1,0 +1,127 @@
+"""CPU hunt for inputs on which the band rebuild's replay iteration does not converge.
+
+Background: a C4 run with 2048 crops per GPU did not finish in round 1.
+One candidate cause is an input on which the replay operator has no fixed point (or a 2-cycle in
+synchronous order), which the oracle's largest-magnitude eviction rule does not exclude (DESIGN.md
+4.6 "Known limit").  This script evolves C4-like crops on the CPU (same generator, features and
+forest recipe as bench.py --workload c4, oracle arithmetic) and after every iteration runs the CPU
+model of the device scheduler (oracle/fmm_sched_model.c), in place and synchronously, with a
+generous sweep budget.  Any non-convergent or mismatching rebuild is saved as an .npz.
+
+    python tools/fmm_cycle_hunt.py --worker 0 --items 400 --out /tmp/hunt
+
+TEST INFRASTRUCTURE (uses oracle/).
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--worker", type=int, default=0)
+    ap.add_argument("--items", type=int, default=100)
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--out", default="/tmp/fmm_hunt")
+    ap.add_argument("--minutes", type=float, default=60.0)
+    args = ap.parse_args()
+    import bench
+    from oracle import oracle as O
+    from test_fmm_algorithm import sched_rebuild
+    O.build()
+    os.makedirs(args.out, exist_ok=True)
+    shape, band, dx = (64, 64, 64), 3.0, np.ones(3)
+    CHUNK = 64          # items are generated 64 at a time (2 MB each)
+    g = np.indices(shape).astype(np.float64)
+    rc = np.sqrt(sum((g[a] - shape[a] / 2.0) ** 2 for a in range(3)))
+    u0 = np.where(rc < 5.0, 1.0, -1.0)
+    specs = bench.SPECS
+    # u-independent planes once per item; everything else per iteration (oracle expressions)
+    def planes_of(img):
+        return [O.image_sample_plane(img, 0.0, dx), O.image_sample_plane(img, 2.0, dx),
+                O.image_edge_plane(img, 0.0, dx), O.image_edge_plane(img, 2.0, dx)]
+
+    def features(u, pl, mask):
+        nb = int(mask.sum())
+        cols = [p[mask] for p in pl]
+        for p in (pl[0], pl[1]):
+            cols.append(np.full(nb, p[mask].mean()))
+        for p in (pl[0], pl[1]):
+            cols.append(np.full(nb, p[mask].std()))
+        pos = u > 0
+        cnt = pos.sum()
+        com = np.array([g[a][pos].sum() / cnt for a in range(3)])
+        cols.append(np.sqrt(sum((g[a][mask] - com[a]) ** 2 for a in range(3))))
+        for a in range(3):
+            cols.append(np.full(nb, com[a]))
+            cols.append(np.full(nb, ((g[a][pos] - com[a]) ** 2).sum() / cnt))
+        cols.append(np.full(nb, float(cnt)))
+        return np.stack(cols, axis=1)
+
+    t_end = time.time() + 60 * args.minutes
+    reg = None
+    n_reb = n_bad = 0
+    worst = 0
+    log = open(os.path.join(args.out, "worker%d.log" % args.worker), "w")
+    imgs = None
+    for b in range(args.items):
+        if b % CHUNK == 0:
+            imgs = bench._blob_items(CHUNK, shape, 10000 + 97 * args.worker + 7919 * (b // CHUNK),
+                                     6, 18, 8)
+        img = O.normalize_image(imgs[b % CHUNK])
+        pl = planes_of(img)
+        u = u0.copy()
+        dist, mask = O.distance_transform(u, band, dx)
+        lvl = [np.zeros(u.size, dtype=np.uint16) for _ in range(2)]
+        hist = [np.zeros(512, dtype=np.int64) for _ in range(2)]
+        gen = [np.array([b * 37], dtype=np.int64) for _ in range(2)]
+        prev = None
+        for it in range(args.iters):
+            if not mask.any():
+                break
+            X = features(u, pl, mask)
+            if reg is None:
+                y = X[:, 1] + 0.2 * np.random.RandomState(1).standard_normal(X.shape[0])
+                reg = bench._fit_forest(X, y, 5 + args.worker)
+            v = np.zeros(u.shape)
+            v[mask] = reg.predict(X)
+            gm = O.gmag_os(u, v, mask, dx)
+            u = u.copy()
+            u[mask] += 0.4 * v[mask] * gm[mask]
+            prev = np.flatnonzero(mask.ravel())
+            wd, wm = O.distance_transform(u, band, dx)
+            for mode in (0, 1):
+                d, m, sweeps, ctr = sched_rebuild(O, u, dx, band, lvl[mode], hist[mode], gen[mode],
+                                                  prev, mode, max_sweeps=3000)
+                n_reb += 1
+                worst = max(worst, int(sweeps))
+                ok = sweeps > 0 and ctr[3] == 0 and np.array_equal(m, wm)
+                exact = ok and np.array_equal(d, wd)
+                if not exact:
+                    n_bad += 1
+                    kind = "NOCONV" if sweeps <= 0 else ("MASK" if not ok else "DIST")
+                    name = os.path.join(args.out, "case_w%d_b%d_it%d_m%d_%s.npz"
+                                        % (args.worker, b, it, mode, kind))
+                    np.savez_compressed(name, u=u, prev=prev, dx=dx, band=band)
+                    log.write("%s item %d it %d mode %d sweeps %d ctr %s maxdiff %g\n" % (
+                        kind, b, it, mode, sweeps, ctr.tolist(),
+                        float(np.abs(d - wd).max()) if sweeps > 0 else -1.0))
+                    log.flush()
+            dist, mask = wd, wm
+        log.write("item %d done: rebuilds %d bad %d worst sweeps %d\n" % (b, n_reb, n_bad, worst))
+        log.flush()
+        if time.time() > t_end:
+            break
+    log.write("END rebuilds %d bad %d worst sweeps %d\n" % (n_reb, n_bad, worst))
+    log.close()
+
+
+if __name__ == "__main__":
+    main()
