@@ -51,6 +51,7 @@ namespace cg = cooperative_groups;
 
 namespace lsml {
 
+// [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 struct FmmGeom {
     int n0, n1, n2;
     i64 voxels, batch;
@@ -64,6 +65,7 @@ struct FmmGeom {
     // halo copies of the neighbour ranks' voxels (whole grid = [0, n0) for a single GPU)
     int own_lo, own_hi;
 };
+// [host-test:end]
 
 static int bits_for(i64 n) { int b = 0; while (((i64)1 << b) < n) ++b; return b; }
 
@@ -106,6 +108,7 @@ struct FmmCounters {      // device-resident
     i64 stamps[32];       // %globaltimer (ns) at the start of those sweeps (diagnostic)
 };
 
+// [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 // Ordering decisions are made on |d| rounded to float32 (see oracle/lsml_oracle.c:qmag): values
 // that tie in exact arithmetic but differ by float64 rounding noise tie exactly here and are
 // ordered by flat index.
@@ -117,6 +120,7 @@ __device__ __forceinline__ double pos_inf() { return __longlong_as_double(0x7ff0
 // where level is the candidate's dependency depth in this rebuild (see Aux::lvl).
 constexpr u8 ST_INIT = 1, ST_CAND = 2;
 constexpr unsigned MAX_LEVEL = 63u;
+// [host-test:end]
 
 // claim voxel g (state 0 -> `value`); returns true for the single winner.  The state is one
 // byte of a 32-bit word; atomicOr on the word keeps the other three bytes intact.
@@ -231,6 +235,7 @@ fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap) {
     if (t == 255) ctr->use_hints = (allow_hints && (ctr->gen % 16) != 0 && scan[255] <= park_cap) ? 1 : 0;
 }
 
+// [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 // Initial frozen value of voxel l (orc_fmm_distance "initial frozen set"): zeros, and voxels
 // with an axis neighbour of opposite sign; d = sign / sqrt(sum_a 1/d_a^2), d_a = nearer linear
 // crossing.  Returns false when l is not in the initial frozen set.
@@ -263,6 +268,7 @@ __device__ __forceinline__ bool init_distance(const double* __restrict__ u, i64 
     d = c < 0 ? -sqrt(1 / dsum) : sqrt(1 / dsum);
     return true;
 }
+// [host-test:end]
 
 // Items that are single-signed (no positive or no non-positive... see distance_transform.py:42)
 // are left untouched => empty mask.  stats[item*8+0] = #(u>0), stats[item*8+7] = #(u==0).
@@ -471,6 +477,7 @@ fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* 
     }
 }
 
+// [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 // ---- the marcher's upwind update on a local stencil ------------------------------------------
 // Stencil slots are numbered by their RANK in flat-index order around x (rank 6 = x itself):
 //   0: -2 along axis 0   1: -1 axis 0   2: -2 axis 1   3: -1 axis 1   4: -2 axis 2   5: -1 axis 2
@@ -733,6 +740,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
     level = min(deepest + 1u, MAX_LEVEL);
     return narrow ? t : inf;
 }
+// [host-test:end]
 
 constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s at worst, then
                                           // `converged` = 0 is reported (never seen)
