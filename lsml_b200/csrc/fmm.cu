@@ -504,12 +504,12 @@ __device__ __forceinline__ bool second_order_ok(double d2, float q2, double v1, 
     return v1 == 0.0 || d2 * v1 < 0 || q2 <= k1;
 }
 
-// Candidate contributor rule for round 2 (DESIGN.md 4.6 "Known limit"), OFF unless the library is
-// built with -DLSML_FMM_RULE_R2 and the oracle runs with LSML_ORACLE_RULE_R2=1: a second
-// neighbour of opposite sign lies across the interface and is exempt from the causality test
-// and from eviction.
+// Contributor rule (oracle/lsml_oracle.c:across): a second neighbour of OPPOSITE
+// sign lies across the interface -- its magnitude says nothing about causality -- and is exempt
+// from the causality test and from eviction.  -DLSML_FMM_RULE_LEGACY (with the oracle's
+// LSML_ORACLE_RULE_R2=0) restores the rule used before, for the regression test of the difference.
 __device__ __forceinline__ bool across(const AxisState& a) {
-#ifdef LSML_FMM_RULE_R2
+#ifndef LSML_FMM_RULE_LEGACY
     return a.v2 * a.v1 < 0;
 #else
     (void)a;
@@ -746,9 +746,9 @@ constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s a
                                           // `converged` = 0 is reported (never seen)
 // Sweeps per REBUILD, counting the single-CTA ones (a grid-wide step can hold 4096 of those, so
 // FMM_MAX_SWEEPS alone does not bound the time).  Far above any dependency depth (a full 1024^3
-// distance map needs ~3 000); a march that gets here is cycling on an input for which the replay
-// operator has no fixed point (DESIGN.md 4.6 "Known limit") and ends with `converged` = 0 after
-// a fraction of a second instead of never.
+// distance map needs ~3 000); a march that gets here would be cycling (never observed; the
+// contributor rule of DESIGN.md 4.6 is what rules it out) and ends with `converged` = 0 after a
+// fraction of a second instead of never.
 constexpr unsigned FMM_SWEEP_LIMIT = 1u << 16;
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;

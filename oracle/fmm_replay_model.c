@@ -22,13 +22,16 @@ typedef unsigned char u8;
  * noise.  The distances themselves stay float64. */
 static inline float qmag(double d) { return (float)fabs(d); }
 
-/* Candidate contributor rule for round 2 (DESIGN.md 4.6 "Known limit"), OFF unless the
- * environment says LSML_ORACLE_RULE_R2=1 (and liblsml_b200.so was built with
- * -DLSML_FMM_RULE_R2): a second neighbour of opposite sign lies across the interface and is
- * exempt from the causality test and from eviction. */
+/* Contributor rule: a second neighbour of OPPOSITE sign lies across the
+ * interface -- its magnitude says nothing about causality -- and is exempt from the causality
+ * test and from eviction.  With it the marcher's freeze values are monotone in freeze order, which
+ * is what makes the sequential result the unique fixed point of the local replay operator the
+ * GPU iterates.  LSML_ORACLE_RULE_R2=0 restores the rule used before (largest magnitude evicted
+ * regardless of side; fmm.cu: -DLSML_FMM_RULE_LEGACY), kept for the regression test of the
+ * difference. */
 static int across(double v1, double v2) {
     static int rule = -1;
-    if (rule < 0) { const char *e = getenv("LSML_ORACLE_RULE_R2"); rule = (e && e[0] == '1') ? 1 : 0; }
+    if (rule < 0) { const char *e = getenv("LSML_ORACLE_RULE_R2"); rule = (e && e[0] == '0') ? 0 : 1; }
     return rule && v2 * v1 < 0;
 }
 

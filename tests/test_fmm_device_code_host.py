@@ -7,9 +7,9 @@ cuda_host_shim.h) and iterated to their fixed point over whole grids.  The resul
 oracle's sequential marcher bit for bit.  oracle/fmm_replay_model.c checks the ALGORITHM with a
 separate C restatement; this test checks the kernel's own source text, where no GPU exists.
 
-Both contributor rules are covered: the current one and the candidate of DESIGN.md 4.6
-(-DLSML_FMM_RULE_R2 / LSML_ORACLE_RULE_R2=1, run in a subprocess because the oracle reads the
-switch once).
+Both contributor rules of DESIGN.md 4.6 are covered: the adopted one and the legacy one
+(-DLSML_FMM_RULE_LEGACY / LSML_ORACLE_RULE_R2=0, run in a subprocess because the oracle reads
+the switch once).
 """
 import ctypes
 import os
@@ -24,20 +24,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def build_host_lib(out_dir, rule_r2):
+def build_host_lib(out_dir, legacy):
     src = open(os.path.join(ROOT, "lsml_b200", "csrc", "fmm.cu")).read()
     regions = re.findall(r"// \[host-test:begin\][^\n]*\n(.*?)// \[host-test:end\]", src, re.S)
     assert len(regions) == 4, "fmm.cu: expected 4 host-testable regions"
     text = ('#include "cuda_host_shim.h"\nnamespace lsml {\n' + "\n".join(regions) +
             open(os.path.join(HERE, "native", "fmm_host_driver.inc")).read())
-    cpp = os.path.join(out_dir, "fmm_device_host%s.cpp" % ("_r2" if rule_r2 else ""))
+    cpp = os.path.join(out_dir, "fmm_device_host%s.cpp" % ("_legacy" if legacy else ""))
     so = cpp[:-4] + ".so"
     with open(cpp, "w") as f:
         f.write(text)
     cmd = ["g++", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
            "-I", os.path.join(HERE, "native"), cpp, "-o", so]
-    if rule_r2:
-        cmd.insert(1, "-DLSML_FMM_RULE_R2")
+    if legacy:
+        cmd.insert(1, "-DLSML_FMM_RULE_LEGACY")
     subprocess.check_call(cmd)
     return so
 
@@ -76,7 +76,7 @@ def campaign(so_path, n_cases, seed):
             if sweeps <= 0 or not np.array_equal(m, wm) or not np.array_equal(d, wd):
                 bad.append((case, jacobi, int(sweeps)))
         checked += 1
-    # the known-limit fixture: differs under the current rule, exact under the candidate
+    # the contributor-rule fixture: exact under the adopted rule, differs under the legacy one
     z = np.load(os.path.join(HERE, "golden", "fmm_nonmonotone_case.npz"))
     wd, wm = O.distance_transform(z["u"], float(z["band"]), z["dx"])
     d, m, sweeps = device_fixed_point(lib, z["u"], z["dx"], float(z["band"]), 0)
@@ -84,11 +84,11 @@ def campaign(so_path, n_cases, seed):
     return checked, bad, limit
 
 
-@pytest.mark.parametrize("rule_r2", [False, True])
-def test_device_replay_source_equals_sequential_marcher(tmp_path, rule_r2):
-    so = build_host_lib(str(tmp_path), rule_r2)
+@pytest.mark.parametrize("legacy", [False, True])
+def test_device_replay_source_equals_sequential_marcher(tmp_path, legacy):
+    so = build_host_lib(str(tmp_path), legacy)
     env = dict(os.environ)
-    env["LSML_ORACLE_RULE_R2"] = "1" if rule_r2 else "0"
+    env["LSML_ORACLE_RULE_R2"] = "0" if legacy else "1"
     env["PYTHONPATH"] = os.pathsep.join([ROOT, HERE, env.get("PYTHONPATH", "")])
     code = ("import sys; sys.path[:0] = [%r, %r]\n"
             "from test_fmm_device_code_host import campaign\n"
@@ -99,4 +99,4 @@ def test_device_replay_source_equals_sequential_marcher(tmp_path, rule_r2):
     assert bad == [], bad
     sweeps, mask_equal, n_diff = limit
     assert sweeps > 0 and mask_equal
-    assert (n_diff == 0) if rule_r2 else (0 < n_diff < 100)
+    assert (0 < n_diff < 100) if legacy else (n_diff == 0)

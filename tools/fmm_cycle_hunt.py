@@ -2,8 +2,8 @@
 
 Background: a C4 run with 2048 crops per GPU did not finish in round 1.
 One candidate cause is an input on which the replay operator has no fixed point (or a 2-cycle in
-synchronous order), which the oracle's largest-magnitude eviction rule does not exclude (DESIGN.md
-4.6 "Known limit").  This script evolves C4-like crops on the CPU (same generator, features and
+synchronous order), which the first contributor rule did not exclude (DESIGN.md 4.6
+"Contributor rule"; `LSML_ORACLE_RULE_R2=0` runs the hunt with that rule).  This script evolves C4-like crops on the CPU (same generator, features and
 forest recipe as bench.py --workload c4, oracle arithmetic) and after every iteration runs the CPU
 model of the device scheduler (oracle/fmm_sched_model.c), in place and synchronously, with a
 generous sweep budget.  Any non-convergent or mismatching rebuild is saved as an .npz.
