@@ -229,9 +229,11 @@ static long heap_pop(fmm_t *m) {
  * value1: the axis is dropped) and the quadratic is solved again (Sethian 1996, the usual
  * implementation of max(D-T, -D+T, 0)).  Upstream scikit-fmm does not make this check; its
  * result then depends on the order in which its heap happens to freeze voxels, which no
- * specification pins down.  With the check every freeze value is >= the values frozen before
- * it, the marcher's result is independent of heap internals and a parallel solver can
- * reproduce it exactly.  Returns 0.0 when there is no frozen neighbour at all. */
+ * specification pins down.  A value2 of OPPOSITE sign (an initial frozen voxel across the
+ * interface) takes part in neither the test nor the removal -- see across().  With the check
+ * every freeze value is >= the values frozen before it, the marcher's result is independent of
+ * heap internals and a parallel solver can reproduce it exactly.  Returns 0.0 when there is no
+ * frozen neighbour at all. */
 static double fmm_solve(int ndim, const double *idx2, const double *v1in, const double *v2in,
                         double phi) {
     const double aa = 9.0 / 4.0, one_third = 1.0 / 3.0;
