@@ -75,6 +75,8 @@ class FeatureProgram:
         kind, a, b = [], [], []
         self.needs_boundary = False
         self.needs_band_stats = False
+        self.needs_u_planes = False
+        self.user_planes = {}     # plane index -> callable(img, dx)
         for spec in self.specs:
             k = spec[0]
             if k == "image_sample":
@@ -105,6 +107,20 @@ class FeatureProgram:
                         kind.append(FK_MOMENT); a.append(int(axis)); b.append(int(order))
             elif k == "dist_to_com":
                 kind.append(FK_DIST_COM); a.append(0); b.append(0)
+            elif k == "smooth_u":
+                # gaussian_filter(u, sigma) sampled on the band (examples/gestalt2d/
+                # prev_iter_feature.py:21-22): a plane recomputed from u every iteration
+                kind.append(FK_PLANE); a.append(self._plane("usmooth", spec[1])); b.append(0)
+                self.needs_u_planes = True
+            elif k == "user_plane":
+                # ("user_plane", key, fn): fn(img, dx) -> dense float64 array, evaluated ONCE per
+                # image on the host by the user's own code (u-independent image features such as
+                # examples/gestalt2d/corner_feature.py), then sampled like any image plane
+                if len(spec) != 3 or not callable(spec[2]):
+                    raise ValueError("user_plane spec must be ('user_plane', key, callable)")
+                idx = self._plane("user", str(spec[1]))
+                self.user_planes[idx] = spec[2]
+                kind.append(FK_PLANE); a.append(idx); b.append(0)
             elif k == "com_ray":
                 # COMRaySample: 2*n_samples columns reading the RAW image (image.py:147-171)
                 n_samples = int(spec[1])
@@ -131,7 +147,7 @@ class FeatureProgram:
         self.b = _lib.int_array(b)
 
     def _plane(self, what, sigma):
-        key = (what, float(sigma))
+        key = (what, sigma if what == "user" else float(sigma))
         if key not in self.planes:
             self.planes.append(key)
         return self.planes.index(key)
@@ -205,6 +221,8 @@ class BandEngine:
                     _lib.c_i64(self.batch))), dtype=torch.uint8, device=d)
             _lib.lib.lsml_fmm_workspace_bytes.restype = _lib.c_i64
             self._ws_fmm = None       # allocated on the first band rebuild
+        self._weights = {}            # (sigma, order) -> (device weights, radius)
+        self._tmp_plane = None
         self.n_band = 0
         self._cap = 0
         self.X = self.vel = self.new_u = None
@@ -264,32 +282,62 @@ class BandEngine:
             self._compute_planes()
 
     def _gauss(self, src, dst, sigma, order, axis, mode):
-        w, radius = gaussian_weights(sigma, order)
-        wd = torch.from_numpy(w).to(self.device)
-        self._keep.append(wd)
+        key = (float(sigma), int(order))
+        if key not in self._weights:              # uploaded once per (sigma, order)
+            w, radius = gaussian_weights(sigma, order)
+            self._weights[key] = (torch.from_numpy(w).to(self.device), radius)
+        wd, radius = self._weights[key]
         _lib.check(_lib.lib.lsml_gauss1d_f64(
             ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(src),
             _lib.ptr(dst), _lib.ptr(wd), ctypes.c_int(radius), ctypes.c_int(1 if order else 0),
             ctypes.c_int(axis), ctypes.c_int(mode), self._stream()), "gauss1d")
 
+    def _smooth_chain(self, src, dst, sigmas):
+        """dst = gaussian_filter1d applied along every axis in turn (scipy's order and
+        arithmetic); axes with sigma <= 1e-15 are skipped as scipy.ndimage.gaussian_filter does."""
+        axes = [i for i in range(self.ndim) if sigmas[i] > 1e-15]
+        if not axes:
+            dst.copy_(src)
+            return
+        if len(axes) > 1 and self._tmp_plane is None:
+            self._tmp_plane = torch.empty_like(self.u)
+        tmp = self._tmp_plane
+        bufs = [tmp, dst] if len(axes) % 2 == 0 else [dst, tmp]
+        for n, i in enumerate(axes):
+            out = bufs[n % 2]
+            self._gauss(src, out, sigmas[i], 0, i, 0)
+            src = out
+        assert src.data_ptr() == dst.data_ptr()
+
+    def _refresh_u_planes(self):
+        """Planes that depend on the level set (`smooth_u`): recomputed before every feature pass."""
+        for p, (what, sigma) in enumerate(self.program.planes):
+            if what == "usmooth":                # scipy.ndimage.gaussian_filter(u, sigma): no /dx
+                self._smooth_chain(self.u, self.planes[p], [float(sigma)] * self.ndim)
+
     def _compute_planes(self):
-        self._keep = []
-        tmp = None
+        img_host = None
         for p, (what, sigma) in enumerate(self.program.planes):
             dst = self.planes[p]
+            if what == "usmooth":
+                continue
+            if what == "user":
+                # the user's own u-independent image feature, once per image, on the host
+                if img_host is None:
+                    img_host = self.img.cpu().numpy()
+                fn = self.program.user_planes[p]
+                for b in range(self.batch):
+                    plane = np.asarray(fn(img_host[b], self.dx.copy()), dtype=np.float64)
+                    if plane.shape != self.shape:
+                        raise ValueError("user plane {!r} has shape {} but must be shape {}".format(
+                            sigma, plane.shape, self.shape))
+                    dst[b].copy_(torch.from_numpy(np.ascontiguousarray(plane)))
+                continue
             if what == "sample":
                 if sigma == 0:
                     dst.copy_(self.img)                              # image.py:22-23
                 else:                                                # image.py:25-31
-                    if tmp is None:
-                        tmp = torch.empty_like(self.img)
-                    src = self.img
-                    bufs = [tmp, dst] if self.ndim % 2 == 0 else [dst, tmp]
-                    for i in range(self.ndim):
-                        out = bufs[i % 2]
-                        self._gauss(src, out, sigma / self.dx[i], 0, i, 0)
-                        src = out
-                    assert src.data_ptr() == dst.data_ptr()
+                    self._smooth_chain(self.img, dst, [sigma / self.dx[i] for i in range(self.ndim)])
             else:
                 if sigma == 0:                                       # image.py:48-49
                     _lib.check(_lib.lib.lsml_np_gradient_mag_f64(
@@ -307,8 +355,6 @@ class BandEngine:
                         else:
                             mode = 2
                         self._gauss(self.img, dst, sigma / self.dx[a], 1, a, mode)
-        torch.cuda.current_stream().synchronize()
-        self._keep = []
 
     # ------------------------------------------------------------------ level sets / band
     def set_level_sets(self, u0, mask=None):
@@ -401,6 +447,8 @@ class BandEngine:
             return self.X[:0] if self.X is not None else None
         npl = len(pr.planes)
         stride = self.total
+        if pr.needs_u_planes:
+            self._refresh_u_planes()
         if pr.needs_band_stats:
             _lib.check(_lib.lib.lsml_band_stats(
                 _lib.c_i64(self.voxels), _lib.c_i64(self.batch), _lib.ptr(self.planes),

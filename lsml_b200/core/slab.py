@@ -177,6 +177,10 @@ class SlabRank:
                 raise NotImplementedError(
                     "COMRaySample reads the image along a ray through the whole volume and is "
                     "not available on slab-decomposed volumes")
+            if spec[0] in ("smooth_u", "user_plane"):
+                raise NotImplementedError(
+                    "feature spec %r is not available on slab-decomposed volumes (it needs a "
+                    "Gaussian halo of u every iteration / the whole image on one host)" % (spec[0],))
             if spec[0] in ("image_sample", "image_edge", "band_mean", "band_std") and spec[1] > 0:
                 gauss = max(gauss, gaussian_weights(float(spec[1]) / dx[0], 0)[1])
         self.layout = lay = SlabLayout(self.gshape[0], rank, world, gauss, overlap)

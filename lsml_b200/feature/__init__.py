@@ -17,3 +17,4 @@ from .provided.shape import (
     Moments,
     Size,
 )
+from .user import PrecomputedImageFeature, PrevIterFeature, SmoothedLevelSet

@@ -1,7 +1,7 @@
 """Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
 
 Run in the build container only (needs /root/reference):  python -m oracle.gen_golden
-(`python -m oracle.gen_golden com_ray` regenerates tests/golden/com_ray.npz alone.)
+(`python -m oracle.gen_golden com_ray` / `prev_iter` regenerate those fixtures alone.)
 
 Every array stored here is an output of the reference's own code imported through
 oracle/ref_shim.py (its compiled C kernels, its feature classes, its FeatureMap, its
@@ -62,9 +62,48 @@ def gen_com_ray():
     print("com_ray.npz", os.path.getsize(os.path.join(OUT, "com_ray.npz")))
 
 
+def gen_prev_iter():
+    """tests/golden/prev_iter.npz: PrevIterFeature of the reference's gestalt2d example
+    (examples/gestalt2d/prev_iter_feature.py), loaded from where it lies."""
+    import importlib.util
+    warnings.simplefilter("ignore")
+    from oracle import oracle as O
+    from oracle.ref_shim import import_reference, REFERENCE_ROOT
+    O.build()
+    import_reference(skfmm_distance=O.skfmm_distance)
+    from lsml.util.distance_transform import distance_transform as ref_dt
+    path = REFERENCE_ROOT / "examples" / "gestalt2d" / "prev_iter_feature.py"
+    mod_spec = importlib.util.spec_from_file_location("ref_prev_iter_feature", str(path))
+    mod = importlib.util.module_from_spec(mod_spec)
+    mod_spec.loader.exec_module(mod)
+    rs = np.random.RandomState(21)
+    f = {}
+    cases = [((45, 38), (1.0, 1.0), (0, 1, 2.5)), ((45, 38), (0.7, 1.4), (3,)),
+             ((17, 20, 16), (1.0, 1.0, 1.0), (1.5,))]
+    for c, (shape, dx, sigmas) in enumerate(cases):
+        ndim, dx = len(shape), np.asarray(dx)
+        gg = np.indices(shape).astype(float)
+        r = np.sqrt(sum(((gg[a] - shape[a] / 2.2) * dx[a]) ** 2 for a in range(ndim)))
+        u = min(s * d for s, d in zip(shape, dx)) / 3.4 - r + 0.3 * rs.randn(*shape)
+        dist, mask = ref_dt(u, band=3, dx=dx)
+        cols = [mod.PrevIterFeature(ndim=ndim, sigma=sg)(u=u, dist=dist, mask=mask, dx=dx)[mask]
+                for sg in sigmas]
+        f.update({"u%d" % c: u, "mask%d" % c: mask, "dx%d" % c: dx,
+                  "sigmas%d" % c: np.asarray(sigmas, dtype=float), "X%d" % c: np.stack(cols, axis=1)})
+    f["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "prev_iter.npz"),
+                        notes="PrevIterFeature of the reference's examples/gestalt2d "
+                              "(scipy.ndimage.gaussian_filter(u, sigma)); band masks via the "
+                              "reference distance_transform wrapper with skfmm plugged by the oracle",
+                        **f)
+    print("prev_iter.npz", os.path.getsize(os.path.join(OUT, "prev_iter.npz")))
+
+
 def main():
     if sys.argv[1:] == ["com_ray"]:       # regenerate that fixture only
         return gen_com_ray()
+    if sys.argv[1:] == ["prev_iter"]:
+        return gen_prev_iter()
     warnings.simplefilter("ignore")
     from oracle import oracle as O
     from oracle.ref_shim import import_reference
@@ -221,6 +260,7 @@ def main():
                               "plugged by the oracle; regressors stored as exported parameters",
                         **seg_fix)
     gen_com_ray()
+    gen_prev_iter()
     for name in sorted(os.listdir(OUT)):
         print(name, os.path.getsize(os.path.join(OUT, name)))
 

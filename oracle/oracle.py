@@ -258,7 +258,7 @@ def boundary_size(u, dx):
 # feature classes (lsml_b200.feature.*.spec()).
 #   ("image_sample", sigma) ("image_edge", sigma) ("band_mean", sigma) ("band_std", sigma)
 #   ("size",) ("boundary_size",) ("isoperimetric",) ("moments", axes, orders) ("dist_to_com",)
-#   ("com_ray", n_samples)
+#   ("com_ray", n_samples) ("smooth_u", sigma) ("user_plane", key, fn(img, dx) -> plane)
 def spec_width(spec):
     if spec[0] == "com_ray":
         return 2 * int(spec[1])
@@ -295,6 +295,11 @@ def feature_columns(spec, u, img, dist, mask, dx):
         return dist_to_com_plane(u, dx)[mask][:, None]
     if kind == "com_ray":
         return com_ray_columns(u, img, mask, dx, int(spec[1]))
+    if kind == "smooth_u":       # examples/gestalt2d/prev_iter_feature.py:21-22
+        from scipy.ndimage import gaussian_filter
+        return gaussian_filter(u, sigma=spec[1])[mask][:, None]
+    if kind == "user_plane":     # a user's u-independent image feature (e.g. corner_feature.py)
+        return np.asarray(spec[2](img, dx), dtype=np.float64)[mask][:, None]
     raise ValueError("unknown feature spec %r" % (spec,))
 
 

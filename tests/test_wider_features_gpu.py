@@ -82,3 +82,59 @@ def test_com_ray_rejected_where_it_cannot_run():
         BandEngine((32,), 1, specs=[("com_ray", 2)])
     with pytest.raises(NotImplementedError):
         SlabVolume((32, 16, 16), world=2, specs=[("com_ray", 2)])
+
+
+# ---- user-feature registry: PrevIterFeature (examples/gestalt2d) and precomputed image planes ----
+def test_smooth_u_reproduces_reference_example_bit_exact():
+    from lsml_b200.core.engine import BandEngine
+    g = load("prev_iter.npz")
+    for c in range(int(g["n_cases"])):
+        u, mask, dx = g["u%d" % c], g["mask%d" % c], g["dx%d" % c]
+        specs = [("smooth_u", float(s)) for s in g["sigmas%d" % c]]
+        eng = BandEngine(u.shape, 1, dx=dx, band=3.0, specs=specs)
+        eng.load_images(np.zeros(u.shape)[None], normalize=False)
+        eng.set_level_sets(u[None])
+        assert np.array_equal(eng.mask[0].cpu().numpy().astype(bool), mask)
+        assert np.array_equal(eng.compute_features().cpu().numpy(), g["X%d" % c])
+
+
+def test_user_features_through_an_evolution(oracle):
+    """smooth_u is refreshed from u every iteration; a precomputed user plane is sampled like an
+    image plane: two evolution steps against the oracle."""
+    from scipy.ndimage import gaussian_filter
+    from sklearn.linear_model import LinearRegression
+    from lsml_b200.core.engine import BandEngine
+    from lsml_b200.feature import FeatureMap, ImageSample, PrecomputedImageFeature, PrevIterFeature
+
+    class Blurred(PrecomputedImageFeature):
+        @property
+        def name(self):
+            return "blurred-squared-{:.2f}".format(self.sigma)
+
+        def compute_plane(self, img, dx):
+            return gaussian_filter(img, sigma=self.sigma) ** 2
+
+    rs = np.random.RandomState(9)
+    shape, dx = (40, 44), np.ones(2)
+    gg = np.indices(shape).astype(float)
+    u = 9.0 - np.sqrt((gg[0] - 19.3) ** 2 + (gg[1] - 22.6) ** 2) + 0.2 * rs.randn(*shape)
+    img = rs.randn(*shape)
+    fm = FeatureMap([ImageSample(2, 0), PrevIterFeature(2, 1.0), Blurred(2, 1.5), PrevIterFeature(2, 2.0)])
+    specs = fm.specs()
+    reg = LinearRegression().fit(rs.randn(32, 4), rs.randn(32))
+    reg.coef_ = np.array([0.3, 0.05, -0.2, 0.02]); reg.intercept_ = 0.1
+    eng = BandEngine(shape, 1, dx=dx, band=3.0, specs=specs)
+    eng.load_images(img[None], normalize=False)
+    eng.set_level_sets(u[None])
+    dist, mask = oracle.distance_transform(u, 3.0, dx)
+    for it in range(2):
+        X = eng.compute_features().cpu().numpy()
+        want = oracle.feature_matrix(specs, u, img, dist, mask, dx)
+        if it == 0:
+            assert np.array_equal(X, want)
+        else:       # u itself now differs in the last bits (dot-product order of the regressor)
+            assert np.allclose(X, want, rtol=1e-10, atol=1e-12), np.abs(X - want).max()
+        eng.step(reg, 0.4)
+        u, dist, mask, _ = oracle.evolve_step(u, img, dist, mask, dx, specs, reg, 0.4, 3.0)
+        assert np.array_equal(eng.mask[0].cpu().numpy().astype(bool), mask)
+        assert np.allclose(eng.u[0].cpu().numpy(), u, rtol=1e-12, atol=1e-12)
