@@ -31,12 +31,23 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="/tmp/fmm_hunt")
     ap.add_argument("--minutes", type=float, default=60.0)
+    ap.add_argument("--device-source-every", type=int, default=0,
+                    help="also iterate the kernel's own source, compiled for the host "
+                         "(tests/test_fmm_device_code_host.py), on every N-th rebuild input")
     args = ap.parse_args()
     import bench
     from oracle import oracle as O
     from test_fmm_algorithm import sched_rebuild
     O.build()
     os.makedirs(args.out, exist_ok=True)
+    dev_lib = None
+    if args.device_source_every:
+        import ctypes
+        import tempfile
+        from test_fmm_device_code_host import build_host_lib, device_fixed_point
+        legacy = os.environ.get("LSML_ORACLE_RULE_R2") == "0"
+        dev_lib = ctypes.CDLL(build_host_lib(tempfile.mkdtemp(), legacy))
+    n_dev = 0
     shape, band, dx = (64, 64, 64), 3.0, np.ones(3)
     CHUNK = 64          # items are generated 64 at a time (2 MB each)
     g = np.indices(shape).astype(np.float64)
@@ -114,12 +125,24 @@ def main():
                         kind, b, it, mode, sweeps, ctr.tolist(),
                         float(np.abs(d - wd).max()) if sweeps > 0 else -1.0))
                     log.flush()
+            if dev_lib is not None and (n_reb // 2) % args.device_source_every == 0:
+                d, m, sweeps = device_fixed_point(dev_lib, u, dx, band, 0)
+                n_dev += 1
+                if sweeps <= 0 or not np.array_equal(m, wm) or not np.array_equal(d, wd):
+                    n_bad += 1
+                    np.savez_compressed(os.path.join(args.out, "case_w%d_b%d_it%d_DEVSRC.npz"
+                                                     % (args.worker, b, it)), u=u, prev=prev, dx=dx,
+                                        band=band)
+                    log.write("DEVSRC item %d it %d sweeps %d\n" % (b, it, sweeps))
+                    log.flush()
             dist, mask = wd, wm
-        log.write("item %d done: rebuilds %d bad %d worst sweeps %d\n" % (b, n_reb, n_bad, worst))
+        log.write("item %d done: rebuilds %d bad %d worst sweeps %d device-source checks %d\n"
+                  % (b, n_reb, n_bad, worst, n_dev))
         log.flush()
         if time.time() > t_end:
             break
-    log.write("END rebuilds %d bad %d worst sweeps %d\n" % (n_reb, n_bad, worst))
+    log.write("END rebuilds %d bad %d worst sweeps %d device-source checks %d\n"
+              % (n_reb, n_bad, worst, n_dev))
     log.close()
 
 
