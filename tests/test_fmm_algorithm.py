@@ -208,20 +208,23 @@ def test_scheduler_model_reproduces_marcher_over_evolution_sequences(oracle, see
     assert replays < 6 * voxels             # and the filter keeps the work bounded
 
 
-def test_contributor_rule_fixture(oracle):
-    """an input on which the LEGACY drop rule (largest magnitude evicted, even a
+@pytest.mark.parametrize("name,n_legacy,tol", [("fmm_nonmonotone_case.npz", 48, 1e-6),
+                                               ("fmm_c4_evolved_case.npz", 32, 1e-3)])
+def test_contributor_rule_fixture(oracle, name, n_legacy, tol):
+    """inputs on which the LEGACY drop rule (largest magnitude evicted, even a
     second neighbour across the interface) makes the marcher's freeze values non-monotone, so that
-    the replay fixed point differs from the sequential marcher in 48 distances by < 1e-7 (masks
-    agree).  With the adopted rule the two are identical; `LSML_ORACLE_RULE_R2=0 pytest` checks
-    the legacy behaviour."""
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "fmm_nonmonotone_case.npz"))
+    the replay fixed point differs from the sequential marcher in a few dozen distances (masks
+    agree): a random one (differences < 1e-7) and a crop of a C4-like evolution found by
+    tools/fmm_cycle_hunt.py (up to 1.6e-4).  With the adopted rule the two are identical;
+    `LSML_ORACLE_RULE_R2=0 pytest` checks the legacy behaviour."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
     u, dx, band = z["u"], z["dx"], float(z["band"])
     wd, wm = oracle.distance_transform(u, band, dx)
     for jacobi in (0, 1):
         d, m, sweeps = fixed_point(oracle, u, dx, band, jacobi)
         assert sweeps > 0 and np.array_equal(m, wm)
-        assert np.abs(d - wd).max() < 1e-6
+        assert np.abs(d - wd).max() < tol
         if os.environ.get("LSML_ORACLE_RULE_R2") == "0":
-            assert 0 < (d != wd).sum() < 100
+            assert (d != wd).sum() == n_legacy
         else:
             assert np.array_equal(d, wd)
