@@ -542,12 +542,13 @@ def main():
     # why this is a separate pass and not the timed region)
     eng.timers = {}
     eng.set_level_sets(u0)
-    cand_sum, sweeps_sum, replay_sum = 0, 0, 0
+    cand_sum, sweeps_sum, replay_sum, not_converged = 0, 0, 0, 0
     for i in range(N_ITERS):
         eng.step(dev_regs[i], STEP)
         if i % 5 == 4:                      # counters of a sample of the rebuilds (host sync)
             ctr = eng.fmm_counters()
             cand_sum += ctr["n_cand"]; sweeps_sum += ctr["sweeps"]; replay_sum += ctr["replays"]
+            not_converged += 0 if ctr["converged"] else 1
     phases = eng.phase_times_ms()
     eng.timers = None
     n_sampled = N_ITERS // 5
@@ -616,7 +617,8 @@ def main():
                        "band_voxel_iterations_per_step": bvi_all // max(1, args.steps),
                        "l2": "working set > L2: 5 x %d MB planes + u; stencil probe flushes L2 "
                              "between launches" % (8 * n ** 3 // 2 ** 20),
-                       "final_segmentation_voxels": seg_voxels},
+                       "final_segmentation_voxels": seg_voxels,
+                       "rebuilds_not_converged": "%d of %d sampled" % (not_converged, n_sampled)},
             "e2e": {"value": e2e_value, "unit": "band-voxel-iterations/s",
                     "h2d_bytes_per_step": int(img_pinned.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel()),
