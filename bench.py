@@ -278,6 +278,35 @@ def _blob_items(count, shape, seed, r_lo, r_hi, jitter):
     return imgs
 
 
+def harris_response(img, sigma):
+    """The user-side Python of examples/gestalt2d/corner_feature.py:
+    corner_harris(gaussian_filter(img, sigma)) with skimage's defaults (method 'k', k = 0.05,
+    structure-tensor sigma 1, Sobel derivatives, constant boundary) written with scipy because
+    scikit-image is not installed here.  Runs ONCE per image (u-independent)."""
+    from scipy import ndimage as ndi
+    sm = ndi.gaussian_filter(img, sigma) if sigma > 0 else img
+    dr = ndi.sobel(sm, axis=0, mode="constant", cval=0)
+    dc = ndi.sobel(sm, axis=1, mode="constant", cval=0)
+    arr = ndi.gaussian_filter(dr * dr, 1.0, mode="constant", cval=0)
+    arc = ndi.gaussian_filter(dr * dc, 1.0, mode="constant", cval=0)
+    acc = ndi.gaussian_filter(dc * dc, 1.0, mode="constant", cval=0)
+    return arr * acc - arc ** 2 - 0.05 * (arr + acc) ** 2
+
+
+def gestalt32_specs():
+    """The F = 32 feature list of examples/gestalt2d/main.py:27-36: basic image features at
+    sigma 0..3 (16), basic shape features (8), CornerFeature x4, PrevIterFeature x4."""
+    import functools
+    sig = (0.0, 1.0, 2.0, 3.0)
+    specs = [(k, s) for k in ("image_sample", "image_edge", "band_mean", "band_std") for s in sig]
+    specs += [("size",), ("boundary_size",), ("isoperimetric",), ("moments", (0, 1), (1, 2)),
+              ("dist_to_com",)]
+    specs += [("user_plane", "corner-reponse-sigma=%.2f" % s,
+               functools.partial(lambda img, dx, s: harris_response(img, s), s=s)) for s in sig]
+    specs += [("smooth_u", s) for s in sig]
+    return specs
+
+
 def _fit_forest(X, y, seed):
     import warnings
     from sklearn.ensemble import RandomForestRegressor
@@ -375,6 +404,8 @@ def run_other_workload(args):
                       ("band_std", 0.0), ("band_std", 2.0), ("dist_to_com",),
                       ("moments", (0, 1), (1, 2)), ("size",), ("boundary_size",),
                       ("isoperimetric",)])
+            if args.features == "gestalt32":
+                specs = gestalt32_specs()
         nd = len(shape)
         eng = BandEngine(shape, hi - lo, dx=np.ones(nd), band=BAND, specs=specs, device=device)
         eng.load_images(imgs, normalize=True)
@@ -452,6 +483,9 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--items", type=int, default=0, help="c2: total images, c4: crops per GPU")
+    ap.add_argument("--features", default="basic", choices=["basic", "gestalt32"],
+                    help="c2: `gestalt32` = the full F = 32 list of examples/gestalt2d (corner and "
+                         "previous-iterate features through the user-feature registry)")
     args = ap.parse_args()
     if args.workload != "c3" and args.impl != "reference":
         return run_other_workload(args)

@@ -19,4 +19,5 @@ for items in 256 512 1024 2048; do
     run bench_c4_$items 240 python bench.py --workload c4 --items $items --steps 1 --warmup 1
 done
 run bench_c2 240 python bench.py --workload c2 --steps 2 --warmup 1
+run bench_c2_f32 240 python bench.py --workload c2 --features gestalt32 --steps 2 --warmup 1
 run slab_512 300 python tools/slab_probe.py 512
