@@ -66,22 +66,20 @@ def overlap_scores(eng, segs_dev):
         return numpy.where(c[:, 1] == 0, 1.0, c[:, 0] / c[:, 1])
 
 
-def balance_mask(y, random_state=None):
-    """lsml/util/balance_mask.py:4-44: randomly down-sample the majority sign of ``y``."""
+def balance_mask(arr, random_state=None):
+    """lsml/util/balance_mask.py:4-44: a mask under which ``arr`` has as many positive as
+    negative entries.  The larger sign class is down-sampled at random (one ``choice`` call, so
+    the RNG stream matches the reference); zeros always stay; an array that cannot be balanced
+    (no positive or no negative entry) or is already balanced keeps everything."""
     rs = numpy.random.RandomState() if random_state is None else random_state
-    n_pos, n_neg = (y > 0).sum(), (y < 0).sum()
-    n = min(n_pos, n_neg)
-    mask = numpy.zeros(y.shape, dtype=bool)
-    if n_pos > n_neg:
-        inds = rs.choice(numpy.where(y > 0)[0], replace=False, size=n)
-        mask[inds] = True
-        mask[y < 0] = True
-    elif n_pos < n_neg:
-        inds = rs.choice(numpy.where(y < 0)[0], replace=False, size=n)
-        mask[inds] = True
-        mask[y > 0] = True
-    else:
-        mask[y != 0] = True
+    pos, neg = arr > 0, arr < 0
+    n_pos, n_neg = int(pos.sum()), int(neg.sum())
+    if n_pos == 0 or n_neg == 0 or n_pos == n_neg:
+        return numpy.ones(arr.shape, dtype=bool)
+    major, n_keep = (pos, n_neg) if n_pos > n_neg else (neg, n_pos)
+    keep = rs.choice(numpy.where(major)[0], replace=False, size=n_keep)
+    mask = ~major
+    mask[keep] = True
     return mask
 
 
@@ -187,6 +185,10 @@ class LevelSetMachineLearning:
         gt.set_level_sets(2.0 * segs.astype(float) - 1.0)
         dist_gt = gt.distance().reshape(-1)
         del gt
+        if callable(seeds):      # e.g. center_of_mass_seeder (the reference's default, model.py:107)
+            import types
+            seeds = [seeds(types.SimpleNamespace(img=imgs[i], seg=segs[i], dx=dxv, dist=None))
+                     for i in range(n)]
         eng.set_level_sets(self._initial_level_sets(eng, seeds=seeds))
 
         def band_targets():
