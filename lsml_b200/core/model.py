@@ -83,6 +83,28 @@ def balance_mask(arr, random_state=None):
     return mask
 
 
+def split_datasets(n, datasets_split, subset_size, random_state):
+    """Indices of the training / validation / testing examples (datasets_handler.py:204-362):
+    three index lists are used as given; three probabilities assign at random with the
+    reference's RNG stream and quirk -- a permutation is drawn
+    (``choice(keys, replace=False, size=subset_size)``) but only its LENGTH is used, so the
+    examples that take part are the first ``subset_size`` ones, each placed by one multinomial
+    draw."""
+    if all(numpy.iterable(s) for s in datasets_split):
+        return tuple(numpy.asarray(s, dtype=int) for s in datasets_split)
+    if not all(isinstance(s, float) for s in datasets_split):
+        raise ValueError("`training`, `validation`, and `testing` should be "
+                         "all floats or all list of ints")
+    if subset_size is not None and subset_size > n:
+        raise ValueError("`subset_size` must be <= `len(keys)`")
+    n_sub = n if subset_size is None else int(subset_size)
+    random_state.choice(n, replace=False, size=n_sub)
+    indicators = random_state.multinomial(n=1, pvals=datasets_split, size=n_sub)
+    assign = indicators.argmax(axis=1)
+    idx = numpy.arange(n_sub)
+    return idx[assign == 0], idx[assign == 1], idx[assign == 2]
+
+
 class LevelSetMachineLearning:
 
     def __init__(self, features, initializer, scorer=jaccard, band=3, normalize_imgs=True):
@@ -164,15 +186,7 @@ class LevelSetMachineLearning:
             if not (dxv == dxv[0]).all():
                 raise NotImplementedError("per-example dx must be identical within a batch")
             dxv = dxv[0]
-        # dataset split (datasets_handler.py:204-362): explicit index lists or probabilities
-        if all(numpy.iterable(s) for s in datasets_split):
-            tr, va, te = [numpy.asarray(s, dtype=int) for s in datasets_split]
-        else:
-            idx = numpy.arange(n)
-            if subset_size is not None:
-                idx = rs.choice(idx, replace=False, size=subset_size)
-            assign = rs.choice(3, size=len(idx), p=numpy.asarray(datasets_split, dtype=float))
-            tr, va, te = idx[assign == 0], idx[assign == 1], idx[assign == 2]
+        tr, va, te = split_datasets(n, datasets_split, subset_size, rs)
         self._split = dict(training=tr, validation=va, testing=te)
 
         specs = self.feature_map.specs()
@@ -237,8 +251,11 @@ class LevelSetMachineLearning:
                 self._is_fitted = True
                 self.save(save_filename)
                 self._is_fitted = False
-            # early exit on the trend of the validation score (fit_job_handler.py:523-562)
-            if self.iteration >= validation_history_len and len(va):
+            # early exit on the trend of the validation score over the last
+            # `validation_history_len` scores, current one included (fit_job_handler.py:523-562:
+            # possible from iteration validation_history_len - 1 on, the score at
+            # initialisation counts)
+            if self.iteration >= validation_history_len - 1 and len(va):
                 hist = numpy.array([numpy.mean(s) for s in
                                     self.scores["validation"][-validation_history_len:]])
                 xs = numpy.c_[numpy.arange(validation_history_len),

@@ -133,3 +133,35 @@ def test_pack_trees_round_trip():
                 idx = (meta & 0x3fffff) + int(right)
             acc[i] += tree[idx].view(np.float64)[0]
     assert np.array_equal(acc / len(root), rf.predict(Xt))
+
+
+def test_fit_host_logic_matches_reference_statements():
+    """The host-side pieces of `fit` that decide WHICH data is used, against literal
+    transcriptions of the reference's statements (datasets_handler.py:312-362; the reference's
+    own function needs h5py): same split for the same RandomState, same RNG consumption."""
+    from lsml_b200.core.model import split_datasets
+
+    def reference_split(n, probs, subset_size, rs):
+        keys = ["%05d" % i for i in range(n)]
+        if subset_size is None:
+            subset_size = len(keys)
+        sub_keys = rs.choice(keys, replace=False, size=subset_size)
+        indicators = rs.multinomial(n=1, pvals=probs, size=len(sub_keys))
+        return [[i for i, ind in enumerate(indicators) if list(ind).index(1) == d] for d in range(3)]
+
+    for seed in range(40):
+        n = 5 + seed
+        subset = None if seed % 3 else max(1, n // 2)
+        want = reference_split(n, (0.6, 0.2, 0.2), subset, np.random.RandomState(seed))
+        rs = np.random.RandomState(seed)
+        got = split_datasets(n, (0.6, 0.2, 0.2), subset, rs)
+        assert [list(g) for g in got] == want
+        ref_rs = np.random.RandomState(seed)
+        reference_split(n, (0.6, 0.2, 0.2), subset, ref_rs)
+        assert rs.randint(1 << 30) == ref_rs.randint(1 << 30)
+    tr, va, te = split_datasets(10, ([0, 1, 2], [3], [4, 5]), None, np.random.RandomState(0))
+    assert list(tr) == [0, 1, 2] and list(va) == [3] and list(te) == [4, 5]
+    with pytest.raises(ValueError):
+        split_datasets(4, (0.6, 0.2, 0.2), 9, np.random.RandomState(0))
+    with pytest.raises(ValueError):
+        split_datasets(4, (1, 0, 0), None, np.random.RandomState(0))
