@@ -1,0 +1,96 @@
+"""CPU-only, and only where /root/reference exists: the HOST side of the drop-in (names, sizes,
+constructor errors, initializers, scores, balance_mask) compared directly with the unmodified
+reference imported through oracle/ref_shim.py."""
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    from oracle.ref_shim import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference is not present on this machine")
+    import_reference(skfmm_distance=oracle.skfmm_distance)
+    import lsml
+    return lsml
+
+
+def test_feature_names_sizes_and_constructor_errors(ref):
+    import lsml.feature.provided.image as rimg
+    import lsml.feature.provided.shape as rshp
+    from lsml.feature.feature_map import FeatureMap as RFM
+    import lsml_b200.feature.provided.image as mimg
+    import lsml_b200.feature.provided.shape as mshp
+    from lsml_b200.feature.feature_map import FeatureMap as MFM
+    pairs = []
+    for ndim in (2, 3):
+        for s in (0, 1.5, 3):
+            for cls in ("ImageSample", "ImageEdgeSample", "InteriorImageAverage", "InteriorImageVariation"):
+                pairs.append((getattr(rimg, cls)(ndim=ndim, sigma=s), getattr(mimg, cls)(ndim=ndim, sigma=s)))
+            pairs.append((rimg.COMRaySample(ndim=ndim, sigma=s, n_samples=7),
+                          mimg.COMRaySample(ndim=ndim, sigma=s, n_samples=7)))
+        for cls in ("Size", "BoundarySize", "IsoperimetricRatio", "DistanceToCenterOfMass"):
+            pairs.append((getattr(rshp, cls)(ndim=ndim), getattr(mshp, cls)(ndim=ndim)))
+        pairs.append((rshp.Moments(ndim=ndim, axes=list(range(ndim)), orders=[1, 2]),
+                      mshp.Moments(ndim=ndim, axes=list(range(ndim)), orders=[1, 2])))
+    for r, m in pairs:
+        for attr in ("name", "size", "type", "locality"):
+            assert getattr(r, attr) == getattr(m, attr), (type(r).__name__, attr)
+    for ndim in (2, 3):
+        rfeats = rimg.get_basic_image_features(ndim=ndim, sigmas=[0, 2, 3]) + rshp.get_basic_shape_features(ndim=ndim)
+        mfeats = mimg.get_basic_image_features(ndim=ndim, sigmas=[0, 2, 3]) + mshp.get_basic_shape_features(ndim=ndim)
+        assert [f.name for f in rfeats] == [f.name for f in mfeats]
+        rf, mf = RFM(rfeats), MFM(mfeats)
+        assert rf.n_features == mf.n_features and rf.feature_slices == mf.feature_slices
+
+    def err(f):
+        try:
+            f()
+        except Exception as e:
+            return type(e).__name__
+        return None
+
+    cases = [lambda M: M[0].COMRaySample(ndim=1), lambda M: M[1].Moments(ndim=2, axes=(2,)),
+             lambda M: M[1].BoundarySize(ndim=1), lambda M: M[1].IsoperimetricRatio(ndim=1),
+             lambda M: M[1].Moments(ndim=2, orders=(0,)), lambda M: M[2]([M[1].Size(2), M[1].Size(2)]),
+             lambda M: M[2]([1, 2]), lambda M: M[2](5)]
+    for c in cases:
+        a, b = err(lambda: c((rimg, rshp, RFM))), err(lambda: c((mimg, mshp, MFM)))
+        assert a == b and a is not None
+
+
+def test_initializers_scores_and_balance_mask(ref):
+    from lsml.initializer.provided.ball import BallInitializer as RB, RandomBallInitializer as RRB
+    from lsml.score_functions import dice as rd, jaccard as rj
+    from lsml.util.balance_mask import balance_mask as rbal
+    from lsml_b200.initializer import BallInitializer as MB, RandomBallInitializer as MRB
+    from lsml_b200.score_functions import dice as md, jaccard as mj
+    from lsml_b200.util.balance_mask import balance_mask as mbal
+    rs = np.random.RandomState(0)
+    for t in range(120):
+        ndim = rs.choice([1, 2, 3])
+        shape = tuple(rs.randint(8, 30, size=ndim))
+        dx = rs.uniform(0.5, 2.0, size=ndim)
+        img = rs.randn(*shape)
+        seed = np.array(shape) / 2
+        loc = None if t % 2 else list(rs.uniform(2, 6, size=ndim))
+        r = rs.uniform(2, 6)
+        assert np.array_equal(RB(radius=r, location=loc).initialize(img=img, dx=dx, seed=seed),
+                              MB(radius=r, location=loc).initialize(img=img, dx=dx, seed=seed))
+        if ndim >= 2:
+            a = RRB(random_state=np.random.RandomState(t), randomize_center=bool(t % 3))
+            b = MRB(random_state=np.random.RandomState(t), randomize_center=bool(t % 3))
+            assert np.array_equal(a.initialize(img=img, dx=dx, seed=seed),
+                                  b.initialize(img=img, dx=dx, seed=seed))
+        u, seg = rs.randn(*shape), rs.rand(*shape) > 0.5
+        assert rj(u, seg) == mj(u, seg) and rd(u, seg) == md(u, seg) and rj(u, seg, 0.3) == mj(u, seg, 0.3)
+        n = rs.randint(1, 60)
+        arr = rs.randn(n) * rs.choice([0, 1, 1, 1], size=n)
+        if t % 7 == 0:
+            arr = np.abs(arr)
+        if t % 11 == 0:
+            arr = -np.abs(arr)
+        r1, r2 = np.random.RandomState(t), np.random.RandomState(t)
+        assert np.array_equal(rbal(arr, r1), mbal(arr, r2))
+        assert r1.randint(1 << 30) == r2.randint(1 << 30)            # same RNG consumption
+    assert mj(np.zeros((4, 4)) - 1, np.zeros((4, 4), bool)) == 1.0
