@@ -50,6 +50,8 @@ def _host_gmag_os_func(ndim):
 def _validate(arr, mask, dx, batched):
     ndim = arr.ndim - (1 if batched else 0)
     assert 1 <= ndim <= 3, "Only dimensions 1-3 supported."
+    if not _is_tensor(arr) and arr.dtype != np.float64:      # checked second, as the reference
+        raise ValueError("`arr` must be float type.")
     if mask is not None and mask.ndim != arr.ndim:
         raise ValueError("Shape mismatch between `mask` and `arr`.")
     if dx is not None:

@@ -94,3 +94,31 @@ def test_initializers_scores_and_balance_mask(ref):
         assert np.array_equal(rbal(arr, r1), mbal(arr, r2))
         assert r1.randint(1 << 30) == r2.randint(1 << 30)            # same RNG consumption
     assert mj(np.zeros((4, 4)) - 1, np.zeros((4, 4), bool)) == 1.0
+
+
+def test_masked_gradient_validation_errors(ref):
+    """Same exception type AND message, in the reference's order of checks
+    (masked_gradient.py:112-127, 202-217); raised before any kernel is reached."""
+    from lsml.gradient import masked_gradient as rmg
+    from lsml_b200.gradient import masked_gradient as mmg
+
+    def err(f):
+        try:
+            f()
+        except BaseException as e:
+            return type(e).__name__, str(e)
+        return None
+
+    a4, a2 = np.zeros((2, 2, 2, 2)), np.zeros((4, 5))
+    f32 = np.zeros((4, 5), dtype=np.float32)
+    cases = [lambda m: m.gradient_centered(a4), lambda m: m.gradient_centered(f32),
+             lambda m: m.gradient_centered(a2, mask=np.ones(4, bool)),
+             lambda m: m.gradient_centered(a2, dx=[1.0]),
+             lambda m: m.gradient_centered(f32, mask=np.ones(4, bool), dx=[1.0]),
+             lambda m: m.gradient_magnitude_osher_sethian(a4, a4),
+             lambda m: m.gradient_magnitude_osher_sethian(f32, f32),
+             lambda m: m.gradient_magnitude_osher_sethian(a2, a2, mask=np.ones(4, bool)),
+             lambda m: m.gradient_magnitude_osher_sethian(a2, a2, dx=[1.0, 2.0, 3.0])]
+    for c in cases:
+        want, got = err(lambda: c(rmg)), err(lambda: c(mmg))
+        assert want is not None and want == got
