@@ -41,7 +41,7 @@ class NumpyForest:
         meta_all = self.nodes[:, 1].astype(np.int64)
         val_all = self.nodes.copy().view(np.float64).ravel()
         rows = np.arange(n)
-        for t, base in enumerate(self.bases):
+        for t, base in enumerate(self.bases[:len(self.root)]):   # (bases may end with a sentinel)
             idx = np.zeros(n, dtype=np.int64)
             leaf = np.full(n, bool(self.root[t]))
             while not leaf.all():
@@ -52,7 +52,7 @@ class NumpyForest:
                 idx[live] = (meta & 0x3fffff) + right
                 leaf[live] = np.where(right, (meta >> 22) & 1, (meta >> 23) & 1).astype(bool)
             acc += val_all[base + idx]
-        return acc / len(self.bases)
+        return acc / len(self.root)
 
 
 def regressors_of(fix, kind):

@@ -37,6 +37,20 @@ def test_feature_restatements_bit_exact(oracle):
         assert np.array_equal(m, mask)
     X = oracle.feature_matrix(specs3, f["u3"], f["img3"], None, f["mask3"], f["dx3"])
     assert np.array_equal(X, f["X3"])
+    _, m = oracle.distance_transform(f["u3"], 3, f["dx3"])
+    assert np.array_equal(m, f["mask3"])
+
+
+def test_every_fixture_band_is_the_current_oracles(oracle):
+    """The fixtures' band masks come from the reference's distance_transform wrapper with the
+    oracle's marcher plugged in for the absent scikit-fmm: a fixture generated before a change of
+    the marcher (e.g. the contributor rule) must be regenerated, or the GPU golden
+    tests would compare against a stale band."""
+    for name in ("com_ray.npz", "prev_iter.npz"):
+        g = load(name)
+        for c in range(int(g["n_cases"])):
+            _, m = oracle.distance_transform(g["u%d" % c], 3, g["dx%d" % c])
+            assert np.array_equal(m, g["mask%d" % c]), (name, c)
 
 
 def test_initializers(oracle):
