@@ -486,7 +486,21 @@ def main():
     ap.add_argument("--features", default="basic", choices=["basic", "gestalt32"],
                     help="c2: `gestalt32` = the full F = 32 list of examples/gestalt2d (corner and "
                          "previous-iterate features through the user-feature registry)")
+    ap.add_argument("--watchdog", type=float, default=1500.0,
+                    help="seconds after which the process kills itself (a hung kernel cannot be "
+                         "interrupted from Python; exiting releases the GPU box instead of "
+                         "holding it until an outer limit); 0 disables")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import threading
+
+        def _abort():
+            print("bench.py: watchdog fired after %.0f s -- aborting (exit 124)" % args.watchdog,
+                  file=sys.stderr, flush=True)
+            os._exit(124)
+        timer = threading.Timer(args.watchdog, _abort)
+        timer.daemon = True
+        timer.start()
     if args.workload != "c3" and args.impl != "reference":
         return run_other_workload(args)
     args.size = args.size or 256
