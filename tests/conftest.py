@@ -28,6 +28,12 @@ NOT_YET_RUN_ON_GPU = ("test_reference_suite.py", "test_wider_features_gpu.py")
 def pytest_collection_modifyitems(config, items):
     items.sort(key=lambda it: 1 if it.fspath.basename in NOT_YET_RUN_ON_GPU else 0)   # stable
     if _has_gpu():
+        # a hung kernel cannot be interrupted from Python: pytest-timeout's thread method ends
+        # the process, which releases the GPU instead of holding the box until an outer limit
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords:
+                    item.add_marker(pytest.mark.timeout(900, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
