@@ -31,6 +31,10 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--out", default="/tmp/fmm_hunt")
     ap.add_argument("--minutes", type=float, default=60.0)
+    ap.add_argument("--size", type=int, default=64, help="edge of the cubic crops")
+    ap.add_argument("--radius", type=float, nargs=2, default=(6.0, 18.0), help="object radius range")
+    ap.add_argument("--init-radius", type=float, default=5.0)
+    ap.add_argument("--jitter", type=float, default=8.0)
     ap.add_argument("--device-source-every", type=int, default=0,
                     help="also iterate the kernel's own source, compiled for the host "
                          "(tests/test_fmm_device_code_host.py), on every N-th rebuild input")
@@ -48,11 +52,11 @@ def main():
         legacy = os.environ.get("LSML_ORACLE_RULE_R2") == "0"
         dev_lib = ctypes.CDLL(build_host_lib(tempfile.mkdtemp(), legacy))
     n_dev = 0
-    shape, band, dx = (64, 64, 64), 3.0, np.ones(3)
-    CHUNK = 64          # items are generated 64 at a time (2 MB each)
+    shape, band, dx = (args.size,) * 3, 3.0, np.ones(3)
+    CHUNK = 16          # items are generated 16 at a time
     g = np.indices(shape).astype(np.float64)
     rc = np.sqrt(sum((g[a] - shape[a] / 2.0) ** 2 for a in range(3)))
-    u0 = np.where(rc < 5.0, 1.0, -1.0)
+    u0 = np.where(rc < args.init_radius, 1.0, -1.0)
     specs = bench.SPECS
     # u-independent planes once per item; everything else per iteration (oracle expressions)
     def planes_of(img):
@@ -85,7 +89,7 @@ def main():
     for b in range(args.items):
         if b % CHUNK == 0:
             imgs = bench._blob_items(CHUNK, shape, 10000 + 97 * args.worker + 7919 * (b // CHUNK),
-                                     6, 18, 8)
+                                     args.radius[0], args.radius[1], args.jitter)
         img = O.normalize_image(imgs[b % CHUNK])
         pl = planes_of(img)
         u = u0.copy()
