@@ -6,7 +6,7 @@ lsml_ball_init (no host grid, no upload) -- same float64 expression, bit-identic
 """
 import numpy
 
-from .initializer_base import InitializerBase
+from ..initializer_base import InitializerBase
 
 
 class BallInitializer(InitializerBase):
@@ -87,3 +87,41 @@ class RandomBallInitializer(InitializerBase):
         indices -= center.reshape(shape)
         indices **= 2
         return indices.sum(axis=0)**0.5 <= radius
+
+
+class ThresholdBallInitializer(InitializerBase):
+    """ A ball around the seed whose radius is the seed's distance to the boundary of the
+    connected component (of ``img > gaussian_filter(img, sigma)``) it lies in, or of the nearest
+    component (reference ball.py:118-159).  Host side, once per image; the distance to the
+    component's complement is the device marcher's (the reference calls ``skfmm.distance``). """
+
+    def __init__(self, sigma=4.0):
+        self.sigma = sigma
+
+    def initialize(self, img, dx, seed):
+        from scipy.ndimage import gaussian_filter, label
+        from ...util.distance_transform import distance_transform
+
+        smoothed = gaussian_filter(img, self.sigma)
+        thresholded = img > smoothed
+        labels, _ = label(thresholded)
+        if labels[self._seed_to_index(seed)] > 0:
+            seed_ = seed
+        else:
+            nonzero = numpy.array(numpy.nonzero(labels)).T.astype(float)
+            nonzero *= dx
+            dists = numpy.linalg.norm(nonzero - seed, axis=1)
+            seed_ = nonzero[dists.argmin()]
+        mask = labels == labels[self._seed_to_index(seed_)]
+        inds = numpy.indices(img.shape, dtype=float)
+        for i in range(inds.shape[0]):
+            inds[i] -= seed_[i]
+            inds[i] *= dx[i]
+        dist_to_seed = (inds ** 2).sum(axis=0) ** 0.5
+        # skfmm.distance(mask, dx): the bool mask as a level set (0 outside, 1 inside)
+        dist_to_boundary, _ = distance_transform(mask.astype(float), band=0, dx=dx)
+        return dist_to_seed < dist_to_boundary[self._seed_to_index(seed_)]
+
+    @staticmethod
+    def _seed_to_index(seed):
+        return tuple(numpy.asarray(seed).round().astype(int))

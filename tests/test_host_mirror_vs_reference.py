@@ -122,3 +122,54 @@ def test_masked_gradient_validation_errors(ref):
     for c in cases:
         want, got = err(lambda: c(rmg)), err(lambda: c(mmg))
         assert want is not None and want == got
+
+
+def test_threshold_ball_initializer_host_logic(ref, oracle, monkeypatch):
+    """ThresholdBallInitializer (ball.py:118-159): the reference with the oracle's marcher plugged
+    in for skfmm vs ours with the same marcher plugged in for the device call -- everything
+    else (smoothing, labelling, seed handling, the ball) is host code and must agree."""
+    from lsml.initializer.provided.ball import ThresholdBallInitializer as RTB
+    from lsml_b200.initializer.provided import ball as mball
+    import lsml_b200.util.distance_transform as mdt
+
+    def oracle_dt(arr, band, dx):
+        d = oracle.skfmm_distance(arr, dx=dx)
+        return np.asarray(d), np.ones(arr.shape, dtype=bool)
+
+    monkeypatch.setattr(mdt, "distance_transform", oracle_dt)
+    rs = np.random.RandomState(4)
+    checked = 0
+    for t in range(12):
+        shape = (40, 48) if t % 2 else (18, 20, 22)
+        g = np.indices(shape).astype(float)
+        c = np.array(shape) / 2.0 + rs.uniform(-2, 2, size=len(shape))
+        r = np.sqrt(sum((g[a] - c[a]) ** 2 for a in range(len(shape))))
+        img = (r < 6).astype(float) * 2.0 + 0.3 * rs.randn(*shape)
+        dx = np.ones(len(shape))
+        seed = np.round(c)
+        want = RTB(sigma=3.0).initialize(img=img, dx=dx, seed=seed)
+        got = mball.ThresholdBallInitializer(sigma=3.0).initialize(img=img, dx=dx, seed=seed)
+        assert got.dtype == bool and np.array_equal(want, got)
+        checked += int(got.any())
+    assert checked >= 8
+    # the seed outside every component: the nearest component is used (the reference's own
+    # fallback multiplies an integer array by dx in place and fails on current numpy)
+    img = np.zeros((30, 30))
+    img[18:25, 18:25] = 5.0
+    got = mball.ThresholdBallInitializer(sigma=2.0).initialize(img=img, dx=np.ones(2), seed=np.array([3.0, 3.0]))
+    assert got.any() and got[18:25, 18:25].any() and not got[:10, :10].any()
+
+
+def test_threshold_initializer_reference_test():
+    """initializer/provided/test/test_threshold.py:8-26 on the host part (`initialize`)."""
+    from lsml_b200.initializer import ThresholdInitializer
+    random_state = np.random.RandomState(1234)
+    mask = np.pad(np.ones((5, 5), dtype=bool), 5, 'constant')
+    image = np.zeros(mask.shape)
+    image[mask] = 1 + 0.5 * random_state.randn(mask.sum())
+    image[~mask] = -1 - 0.5 * random_state.rand((~mask).sum())
+    assert (mask == ThresholdInitializer(sigma=0).initialize(image, np.ones(2), None)).all()
+    blurred = ThresholdInitializer(sigma=1.0).initialize(image, np.ones(2), None)
+    assert blurred.dtype == bool and blurred[7, 7] and not blurred[0, 0]
+    with pytest.raises(ValueError):
+        ThresholdInitializer(sigma=-1)

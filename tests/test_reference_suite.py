@@ -9,7 +9,7 @@ same calls, same assertions, with ``lsml.*`` replaced by a ``pkg`` fixture.  ``p
 
 Tests that never reach a kernel (validation, equality, balance_mask, seeds) run against
 ``lsml_b200`` on the CPU as well.  Left out, with the reason: ``test_datasets_handler.py`` (HDF5
-store, out of scope), ``test_threshold.py`` (needs scikit-image's Otsu), the 3-D
+store, out of scope), the 3-D
 ``BoundarySize`` / ``IsoperimetricRatio`` tests (Lewiner marching cubes: not implemented,
 asserted as such).  The 3-D grids of test_shape.py are subsampled by 2 per axis on the CPU
 (reference) leg to keep it to seconds; the GPU leg uses the reference's sizes.
@@ -445,6 +445,20 @@ def test_ball_initializers(pkg):
     image[~mask] = -1 - 0.5 * random_state.rand((~mask).sum())
     u0, _, _ = pkg.RandomBallInitializer(random_state=random_state)(image)
     assert (u0 > 0).any()
+
+
+def test_threshold_initializer_square_image(pkg):
+    """initializer/provided/test/test_threshold.py:8-26"""
+    if pkg.name == "reference":
+        pytest.skip("scikit-image (threshold_otsu) is not installed: the reference leg cannot run")
+    from lsml_b200.initializer import ThresholdInitializer
+    random_state = np.random.RandomState(1234)
+    mask = np.pad(np.ones((5, 5), dtype=bool), 5, 'constant')
+    image = np.zeros(mask.shape)
+    image[mask] = 1 + 0.5 * random_state.randn(mask.sum())
+    image[~mask] = -1 - 0.5 * random_state.rand((~mask).sum())
+    u0, _, _ = ThresholdInitializer(sigma=0)(image)
+    assert (mask == (u0 > 0)).all()
 
 
 def test_initializer_base_call(pkg):
