@@ -12,6 +12,7 @@ memory, keeps the level sets of ALL examples resident in HBM as one batch, train
 scikit-learn regressor on the host each iteration and keeps the fitted regressors in memory.
 ``segment`` never touches the disk.
 """
+import copy
 import functools
 import pickle
 
@@ -238,7 +239,11 @@ class LevelSetMachineLearning:
                     keep.append(numpy.arange(off[i], off[i + 1])[balance_mask(yi, rs)])
                 keep = numpy.concatenate(keep) if keep else numpy.zeros(0, dtype=int)
                 Xtr, ytr = X[keep], y[keep]
-            model = regression_model_class(**kwargs)
+            # The reference fits in a forked child process and pickles the result
+            # (fit_job_handler.py:398-424): the objects in `regression_model_kwargs` (estimator
+            # instances of a Pipeline, a shared RandomState ...) are COPIES there -- the parent's
+            # are never fitted or advanced, and every iteration's model is its own snapshot.
+            model = regression_model_class(**copy.deepcopy(kwargs))
             model.fit(Xtr, ytr)
             self.regression_models.append(model)
             eng.step(model, self._step)

@@ -99,7 +99,80 @@ def gen_prev_iter():
     print("prev_iter.npz", os.path.getsize(os.path.join(OUT, "prev_iter.npz")))
 
 
+def gen_fit():
+    """tests/golden/fit.npz: the UNMODIFIED reference's LevelSetMachineLearning.fit (model.py:89-249,
+    fit_job_handler.py) run end to end on a small in-memory dataset -- h5py replaced by
+    oracle/fake_h5py.py, skfmm by the oracle's marcher -- and its segment() on a held-out image."""
+    import tempfile
+    warnings.simplefilter("ignore")
+    from oracle import oracle as O
+    from oracle import fake_h5py
+    from oracle.ref_shim import import_reference
+    O.build()
+    lsml = import_reference(skfmm_distance=O.skfmm_distance)
+    from lsml.feature import (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                              InteriorImageVariation, Size, Moments, DistanceToCenterOfMass)
+    from lsml.initializer import BallInitializer
+    from lsml.data.dim2 import hamburger
+    from sklearn.linear_model import LinearRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    imgs, segs = hamburger.make_dataset(N=15, n=41, random_state=np.random.RandomState(3))
+    imgs, segs = np.asarray(imgs, dtype=float), np.asarray(segs, dtype=bool)
+    feats = ([cls(ndim=2, sigma=s) for cls in (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                                               InteriorImageVariation) for s in (0, 2)] +
+             [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
+    out = {"imgs": imgs, "segs": segs}
+    cwd = os.getcwd()
+    for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5)):
+        fake_h5py.reset()
+        tmp = tempfile.mkdtemp()
+        os.chdir(tmp)
+        try:
+            model = lsml.LevelSetMachineLearning(features=feats, initializer=BallInitializer(radius=6),
+                                                 band=3)
+            model.fit('dataset.h5', imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
+                      random_state=np.random.RandomState(seed),
+                      regression_model_class=Pipeline,
+                      regression_model_kwargs=dict(steps=[('s', StandardScaler()),
+                                                          ('r', LinearRegression())]),
+                      balance_regression_targets=balance, temp_data_dir=tmp,
+                      save_filename=os.path.join(tmp, 'm.pkl'), redirect_stdout_to_logfile=False,
+                      validation_history_len=4, validation_history_tol=-1.0)
+            fj = model.fit_job_handler
+            for key in ("training", "validation", "testing"):
+                idx = [int(k.split("-")[-1]) for k in fj.datasets_handler.datasets[key]]
+                out["%s_%s_idx" % (tag, key)] = np.asarray(idx, dtype=np.int64)
+            out["%s_step" % tag] = float(model.step)
+            out["%s_iterations" % tag] = int(fj.iteration)
+            out["%s_training_scores" % tag] = np.asarray(model.training_scores)
+            out["%s_validation_scores" % tag] = np.asarray(model.validation_scores)
+            out["%s_testing_scores" % tag] = np.asarray(model.testing_scores)
+            for i in range(1, fj.iteration + 1):
+                reg = model.regression_model(i)
+                out["%s_mean_%d" % (tag, i)] = reg.steps[0][1].mean_
+                out["%s_scale_%d" % (tag, i)] = reg.steps[0][1].scale_
+                out["%s_coef_%d" % (tag, i)] = reg.steps[1][1].coef_
+                out["%s_intercept_%d" % (tag, i)] = np.asarray(reg.steps[1][1].intercept_)
+            out["%s_us" % tag] = model.segment(imgs[14], verbose=False,
+                                               iterate_until_validation_max=False)
+            out["%s_us_valmax" % tag] = model.segment(imgs[14], verbose=False)
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "fit.npz"),
+                        notes="the reference's own fit() (in-memory h5py stand-in, skfmm plugged by "
+                              "the oracle): split, auto step, scores, per-iteration StandardScaler+"
+                              "LinearRegression parameters, segment() of a held-out image; "
+                              "random_state seeds 77 (balanced targets) and 5 (not balanced), "
+                              "14 training images 41x41, BallInitializer(radius=6), band 3, "
+                              "max_iters 7, validation_history_len 4, tol -1 (never exits early)",
+                        **out)
+    print("fit.npz", os.path.getsize(os.path.join(OUT, "fit.npz")))
+
+
 def main():
+    if sys.argv[1:] == ["fit"]:
+        return gen_fit()
     if sys.argv[1:] == ["com_ray"]:       # regenerate that fixture only
         return gen_com_ray()
     if sys.argv[1:] == ["prev_iter"]:
@@ -261,6 +334,7 @@ def main():
                         **seg_fix)
     gen_com_ray()
     gen_prev_iter()
+    gen_fit()
     for name in sorted(os.listdir(OUT)):
         print(name, os.path.getsize(os.path.join(OUT, name)))
 

@@ -1,0 +1,50 @@
+"""GPU: ``lsml_b200``'s ``fit`` + ``segment`` with the real device engine against the reference's
+OWN ``fit`` (tests/golden/fit.npz; see tests/test_fit_host_logic_cpu.py for the same comparison
+with the oracle's numerics, where it is bit-exact)."""
+import numpy as np
+import pytest
+
+from golden_util import load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5)])
+def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
+    from sklearn.linear_model import LinearRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from lsml_b200 import LevelSetMachineLearning
+    from lsml_b200.feature import (DistanceToCenterOfMass, Moments, Size, get_basic_image_features)
+    from lsml_b200.initializer import BallInitializer
+    g = load("fit.npz")
+    imgs, segs = g["imgs"], g["segs"]
+    feats = (get_basic_image_features(ndim=2, sigmas=[0, 2]) +
+             [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
+    model = LevelSetMachineLearning(feats, BallInitializer(radius=6), band=3)
+    model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
+              random_state=np.random.RandomState(seed), regression_model_class=Pipeline,
+              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', LinearRegression())]),
+              balance_regression_targets=balance, validation_history_len=4,
+              validation_history_tol=-1.0)
+    for key in ("training", "validation", "testing"):
+        assert list(model._split[key]) == list(g["%s_%s_idx" % (tag, key)])
+    assert model.step == float(g[tag + "_step"])            # max |ground-truth distance| on the band
+    assert model.iteration == int(g[tag + "_iterations"])
+    for i in range(1, model.iteration + 1):
+        reg = model.regression_model(i)
+        # the training matrices agree to the last bits (band statistics are summed in another
+        # order); least squares amplifies that by its conditioning
+        assert np.allclose(reg.steps[0][1].mean_, g["%s_mean_%d" % (tag, i)], rtol=1e-9, atol=1e-12), i
+        assert np.allclose(reg.steps[0][1].scale_, g["%s_scale_%d" % (tag, i)], rtol=1e-9, atol=1e-12), i
+        assert np.allclose(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)], rtol=1e-5, atol=1e-7), i
+    for key in ("training", "validation", "testing"):
+        assert np.allclose(getattr(model, key + "_scores"), g["%s_%s_scores" % (tag, key)],
+                           rtol=0, atol=1e-9), key
+    for flag, name in ((False, "_us"), (True, "_us_valmax")):
+        us = model.segment(imgs[14], verbose=False, iterate_until_validation_max=flag)
+        want = g[tag + name]
+        assert us.shape == want.shape
+        for i in range(us.shape[0]):
+            assert np.array_equal(us[i] > 0, want[i] > 0), i
+            assert np.allclose(us[i], want[i], rtol=1e-5, atol=1e-8), np.abs(us[i] - want[i]).max()

@@ -1,0 +1,65 @@
+"""CPU-only: the HOST logic of ``lsml_b200``'s ``fit`` and ``segment`` against the reference's
+OWN ``fit`` (tests/golden/fit.npz, made by oracle/gen_golden.py from the unmodified reference
+with an in-memory h5py stand-in).
+
+The device engine is replaced by tests/oracle_engine.py (oracle numerics), everything else is
+the product's code: dataset split and RNG stream, ball initializer parameters, ground-truth
+distances as regression targets, the automatic step, per-example target balancing, the order of
+the training rows, the per-iteration scikit-learn fit, score bookkeeping, ``segment``'s
+reconstruction of all iterates.  With identical numerics underneath, the result has to be the
+reference's bit for bit.  tests/test_model_gpu.py repeats the comparison with the real engine."""
+import numpy as np
+import pytest
+
+from golden_util import load
+
+
+@pytest.fixture()
+def patched_model(monkeypatch, oracle):
+    import oracle_engine
+    from lsml_b200.core import model as M
+    monkeypatch.setattr(M, "BandEngine", oracle_engine.OracleEngine)
+    monkeypatch.setattr(M, "_ball_u0", oracle_engine.ball_u0)
+    monkeypatch.setattr(M, "overlap_scores", oracle_engine.overlap_scores)
+    monkeypatch.setattr(M.LevelSetMachineLearning, "_device_model",
+                        lambda self, i, device: self.regression_models[i])
+    return M
+
+
+def reference_features():
+    from lsml_b200.feature import (DistanceToCenterOfMass, Moments, Size, get_basic_image_features)
+    return (get_basic_image_features(ndim=2, sigmas=[0, 2]) +
+            [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
+
+
+@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5)])
+def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
+    from sklearn.linear_model import LinearRegression
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from lsml_b200.initializer import BallInitializer
+    g = load("fit.npz")
+    imgs, segs = g["imgs"], g["segs"]
+    model = patched_model.LevelSetMachineLearning(reference_features(), BallInitializer(radius=6), band=3)
+    model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
+              random_state=np.random.RandomState(seed), regression_model_class=Pipeline,
+              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', LinearRegression())]),
+              balance_regression_targets=balance, validation_history_len=4,
+              validation_history_tol=-1.0, device="cpu")
+    for key in ("training", "validation", "testing"):
+        assert list(model._split[key]) == list(g["%s_%s_idx" % (tag, key)])
+    assert model.step == float(g[tag + "_step"])
+    assert model.iteration == int(g[tag + "_iterations"])
+    for i in range(1, model.iteration + 1):
+        reg = model.regression_model(i)
+        assert np.array_equal(reg.steps[0][1].mean_, g["%s_mean_%d" % (tag, i)]), i
+        assert np.array_equal(reg.steps[0][1].scale_, g["%s_scale_%d" % (tag, i)]), i
+        assert np.array_equal(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)]), i
+        assert np.array_equal(reg.steps[1][1].intercept_, g["%s_intercept_%d" % (tag, i)]), i
+    assert np.array_equal(model.training_scores, g[tag + "_training_scores"])
+    assert np.array_equal(model.validation_scores, g[tag + "_validation_scores"])
+    assert np.array_equal(model.testing_scores, g[tag + "_testing_scores"])
+    us = model.segment(imgs[14], verbose=False, iterate_until_validation_max=False, device="cpu")
+    assert np.array_equal(us, g[tag + "_us"])
+    us = model.segment(imgs[14], verbose=False, device="cpu")
+    assert np.array_equal(us, g[tag + "_us_valmax"])
