@@ -124,18 +124,25 @@ def gen_fit():
              [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
     out = {"imgs": imgs, "segs": segs}
     cwd = os.getcwd()
-    for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5)):
+    from sklearn.ensemble import RandomForestRegressor
+    out["probe"] = np.random.RandomState(0).randn(64, 14) * np.r_[[1.0] * 8, 5, 20, 10, 20, 10, 100]
+    for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5), ("forest", True, 9)):
         fake_h5py.reset()
         tmp = tempfile.mkdtemp()
         os.chdir(tmp)
         try:
             model = lsml.LevelSetMachineLearning(features=feats, initializer=BallInitializer(radius=6),
                                                  band=3)
+            rs = np.random.RandomState(seed)
+            if tag == "forest":      # the SAME RandomState for fit() and the forest, as in
+                final = RandomForestRegressor(n_estimators=10, max_samples=200,   # examples/*/main.py
+                                              random_state=rs)
+            else:
+                final = LinearRegression()
             model.fit('dataset.h5', imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
-                      random_state=np.random.RandomState(seed),
+                      random_state=rs,
                       regression_model_class=Pipeline,
-                      regression_model_kwargs=dict(steps=[('s', StandardScaler()),
-                                                          ('r', LinearRegression())]),
+                      regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
                       balance_regression_targets=balance, temp_data_dir=tmp,
                       save_filename=os.path.join(tmp, 'm.pkl'), redirect_stdout_to_logfile=False,
                       validation_history_len=4, validation_history_tol=-1.0)
@@ -152,8 +159,11 @@ def gen_fit():
                 reg = model.regression_model(i)
                 out["%s_mean_%d" % (tag, i)] = reg.steps[0][1].mean_
                 out["%s_scale_%d" % (tag, i)] = reg.steps[0][1].scale_
-                out["%s_coef_%d" % (tag, i)] = reg.steps[1][1].coef_
-                out["%s_intercept_%d" % (tag, i)] = np.asarray(reg.steps[1][1].intercept_)
+                out["%s_probe_%d" % (tag, i)] = reg.predict(out["probe"])
+                if tag != "forest":
+                    out["%s_coef_%d" % (tag, i)] = reg.steps[1][1].coef_
+                    out["%s_intercept_%d" % (tag, i)] = np.asarray(reg.steps[1][1].intercept_)
+            out["%s_rng_after" % tag] = rs.randint(1 << 30)          # the caller's stream afterwards
             out["%s_us" % tag] = model.segment(imgs[14], verbose=False,
                                                iterate_until_validation_max=False)
             out["%s_us_valmax" % tag] = model.segment(imgs[14], verbose=False)
@@ -163,7 +173,8 @@ def gen_fit():
                         notes="the reference's own fit() (in-memory h5py stand-in, skfmm plugged by "
                               "the oracle): split, auto step, scores, per-iteration StandardScaler+"
                               "LinearRegression parameters, segment() of a held-out image; "
-                              "random_state seeds 77 (balanced targets) and 5 (not balanced), "
+                              "random_state seeds 77 (balanced targets) and 5 (not balanced), 9 (a "
+                              "10-tree forest sharing fit()'s RandomState), "
                               "14 training images 41x41, BallInitializer(radius=6), band 3, "
                               "max_iters 7, validation_history_len 4, tol -1 (never exits early)",
                         **out)

@@ -9,8 +9,10 @@ from golden_util import load
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5)])
+@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
+                                              ("forest", True, 9)])
 def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
+    from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
     from sklearn.pipeline import Pipeline
     from sklearn.preprocessing import StandardScaler
@@ -22,11 +24,15 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
     feats = (get_basic_image_features(ndim=2, sigmas=[0, 2]) +
              [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
     model = LevelSetMachineLearning(feats, BallInitializer(radius=6), band=3)
+    rs = np.random.RandomState(seed)
+    final = (RandomForestRegressor(n_estimators=10, max_samples=200, random_state=rs)
+             if tag == "forest" else LinearRegression())
     model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
-              random_state=np.random.RandomState(seed), regression_model_class=Pipeline,
-              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', LinearRegression())]),
+              random_state=rs, regression_model_class=Pipeline,
+              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
               balance_regression_targets=balance, validation_history_len=4,
               validation_history_tol=-1.0)
+    assert rs.randint(1 << 30) == int(g[tag + "_rng_after"])
     for key in ("training", "validation", "testing"):
         assert list(model._split[key]) == list(g["%s_%s_idx" % (tag, key)])
     assert model.step == float(g[tag + "_step"])            # max |ground-truth distance| on the band
@@ -37,7 +43,9 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
         # order); least squares amplifies that by its conditioning
         assert np.allclose(reg.steps[0][1].mean_, g["%s_mean_%d" % (tag, i)], rtol=1e-9, atol=1e-12), i
         assert np.allclose(reg.steps[0][1].scale_, g["%s_scale_%d" % (tag, i)], rtol=1e-9, atol=1e-12), i
-        assert np.allclose(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)], rtol=1e-5, atol=1e-7), i
+        assert np.allclose(reg.predict(g["probe"]), g["%s_probe_%d" % (tag, i)], rtol=1e-5, atol=1e-6), i
+        if tag != "forest":
+            assert np.allclose(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)], rtol=1e-5, atol=1e-7), i
     for key in ("training", "validation", "testing"):
         assert np.allclose(getattr(model, key + "_scores"), g["%s_%s_scores" % (tag, key)],
                            rtol=0, atol=1e-9), key

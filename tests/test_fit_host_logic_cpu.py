@@ -32,8 +32,10 @@ def reference_features():
             [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
 
 
-@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5)])
+@pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
+                                              ("forest", True, 9)])
 def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
+    from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
     from sklearn.pipeline import Pipeline
     from sklearn.preprocessing import StandardScaler
@@ -41,11 +43,17 @@ def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     g = load("fit.npz")
     imgs, segs = g["imgs"], g["segs"]
     model = patched_model.LevelSetMachineLearning(reference_features(), BallInitializer(radius=6), band=3)
+    rs = np.random.RandomState(seed)
+    # "forest": ONE RandomState for fit() and for the forest, as the reference's examples do; the
+    # reference fits in a forked child, so the forest never advances the caller's stream
+    final = (RandomForestRegressor(n_estimators=10, max_samples=200, random_state=rs)
+             if tag == "forest" else LinearRegression())
     model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
-              random_state=np.random.RandomState(seed), regression_model_class=Pipeline,
-              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', LinearRegression())]),
+              random_state=rs, regression_model_class=Pipeline,
+              regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
               balance_regression_targets=balance, validation_history_len=4,
               validation_history_tol=-1.0, device="cpu")
+    assert rs.randint(1 << 30) == int(g[tag + "_rng_after"])
     for key in ("training", "validation", "testing"):
         assert list(model._split[key]) == list(g["%s_%s_idx" % (tag, key)])
     assert model.step == float(g[tag + "_step"])
@@ -54,8 +62,10 @@ def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
         reg = model.regression_model(i)
         assert np.array_equal(reg.steps[0][1].mean_, g["%s_mean_%d" % (tag, i)]), i
         assert np.array_equal(reg.steps[0][1].scale_, g["%s_scale_%d" % (tag, i)]), i
-        assert np.array_equal(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)]), i
-        assert np.array_equal(reg.steps[1][1].intercept_, g["%s_intercept_%d" % (tag, i)]), i
+        assert np.array_equal(reg.predict(g["probe"]), g["%s_probe_%d" % (tag, i)]), i
+        if tag != "forest":
+            assert np.array_equal(reg.steps[1][1].coef_, g["%s_coef_%d" % (tag, i)]), i
+            assert np.array_equal(reg.steps[1][1].intercept_, g["%s_intercept_%d" % (tag, i)]), i
     assert np.array_equal(model.training_scores, g[tag + "_training_scores"])
     assert np.array_equal(model.validation_scores, g[tag + "_validation_scores"])
     assert np.array_equal(model.testing_scores, g[tag + "_testing_scores"])
