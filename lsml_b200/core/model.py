@@ -23,6 +23,7 @@ from .. import _lib
 from ..feature.feature_map import FeatureMap
 from ..initializer.initializer_base import InitializerBase
 from ..initializer.provided import BallInitializer
+from ..initializer.seed import center_of_mass_seeder
 from ..score_functions import jaccard
 from .engine import BandEngine
 from .regressors import export_regressor
@@ -162,7 +163,8 @@ class LevelSetMachineLearning:
     # ------------------------------------------------------------------ fit
     def fit(self, data_filename=None, regression_model_class=None, regression_model_kwargs=None,
             balance_regression_targets=True, datasets_split=(0.6, 0.2, 0.2), dx=None, imgs=None,
-            max_iters=100, random_state=None, save_filename=None, seeds=None, segs=None,
+            max_iters=100, random_state=None, save_filename=None, seeds=center_of_mass_seeder,
+            segs=None,
             step=None, subset_size=None, temp_data_dir=None, validation_history_len=5,
             validation_history_tol=0.0, redirect_stdout_to_logfile=False, device="cuda",
             verbose=False):

@@ -126,13 +126,30 @@ def gen_fit():
     cwd = os.getcwd()
     from sklearn.ensemble import RandomForestRegressor
     out["probe"] = np.random.RandomState(0).randn(64, 14) * np.r_[[1.0] * 8, 5, 20, 10, 20, 10, 100]
-    for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5), ("forest", True, 9)):
+    from lsml.initializer.initializer_base import InitializerBase
+
+    def seed_ball_initialize(self, img, dx, seed):
+        ind = np.indices(img.shape, dtype=float)
+        for a in range(img.ndim):
+            ind[a] = ind[a] * dx[a] - seed[a]
+        return np.sqrt((ind ** 2).sum(axis=0)) < 5.0
+
+    # A user initializer that runs on the host and USES the seed (default seeds =
+    # center_of_mass_seeder, model.py:107): a ball of radius 5 around it.  Module-level so that
+    # the reference can pickle the model; the same class is defined on lsml_b200's
+    # InitializerBase in tests/test_fit_host_logic_cpu.py.
+    global SeedBall
+    SeedBall = type("SeedBall", (InitializerBase,), {"initialize": seed_ball_initialize,
+                                                     "__module__": __name__})
+
+    for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5), ("forest", True, 9),
+                               ("seedball", True, 21)):
         fake_h5py.reset()
         tmp = tempfile.mkdtemp()
         os.chdir(tmp)
         try:
-            model = lsml.LevelSetMachineLearning(features=feats, initializer=BallInitializer(radius=6),
-                                                 band=3)
+            init = SeedBall() if tag == "seedball" else BallInitializer(radius=6)
+            model = lsml.LevelSetMachineLearning(features=feats, initializer=init, band=3)
             rs = np.random.RandomState(seed)
             if tag == "forest":      # the SAME RandomState for fit() and the forest, as in
                 final = RandomForestRegressor(n_estimators=10, max_samples=200,   # examples/*/main.py

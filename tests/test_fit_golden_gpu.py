@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
-                                              ("forest", True, 9)])
+                                              ("forest", True, 9), ("seedball", True, 21)])
 def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
     from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
@@ -23,7 +23,9 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
     imgs, segs = g["imgs"], g["segs"]
     feats = (get_basic_image_features(ndim=2, sigmas=[0, 2]) +
              [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
-    model = LevelSetMachineLearning(feats, BallInitializer(radius=6), band=3)
+    from test_fit_host_logic_cpu import seed_ball_initializer
+    init = seed_ball_initializer() if tag == "seedball" else BallInitializer(radius=6)
+    model = LevelSetMachineLearning(feats, init, band=3)
     rs = np.random.RandomState(seed)
     final = (RandomForestRegressor(n_estimators=10, max_samples=200, random_state=rs)
              if tag == "forest" else LinearRegression())

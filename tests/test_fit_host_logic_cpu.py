@@ -32,8 +32,23 @@ def reference_features():
             [DistanceToCenterOfMass(ndim=2), Moments(ndim=2), Size(ndim=2)])
 
 
+def seed_ball_initializer():
+    """The user initializer of the `seedball` golden case (oracle/gen_golden.py:gen_fit): runs on
+    the host and USES the seed, which defaults to the centre of mass of the segmentation."""
+    from lsml_b200.initializer import InitializerBase
+
+    class SeedBall(InitializerBase):
+        def initialize(self, img, dx, seed):
+            ind = np.indices(img.shape, dtype=float)
+            for a in range(img.ndim):
+                ind[a] = ind[a] * dx[a] - seed[a]
+            return np.sqrt((ind ** 2).sum(axis=0)) < 5.0
+
+    return SeedBall()
+
+
 @pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
-                                              ("forest", True, 9)])
+                                              ("forest", True, 9), ("seedball", True, 21)])
 def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
@@ -42,7 +57,8 @@ def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     from lsml_b200.initializer import BallInitializer
     g = load("fit.npz")
     imgs, segs = g["imgs"], g["segs"]
-    model = patched_model.LevelSetMachineLearning(reference_features(), BallInitializer(radius=6), band=3)
+    init = seed_ball_initializer() if tag == "seedball" else BallInitializer(radius=6)
+    model = patched_model.LevelSetMachineLearning(reference_features(), init, band=3)
     rs = np.random.RandomState(seed)
     # "forest": ONE RandomState for fit() and for the forest, as the reference's examples do; the
     # reference fits in a forked child, so the forest never advances the caller's stream
