@@ -181,6 +181,32 @@ class LevelSetMachineLearning:
             raise ValueError("`regression_model_class` is required")
         kwargs = dict(regression_model_kwargs or {})
         rs = random_state if random_state is not None else numpy.random.RandomState()
+        # input validation of datasets_handler.py:131-170 (same exceptions and messages)
+        if len(imgs) != len(segs):
+            msg = "Mismatch in number of examples: imgs ({}), segs ({})"
+            raise ValueError(msg.format(len(imgs), len(segs)))
+        ndim_ = numpy.ndim(imgs[0])
+        for i, (img, seg) in enumerate(zip(imgs, segs)):
+            if img.dtype != float:
+                raise TypeError("imgs[{}] (dtype {}) was not float".format(i, img.dtype))
+            if seg.dtype != bool:
+                raise TypeError("seg[{}] (dtype {}) was not bool".format(i, seg.dtype))
+            if img.ndim != ndim_:
+                msg = "imgs[{}] (ndim={}) did not have correct dimensions ({})"
+                raise ValueError(msg.format(i, img.ndim, ndim_))
+            if seg.ndim != ndim_:
+                msg = "segs[{}] (ndim={}) did not have correct dimensions ({})"
+                raise ValueError(msg.format(i, seg.ndim, ndim_))
+            if img.shape != seg.shape:
+                msg = "imgs[{}] shape {} does not match segs[{}] shape {}"
+                raise ValueError(msg.format(i, img.shape, i, seg.shape))
+        if dx is not None and numpy.ndim(dx) == 2 and numpy.shape(dx) != (len(imgs), ndim_):
+            msg = "`dx` was shape {} but should be shape {}"
+            raise ValueError(msg.format(numpy.shape(dx), (len(imgs), ndim_)))
+        if len({numpy.shape(i) for i in imgs}) != 1:
+            raise NotImplementedError(
+                "lsml_b200.fit keeps all examples in one device batch: the images must share "
+                "one shape (the reference stores them one by one in HDF5)")
         imgs = numpy.ascontiguousarray(numpy.stack([numpy.asarray(i, dtype=float) for i in imgs]))
         segs = numpy.ascontiguousarray(numpy.stack([numpy.asarray(s, dtype=bool) for s in segs]))
         n, shape = imgs.shape[0], imgs.shape[1:]

@@ -142,8 +142,9 @@ def gen_fit():
     SeedBall = type("SeedBall", (InitializerBase,), {"initialize": seed_ball_initialize,
                                                      "__module__": __name__})
 
+    out["aniso_dx"] = np.array([1.0, 0.5])
     for tag, balance, seed in (("bal", True, 77), ("nobal", False, 5), ("forest", True, 9),
-                               ("seedball", True, 21)):
+                               ("seedball", True, 21), ("aniso", True, 33)):
         fake_h5py.reset()
         tmp = tempfile.mkdtemp()
         os.chdir(tmp)
@@ -160,6 +161,7 @@ def gen_fit():
                       random_state=rs,
                       regression_model_class=Pipeline,
                       regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
+                      dx=(np.tile(out["aniso_dx"], (14, 1)) if tag == "aniso" else None),
                       balance_regression_targets=balance, temp_data_dir=tmp,
                       save_filename=os.path.join(tmp, 'm.pkl'), redirect_stdout_to_logfile=False,
                       validation_history_len=4, validation_history_tol=-1.0)
@@ -181,9 +183,10 @@ def gen_fit():
                     out["%s_coef_%d" % (tag, i)] = reg.steps[1][1].coef_
                     out["%s_intercept_%d" % (tag, i)] = np.asarray(reg.steps[1][1].intercept_)
             out["%s_rng_after" % tag] = rs.randint(1 << 30)          # the caller's stream afterwards
-            out["%s_us" % tag] = model.segment(imgs[14], verbose=False,
+            sdx = out["aniso_dx"] if tag == "aniso" else None
+            out["%s_us" % tag] = model.segment(imgs[14], dx=sdx, verbose=False,
                                                iterate_until_validation_max=False)
-            out["%s_us_valmax" % tag] = model.segment(imgs[14], verbose=False)
+            out["%s_us_valmax" % tag] = model.segment(imgs[14], dx=sdx, verbose=False)
         finally:
             os.chdir(cwd)
     np.savez_compressed(os.path.join(OUT, "fit.npz"),

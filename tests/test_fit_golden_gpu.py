@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
-                                              ("forest", True, 9), ("seedball", True, 21)])
+                                              ("forest", True, 9), ("seedball", True, 21),
+                                              ("aniso", True, 33)])
 def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
     from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
@@ -32,6 +33,7 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
     model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
               random_state=rs, regression_model_class=Pipeline,
               regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
+              dx=(np.tile(g["aniso_dx"], (14, 1)) if tag == "aniso" else None),
               balance_regression_targets=balance, validation_history_len=4,
               validation_history_tol=-1.0)
     assert rs.randint(1 << 30) == int(g[tag + "_rng_after"])
@@ -52,7 +54,8 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
         assert np.allclose(getattr(model, key + "_scores"), g["%s_%s_scores" % (tag, key)],
                            rtol=0, atol=1e-9), key
     for flag, name in ((False, "_us"), (True, "_us_valmax")):
-        us = model.segment(imgs[14], verbose=False, iterate_until_validation_max=flag)
+        us = model.segment(imgs[14], dx=(g["aniso_dx"] if tag == "aniso" else None), verbose=False,
+                           iterate_until_validation_max=flag)
         want = g[tag + name]
         assert us.shape == want.shape
         for i in range(us.shape[0]):

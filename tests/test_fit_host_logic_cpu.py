@@ -48,7 +48,8 @@ def seed_ball_initializer():
 
 
 @pytest.mark.parametrize("tag,balance,seed", [("bal", True, 77), ("nobal", False, 5),
-                                              ("forest", True, 9), ("seedball", True, 21)])
+                                              ("forest", True, 9), ("seedball", True, 21),
+                                              ("aniso", True, 33)])
 def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     from sklearn.ensemble import RandomForestRegressor
     from sklearn.linear_model import LinearRegression
@@ -67,6 +68,7 @@ def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     model.fit(imgs=list(imgs[:14]), segs=list(segs[:14]), max_iters=7,
               random_state=rs, regression_model_class=Pipeline,
               regression_model_kwargs=dict(steps=[('s', StandardScaler()), ('r', final)]),
+              dx=(np.tile(g["aniso_dx"], (14, 1)) if tag == "aniso" else None),
               balance_regression_targets=balance, validation_history_len=4,
               validation_history_tol=-1.0, device="cpu")
     assert rs.randint(1 << 30) == int(g[tag + "_rng_after"])
@@ -85,7 +87,36 @@ def test_fit_reproduces_the_references_fit(patched_model, tag, balance, seed):
     assert np.array_equal(model.training_scores, g[tag + "_training_scores"])
     assert np.array_equal(model.validation_scores, g[tag + "_validation_scores"])
     assert np.array_equal(model.testing_scores, g[tag + "_testing_scores"])
-    us = model.segment(imgs[14], verbose=False, iterate_until_validation_max=False, device="cpu")
+    sdx = g["aniso_dx"] if tag == "aniso" else None
+    us = model.segment(imgs[14], dx=sdx, verbose=False, iterate_until_validation_max=False, device="cpu")
     assert np.array_equal(us, g[tag + "_us"])
-    us = model.segment(imgs[14], verbose=False, device="cpu")
+    us = model.segment(imgs[14], dx=sdx, verbose=False, device="cpu")
     assert np.array_equal(us, g[tag + "_us_valmax"])
+
+
+def test_fit_input_validation_as_the_reference(patched_model):
+    """datasets_handler.py:131-170: same exception types for bad `imgs` / `segs` / `dx`."""
+    from sklearn.linear_model import LinearRegression
+    from lsml_b200.initializer import BallInitializer
+    M = patched_model
+    img, seg = np.zeros((8, 9)), np.zeros((8, 9), dtype=bool)
+
+    def fit(imgs, segs, **kw):
+        M.LevelSetMachineLearning(reference_features(), BallInitializer(radius=2)).fit(
+            imgs=imgs, segs=segs, regression_model_class=LinearRegression,
+            random_state=np.random.RandomState(0), device="cpu", **kw)
+
+    with pytest.raises(ValueError):
+        fit([img, img], [seg])
+    with pytest.raises(TypeError):
+        fit([img.astype(np.float32)], [seg])
+    with pytest.raises(TypeError):
+        fit([img], [seg.astype(np.uint8)])
+    with pytest.raises(ValueError):
+        fit([img, np.zeros((8, 9, 2))], [seg, np.zeros((8, 9, 2), dtype=bool)])
+    with pytest.raises(ValueError):
+        fit([img], [np.zeros((8, 8), dtype=bool)])
+    with pytest.raises(ValueError):
+        fit([img, img], [seg, seg], dx=np.ones((3, 2)))
+    with pytest.raises(NotImplementedError):      # the one deliberate restriction
+        fit([img, np.zeros((9, 9))], [seg, np.zeros((9, 9), dtype=bool)])
