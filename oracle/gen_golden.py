@@ -201,7 +201,70 @@ def gen_fit():
     print("fit.npz", os.path.getsize(os.path.join(OUT, "fit.npz")))
 
 
+def gen_fit3d():
+    """tests/golden/fit3d.npz: the reference's own fit() + segment() on small 3-D volumes
+    (lsml/data/dim3/hamburger.py), tree-ensemble velocity -- the C3 workload family end to end."""
+    import tempfile
+    warnings.simplefilter("ignore")
+    from oracle import oracle as O
+    from oracle import fake_h5py
+    from oracle.ref_shim import import_reference
+    O.build()
+    lsml = import_reference(skfmm_distance=O.skfmm_distance)
+    from lsml.feature import (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                              InteriorImageVariation, Size, Moments, DistanceToCenterOfMass)
+    from lsml.initializer import BallInitializer
+    from lsml.data.dim3 import hamburger
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    imgs, segs = hamburger.make_dataset(N=9, n=25, rad=[6, 9], rs=np.random.RandomState(8),
+                                        verbose=False)
+    imgs, segs = np.asarray(imgs, dtype=float), np.asarray(segs, dtype=bool)
+    feats = ([cls(ndim=3, sigma=s) for cls in (ImageSample, ImageEdgeSample, InteriorImageAverage,
+                                               InteriorImageVariation) for s in (0, 1.5)] +
+             [DistanceToCenterOfMass(ndim=3), Moments(ndim=3, axes=(0, 1, 2), orders=(1, 2)),
+              Size(ndim=3)])
+    out = {"imgs": imgs, "segs": segs,
+           "probe": np.random.RandomState(0).randn(64, 16) * np.r_[[1.0] * 8, 4, [12, 6] * 3, 300]}
+    cwd = os.getcwd()
+    fake_h5py.reset()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+    try:
+        rs = np.random.RandomState(12)
+        model = lsml.LevelSetMachineLearning(features=feats, initializer=BallInitializer(radius=4),
+                                             band=3)
+        model.fit('dataset.h5', imgs=list(imgs[:8]), segs=list(segs[:8]), max_iters=5,
+                  random_state=rs, regression_model_class=Pipeline,
+                  regression_model_kwargs=dict(steps=[
+                      ('s', StandardScaler()),
+                      ('r', RandomForestRegressor(n_estimators=12, max_samples=300, random_state=rs))]),
+                  datasets_split=([0, 1, 2, 3, 4], [5, 6], [7]), temp_data_dir=tmp,
+                  save_filename=os.path.join(tmp, 'm.pkl'), redirect_stdout_to_logfile=False,
+                  validation_history_len=3, validation_history_tol=-1.0)
+        fj = model.fit_job_handler
+        out["step"] = float(model.step)
+        out["iterations"] = int(fj.iteration)
+        for key in ("training", "validation", "testing"):
+            out[key + "_scores"] = np.asarray(getattr(model, key + "_scores"))
+        for i in range(1, fj.iteration + 1):
+            out["probe_%d" % i] = model.regression_model(i).predict(out["probe"])
+        out["rng_after"] = rs.randint(1 << 30)
+        out["us"] = model.segment(imgs[8], verbose=False, iterate_until_validation_max=False)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "fit3d.npz"),
+                        notes="the reference's own fit() on 8 volumes 25^3 (explicit split 5/2/1), "
+                              "F = 16, StandardScaler + 12-tree forest sharing fit()'s RandomState(12), "
+                              "BallInitializer(radius=4), band 3, 5 iterations; segment() of a 9th "
+                              "volume; h5py stand-in, skfmm plugged by the oracle", **out)
+    print("fit3d.npz", os.path.getsize(os.path.join(OUT, "fit3d.npz")))
+
+
 def main():
+    if sys.argv[1:] == ["fit3d"]:
+        return gen_fit3d()
     if sys.argv[1:] == ["fit"]:
         return gen_fit()
     if sys.argv[1:] == ["com_ray"]:       # regenerate that fixture only
@@ -366,6 +429,7 @@ def main():
     gen_com_ray()
     gen_prev_iter()
     gen_fit()
+    gen_fit3d()
     for name in sorted(os.listdir(OUT)):
         print(name, os.path.getsize(os.path.join(OUT, name)))
 

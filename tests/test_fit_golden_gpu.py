@@ -61,3 +61,24 @@ def test_fit_reproduces_the_references_fit_on_device(tag, balance, seed):
         for i in range(us.shape[0]):
             assert np.array_equal(us[i] > 0, want[i] > 0), i
             assert np.allclose(us[i], want[i], rtol=1e-5, atol=1e-8), np.abs(us[i] - want[i]).max()
+
+
+def test_fit_3d_reproduces_the_references_fit_on_device():
+    """8 volumes 25^3, F = 16, 12-tree forest: the C3 workload family end to end (fit3d.npz)."""
+    from lsml_b200.core import model as M
+    from test_fit_host_logic_cpu import fit3d_model
+    g = load("fit3d.npz")
+    model, rs = fit3d_model(M, g, "cuda")
+    assert rs.randint(1 << 30) == int(g["rng_after"])
+    assert model.step == float(g["step"]) and model.iteration == int(g["iterations"])
+    for i in range(1, model.iteration + 1):
+        assert np.allclose(model.regression_model(i).predict(g["probe"]), g["probe_%d" % i],
+                           rtol=1e-5, atol=1e-6), i
+    for key in ("training", "validation", "testing"):
+        assert np.allclose(getattr(model, key + "_scores"), g[key + "_scores"], rtol=0, atol=1e-9)
+    us = model.segment(g["imgs"][8], verbose=False, iterate_until_validation_max=False)
+    want = g["us"]
+    assert us.shape == want.shape
+    for i in range(us.shape[0]):
+        assert np.array_equal(us[i] > 0, want[i] > 0), i
+        assert np.allclose(us[i], want[i], rtol=1e-5, atol=1e-8), np.abs(us[i] - want[i]).max()

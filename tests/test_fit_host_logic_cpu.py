@@ -120,3 +120,38 @@ def test_fit_input_validation_as_the_reference(patched_model):
         fit([img, img], [seg, seg], dx=np.ones((3, 2)))
     with pytest.raises(NotImplementedError):      # the one deliberate restriction
         fit([img, np.zeros((9, 9))], [seg, np.zeros((9, 9), dtype=bool)])
+
+
+def fit3d_model(M, g, device):
+    """The 3-D golden case (oracle/gen_golden.py:gen_fit3d) through `M.LevelSetMachineLearning`."""
+    from sklearn.ensemble import RandomForestRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from lsml_b200.feature import (DistanceToCenterOfMass, Moments, Size, get_basic_image_features)
+    from lsml_b200.initializer import BallInitializer
+    feats = (get_basic_image_features(ndim=3, sigmas=[0, 1.5]) +
+             [DistanceToCenterOfMass(ndim=3), Moments(ndim=3, axes=(0, 1, 2), orders=(1, 2)),
+              Size(ndim=3)])
+    rs = np.random.RandomState(12)
+    model = M.LevelSetMachineLearning(feats, BallInitializer(radius=4), band=3)
+    model.fit(imgs=list(g["imgs"][:8]), segs=list(g["segs"][:8]), max_iters=5, random_state=rs,
+              regression_model_class=Pipeline,
+              regression_model_kwargs=dict(steps=[
+                  ('s', StandardScaler()),
+                  ('r', RandomForestRegressor(n_estimators=12, max_samples=300, random_state=rs))]),
+              datasets_split=([0, 1, 2, 3, 4], [5, 6], [7]), validation_history_len=3,
+              validation_history_tol=-1.0, device=device)
+    return model, rs
+
+
+def test_fit_3d_reproduces_the_references_fit(patched_model):
+    g = load("fit3d.npz")
+    model, rs = fit3d_model(patched_model, g, "cpu")
+    assert rs.randint(1 << 30) == int(g["rng_after"])
+    assert model.step == float(g["step"]) and model.iteration == int(g["iterations"])
+    for i in range(1, model.iteration + 1):
+        assert np.array_equal(model.regression_model(i).predict(g["probe"]), g["probe_%d" % i]), i
+    for key in ("training", "validation", "testing"):
+        assert np.array_equal(getattr(model, key + "_scores"), g[key + "_scores"])
+    us = model.segment(g["imgs"][8], verbose=False, iterate_until_validation_max=False, device="cpu")
+    assert np.array_equal(us, g["us"])
