@@ -286,6 +286,8 @@ contour_length_kernel(const double* __restrict__ u, int m, int n, double sr, dou
     if (threadIdx.x == 0) partial[(i64)item * gridDim.x + blockIdx.x] = t;
 }
 
+// [host-test:begin] (tests/test_feature_kernels_host.py compiles this region with g++: the two
+// kernels below have no block-level cooperation, so one host "thread" can run them as they are)
 // ---------------------------------------------------------------------------------------------
 // per-item ("global") feature values
 // ---------------------------------------------------------------------------------------------
@@ -416,6 +418,7 @@ assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
         X[t] = v;
     }
 }
+// [host-test:end]
 
 // ---------------------------------------------------------------------------------------------
 // host launchers

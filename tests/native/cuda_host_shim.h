@@ -24,3 +24,9 @@ static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 using std::max;
 using std::min;
+
+// ---- kernels without block-level cooperation run as plain functions on one host "thread" ----
+#define __global__
+#define __launch_bounds__(...)
+struct HostDim3 { unsigned x, y, z; };
+static HostDim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
