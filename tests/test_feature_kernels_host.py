@@ -122,3 +122,24 @@ def test_feature_program_on_a_batch_against_oracle(oracle, host_lib):
         assert np.array_equal(got[:, 1 + 2 * n_samples], want[:, 1 + 2 * n_samples])   # dist to COM
         assert np.allclose(got, want, rtol=1e-12, atol=1e-13)                 # moments: sum order
     assert row == X.shape[0]
+
+
+def test_reference_com_ray_test_through_the_kernel_source(oracle, host_lib):
+    """lsml/feature/provided/test/test_image.py:159-189 (non-dyadic dx, a single band voxel) on
+    the kernels' source: what tests/test_reference_suite.py asserts on the GPU."""
+    x, dx = np.linspace(-2, 2, 301, retstep=True)
+    y, dy = np.linspace(-2, 2, 201, retstep=True)
+    xx, yy = np.meshgrid(x, y)
+    img = 1 - np.sqrt(xx ** 2 + yy ** 2)
+    mask = abs(img) < 0.01
+    ii, jj = np.where(mask)
+    mask[ii[1:], jj[1:]] = False
+    X = run_feature_kernels(host_lib, oracle, [("com_ray", 10)], img[None], img[None], mask[None],
+                            np.array([dy, dx]))
+    samples = X[0]
+    _, dt = np.linspace(-1, 1, 22, retstep=True)
+    ds = np.diff(samples)
+    assert round(abs(ds.var()), 10) == 0
+    assert round(abs((ds / dt).mean() - 1), 1) == 0
+    want = oracle.feature_matrix([("com_ray", 10)], img, img, None, mask, np.array([dy, dx]))
+    assert np.allclose(X, want, rtol=1e-12, atol=1e-13)
