@@ -80,6 +80,7 @@ static int make_fmm_geom(const Geom& g, FmmGeom& fg) {
     return 0;
 }
 
+// [host-sched:begin] (tests/test_fmm_scheduler_host.py: the scheduler's device functions on one host thread)
 struct FmmCounters {      // device-resident
     i64 n_init;           // initial frozen voxels: list[0 .. n_init)
     i64 n_cand;           // candidates: list[cap-1 .. cap-n_cand] (growing downwards)
@@ -107,6 +108,7 @@ struct FmmCounters {      // device-resident
     i64 sizes[32];        // work-set size of the first 32 grid-wide sweeps (diagnostic)
     i64 stamps[32];       // %globaltimer (ns) at the start of those sweeps (diagnostic)
 };
+// [host-sched:end]
 
 // [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 // Ordering decisions are made on |d| rounded to float32 (see oracle/lsml_oracle.c:qmag): values
@@ -122,6 +124,7 @@ constexpr u8 ST_INIT = 1, ST_CAND = 2;
 constexpr unsigned MAX_LEVEL = 63u;
 // [host-test:end]
 
+// [host-sched:begin] (tests/test_fmm_scheduler_host.py: the scheduler's device functions on one host thread)
 // claim voxel g (state 0 -> `value`); returns true for the single winner.  The state is one
 // byte of a 32-bit word; atomicOr on the word keeps the other three bytes intact.
 __device__ __forceinline__ bool claim(u8* mask, i64 g, unsigned value) {
@@ -203,6 +206,8 @@ fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__
     }
 }
 
+// [host-sched:end]
+
 // Start of a rebuild (one CTA of 256 threads): reset the per-rebuild counters, advance the hint
 // generation, turn last rebuild's hint histogram into parking-bucket offsets.
 __global__ void __launch_bounds__(256)
@@ -270,6 +275,7 @@ __device__ __forceinline__ bool init_distance(const double* __restrict__ u, i64 
 }
 // [host-test:end]
 
+// [host-sched:begin] (tests/test_fmm_scheduler_host.py: the scheduler's device functions on one host thread)
 // Items that are single-signed (no positive or no non-positive... see distance_transform.py:42)
 // are left untouched => empty mask.  stats[item*8+0] = #(u>0), stats[item*8+7] = #(u==0).
 __device__ __forceinline__ bool item_has_contour(const u64* __restrict__ stats, i64 item,
@@ -476,6 +482,7 @@ fmm_seed_kernel(u8* mask, Aux* aux, i64* list, i64 cap, FmmGeom g, FmmCounters* 
         expose_neighbours<NDIM>(e, l, coord, g, mask, list, cap, sc);
     }
 }
+// [host-sched:end]
 
 // [host-test:begin] (tests/test_fmm_device_code_host.py compiles the marked regions with g++)
 // ---- the marcher's upwind update on a local stencil ------------------------------------------
@@ -742,6 +749,7 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
 }
 // [host-test:end]
 
+// [host-sched:begin] (tests/test_fmm_scheduler_host.py: the scheduler's device functions on one host thread)
 constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s at worst, then
                                           // `converged` = 0 is reported (never seen)
 // Sweeps per REBUILD, counting the single-CTA ones (a grid-wide step can hold 4096 of those, so
@@ -885,6 +893,8 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     publish_change<NDIM>(e, l, coord, fminf(qmag(old), qmag(nw)),
                          fabs(nw) <= band && !(fabs(old) <= band), g, mask, list, cap, sc);
 }
+
+// [host-sched:end]
 
 // Sweeps of the replay operator until no candidate is queued.  A candidate is queued when it is
 // created and whenever a stencil voxel within its reach changes value; the thread that queues
