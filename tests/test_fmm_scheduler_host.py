@@ -56,6 +56,10 @@ class HostScheduler:
     def set_gen(self, gen):
         self.lib.hs_set_gen(self.h, ctypes.c_longlong(gen))
 
+    def set_order(self, order):
+        """Evaluation order inside a sweep: 0 as queued, 1 reversed, 2 shuffled."""
+        self.lib.hs_set_order(self.h, ctypes.c_int(order))
+
     def rebuild(self, us, band, prev_band=None, allow_hints=1):
         us = np.ascontiguousarray(us, dtype=np.float64)
         stats = np.zeros((self.batch, 8), dtype=np.uint64)
@@ -102,6 +106,7 @@ def test_scheduler_source_reproduces_marcher_on_evolving_batches(oracle, sched_l
         band = float(rs.choice([2.0, 3.0, 4.5]))
         hs = HostScheduler(sched_lib, shape, batch, dx)
         hs.set_gen(int(rs.choice([0, 14, 120, 124, 250, 252, 380, 507])))     # tag wrap / wipes
+        hs.set_order(case % 3)              # the result may not depend on the order within a sweep
         us = _items(rs, shape, batch)
         if batch > 1 and case % 3 == 0:
             us[-1] = -1.0                           # an item without a contour stays untouched
