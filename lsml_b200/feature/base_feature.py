@@ -17,6 +17,17 @@ LOCAL_FEATURE_TYPE = 'local'
 GLOBAL_FEATURE_TYPE = 'global'
 
 
+def _require_array(value, var):
+    if not isinstance(value, numpy.ndarray):
+        raise TypeError("`{var}` must be a numpy array".format(var=var))
+
+
+def _require_shape(value, shape, var):
+    if value.shape != shape:
+        raise ValueError("`{var}` has shape {shape}, but must be shape {correct_shape}".format(
+            var=var, shape=value.shape, correct_shape=shape))
+
+
 class BaseFeature(abc.ABC):
     """ The abstract base class for all features (reference :13-139) """
 
@@ -61,52 +72,36 @@ class BaseFeature(abc.ABC):
                 self.name, type(self).__name__))
 
     def __call__(self, u, img=None, dist=None, mask=None, dx=None):
-        """ Validates the inputs (reference :67-139) and computes the feature on the GPU """
-        not_ndarray = "`{var}` must be a numpy array"
-        if not isinstance(u, numpy.ndarray):
-            raise TypeError(not_ndarray.format(var='u'))
-        shape = u.shape
-        shape_mismatch = ("`{{var}}` has shape {{shape}}, "
-                          "but must be shape {correct_shape}")
-        shape_mismatch = shape_mismatch.format(correct_shape=shape)
-
-        if isinstance(self, BaseImageFeature):
+        """ Validates the inputs in the reference's order and with its messages (reference
+        :67-139), then computes the feature on the GPU. """
+        _require_array(u, 'u')
+        image_feature = isinstance(self, BaseImageFeature)
+        if image_feature:
             if img is None:
                 raise ValueError("`img` must be present for image features")
-            if not isinstance(img, numpy.ndarray):
-                raise TypeError(not_ndarray.format(var='img'))
-            if img.shape != shape:
-                raise ValueError(shape_mismatch.format(var='img', shape=img.shape))
-
+            _require_array(img, 'img')
+            _require_shape(img, u.shape, 'img')
         if dist is not None:
-            if not isinstance(dist, numpy.ndarray):
-                raise TypeError(not_ndarray.format(var='dist'))
-            if dist.shape != shape:
-                raise ValueError(shape_mismatch.format(var='img', shape=dist.shape))
-
+            _require_array(dist, 'dist')
+            _require_shape(dist, u.shape, 'img')      # (the reference names `img` here too)
         if dx is None:
             dx = numpy.ones(self.ndim, dtype=float)
         else:
             dx = numpy.array(dx, dtype=float)
             if len(dx) != self.ndim:
-                msg = "Number of dx terms ({}) doesn't match dimensions ({})"
-                raise ValueError(msg.format(len(dx), self.ndim))
-
+                raise ValueError("Number of dx terms ({}) doesn't match dimensions ({})".format(
+                    len(dx), self.ndim))
         if mask is None:
-            mask = numpy.ones(shape, dtype=bool)
-        if not isinstance(mask, numpy.ndarray):
-            raise TypeError(not_ndarray.format(var='mask'))
-        if mask.shape != shape:
-            raise ValueError(shape_mismatch.format(var='mask', shape=mask.shape))
+            mask = numpy.ones(u.shape, dtype=bool)
+        _require_array(mask, 'mask')
+        _require_shape(mask, u.shape, 'mask')
         if mask.dtype != bool:
             raise TypeError("`mask` dtype ({}) was not of type bool".format(mask.dtype))
-
         if not mask.any():
             return numpy.empty(u.shape + (self.size,))
-
-        if isinstance(self, BaseImageFeature):
+        if image_feature:
             return self.compute_feature(u=u, img=img, dist=dist, mask=mask, dx=dx)
-        elif isinstance(self, BaseShapeFeature):
+        if isinstance(self, BaseShapeFeature):
             return self.compute_feature(u=u, dist=dist, mask=mask, dx=dx)
 
     def compute_feature(self, u, img=None, dist=None, mask=None, dx=None):

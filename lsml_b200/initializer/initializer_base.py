@@ -1,4 +1,9 @@
-"""InitializerBase -- mirror of lsml/initializer/initializer_base.py."""
+"""InitializerBase -- drop-in for lsml/initializer/initializer_base.py.
+
+A subclass provides ``initialize(img, dx, seed) -> bool ndarray``; calling the instance returns
+``(u0, dist, mask)`` with ``u0 = 2*init - 1`` and the narrow band of ``u0`` (reference :19-61; the
+band comes from the device marcher instead of scikit-fmm).  Argument handling and error messages
+are the reference's."""
 import abc
 
 import numpy
@@ -6,35 +11,39 @@ import numpy
 from ..util.distance_transform import distance_transform
 
 
+def _spacing(dx, ndim):
+    """``dx`` as a float vector of length ``ndim`` (ones when omitted)."""
+    if dx is None:
+        return numpy.ones(ndim, dtype=float)
+    dx = numpy.array(dx, dtype=float)
+    if len(dx) != ndim:
+        raise ValueError("Number of dx terms ({}) doesn't match dimensions ({})".format(len(dx), ndim))
+    return dx
+
+
+def _checked(init_mask, shape):
+    """The user's ``initialize`` result, validated like the reference (:41-53)."""
+    if not isinstance(init_mask, numpy.ndarray):
+        raise TypeError("Returned initializer was type {} but "
+                        "should be numpy.ndarray".format(type(init_mask)))
+    if init_mask.dtype != bool:
+        raise TypeError("Returned initializer was dtype {} but should be bool".format(init_mask.dtype))
+    if init_mask.shape != shape:
+        raise ValueError("Returned initializer was shape {} but should be {}".format(
+            init_mask.shape, shape))
+    return init_mask
+
+
 class InitializerBase(abc.ABC):
-    """ ``initializer(img, band, dx=, seed=) -> (u0, dist, mask)`` (reference :19-61) """
 
     def __init__(self):
         pass
 
     def __call__(self, img, band=0, dx=None, seed=None):
-        if dx is None:
-            dx = numpy.ones(img.ndim, dtype=float)
-        else:
-            dx = numpy.array(dx, dtype=float)
-            if len(dx) != img.ndim:
-                msg = "Number of dx terms ({}) doesn't match dimensions ({})"
-                raise ValueError(msg.format(len(dx), img.ndim))
-        if seed is None:
-            seed = numpy.array(img.shape) / 2
-        else:
-            seed = numpy.array(seed)
-        init_mask = self.initialize(img=img, dx=dx, seed=seed)
-        if not isinstance(init_mask, numpy.ndarray):
-            msg = "Returned initializer was type {} but should be numpy.ndarray"
-            raise TypeError(msg.format(type(init_mask)))
-        if init_mask.dtype != bool:
-            msg = "Returned initializer was dtype {} but should be bool"
-            raise TypeError(msg.format(init_mask.dtype))
-        if init_mask.shape != img.shape:
-            msg = "Returned initializer was shape {} but should be {}"
-            raise ValueError(msg.format(init_mask.shape, img.shape))
-        u = 2 * init_mask.astype(float) - 1
+        dx = _spacing(dx, img.ndim)
+        seed = numpy.array(img.shape) / 2 if seed is None else numpy.array(seed)
+        inside = _checked(self.initialize(img=img, dx=dx, seed=seed), img.shape)
+        u = 2 * inside.astype(float) - 1
         dist, mask = distance_transform(arr=u, band=band, dx=dx)
         return u, dist, mask
 

@@ -90,38 +90,32 @@ class RandomBallInitializer(InitializerBase):
 
 
 class ThresholdBallInitializer(InitializerBase):
-    """ A ball around the seed whose radius is the seed's distance to the boundary of the
-    connected component (of ``img > gaussian_filter(img, sigma)``) it lies in, or of the nearest
-    component (reference ball.py:118-159).  Host side, once per image; the distance to the
-    component's complement is the device marcher's (the reference calls ``skfmm.distance``). """
+    """ A ball around the seed that just fits into the bright component the seed lies in
+    (reference ball.py:118-159).  "Bright" means brighter than the image smoothed with a Gaussian
+    of width ``sigma``; if the seed is in no component the nearest component voxel takes its
+    place.  The radius is the seed's distance to the component's complement, taken from the device
+    marcher where the reference calls ``skfmm.distance``.  Host side, once per image. """
 
     def __init__(self, sigma=4.0):
         self.sigma = sigma
 
-    def initialize(self, img, dx, seed):
-        from scipy.ndimage import gaussian_filter, label
-        from ...util.distance_transform import distance_transform
-
-        smoothed = gaussian_filter(img, self.sigma)
-        thresholded = img > smoothed
-        labels, _ = label(thresholded)
-        if labels[self._seed_to_index(seed)] > 0:
-            seed_ = seed
-        else:
-            nonzero = numpy.array(numpy.nonzero(labels)).T.astype(float)
-            nonzero *= dx
-            dists = numpy.linalg.norm(nonzero - seed, axis=1)
-            seed_ = nonzero[dists.argmin()]
-        mask = labels == labels[self._seed_to_index(seed_)]
-        inds = numpy.indices(img.shape, dtype=float)
-        for i in range(inds.shape[0]):
-            inds[i] -= seed_[i]
-            inds[i] *= dx[i]
-        dist_to_seed = (inds ** 2).sum(axis=0) ** 0.5
-        # skfmm.distance(mask, dx): the bool mask as a level set (0 outside, 1 inside)
-        dist_to_boundary, _ = distance_transform(mask.astype(float), band=0, dx=dx)
-        return dist_to_seed < dist_to_boundary[self._seed_to_index(seed_)]
-
     @staticmethod
     def _seed_to_index(seed):
         return tuple(numpy.asarray(seed).round().astype(int))
+
+    def initialize(self, img, dx, seed):
+        from scipy import ndimage
+        from ...util.distance_transform import distance_transform
+
+        components, _ = ndimage.label(img > ndimage.gaussian_filter(img, self.sigma))
+        centre = numpy.asarray(seed, dtype=float)
+        if components[self._seed_to_index(centre)] == 0:
+            voxels = numpy.argwhere(components > 0) * numpy.asarray(dx, dtype=float)
+            centre = voxels[numpy.linalg.norm(voxels - centre, axis=1).argmin()]
+        at = self._seed_to_index(centre)
+        component = components == components[at]
+        # the bool component as a level set (0 outside, 1 inside), full distance map
+        to_boundary, _ = distance_transform(component.astype(float), band=0, dx=dx)
+        grid = numpy.indices(img.shape, dtype=float)
+        offsets = [(grid[a] - centre[a]) * dx[a] for a in range(img.ndim)]
+        return numpy.sqrt(sum(o * o for o in offsets)) < to_boundary[at]

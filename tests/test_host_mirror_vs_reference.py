@@ -173,3 +173,37 @@ def test_threshold_initializer_reference_test():
     assert blurred.dtype == bool and blurred[7, 7] and not blurred[0, 0]
     with pytest.raises(ValueError):
         ThresholdInitializer(sigma=-1)
+
+
+def test_base_feature_error_messages(ref):
+    """Same exception type and text as the reference for every kind of bad call
+    (feature/base_feature.py:67-139)."""
+    from lsml.feature.provided.image import ImageSample as RI
+    from lsml.feature.provided.shape import Size as RS
+    from lsml_b200.feature import ImageSample as MI, Size as MS
+
+    def err(f):
+        try:
+            f()
+        except Exception as e:
+            return type(e).__name__, str(e)
+        return None
+
+    u, img = np.ones((3, 2)), np.ones((3, 2))
+    mask = np.ones((3, 2), dtype=bool)
+    calls = [
+        lambda I, S: I(ndim=2, sigma=0)(u='x'),
+        lambda I, S: I(ndim=2, sigma=0)(u=u),
+        lambda I, S: I(ndim=2, sigma=0)(u=u, img='x'),
+        lambda I, S: I(ndim=2, sigma=0)(u=u, img=np.ones((3, 1))),
+        lambda I, S: S(ndim=2)(u=u, dist='x'),
+        lambda I, S: S(ndim=2)(u=u, dist=np.ones((3,))),
+        lambda I, S: S(ndim=2)(u=u, dx=[1]),
+        lambda I, S: S(ndim=2)(u=u, mask='x'),
+        lambda I, S: S(ndim=2)(u=u, mask=np.ones((3, 9), dtype=bool)),
+        lambda I, S: S(ndim=2)(u=u, mask=u),
+        lambda I, S: I(ndim=2, sigma=0)(u=u, img=img, dist=np.ones((2, 2)), mask=mask, dx=[1, 2, 3]),
+    ]
+    for c in calls:
+        want, got = err(lambda: c(RI, RS)), err(lambda: c(MI, MS))
+        assert want is not None and want == got, (want, got)
