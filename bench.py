@@ -698,6 +698,15 @@ def main():
                                  "peak_source": peak_src, "ms": st_ms},
             "phases_ms_per_step": {k: v[1] for k, v in phases.items()},
         }
+        # SURVEY.md 8(d) region (A): features + velocity + update with the band given -- the part
+        # BASELINE.json's metric names; `value` above is region (B), the full step with band
+        # rebuild and compaction.  From the per-phase device times of the evidence pass (one
+        # step on rank 0's volume).
+        ms_a = sum(phases.get(k, (0, 0.0))[1] for k in ("features", "predict", "update"))
+        if ms_a > 0:
+            line["region_a"] = {"value": (bvi_all / world / max(1, args.steps)) / (ms_a * 1e-3),
+                                "unit": "band-voxel-iterations/s", "ms_per_step": ms_a,
+                                "what": "features + velocity + update, band given, one GPU"}
         if not args.no_cpu_baseline:
             res = cpu_reference_run(n, 1234, 1, 0, regs=None, budget_s=25.0, log=log)
             v = res["band_voxel_iterations"] / res["seconds"]
