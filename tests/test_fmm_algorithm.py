@@ -215,7 +215,7 @@ def test_contributor_rule_fixture(oracle, name, n_legacy, tol):
     second neighbour across the interface) makes the marcher's freeze values non-monotone, so that
     the replay fixed point differs from the sequential marcher in a few dozen distances (masks
     agree): a random one (differences < 1e-7) and a crop of a C4-like evolution found by
-    tools/fmm_cycle_hunt.py (up to 1.6e-4).  With the adopted rule the two are identical;
+    tests/tools/fmm_cycle_hunt.py (up to 1.6e-4).  With the adopted rule the two are identical;
     `LSML_ORACLE_RULE_R2=0 pytest` checks the legacy behaviour."""
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
     u, dx, band = z["u"], z["dx"], float(z["band"])

@@ -8,9 +8,9 @@ forest recipe as bench.py --workload c4, oracle arithmetic) and after every iter
 model of the device scheduler (oracle/fmm_sched_model.c), in place and synchronously, with a
 generous sweep budget.  Any non-convergent or mismatching rebuild is saved as an .npz.
 
-    python tools/fmm_cycle_hunt.py --worker 0 --items 400 --out /tmp/hunt
+    python tests/tools/fmm_cycle_hunt.py --worker 0 --items 400 --out /tmp/hunt
 
-TEST INFRASTRUCTURE (uses oracle/).
+TEST INFRASTRUCTURE (uses oracle/; lives under tests/ for that reason).
 """
 import argparse
 import os
@@ -19,7 +19,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
