@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--radius", type=float, nargs=2, default=(6.0, 18.0), help="object radius range")
     ap.add_argument("--init-radius", type=float, default=5.0)
     ap.add_argument("--jitter", type=float, default=8.0)
+    ap.add_argument("--scheduler-source", action="store_true",
+                    help="also rebuild every band with the kernel's scheduler source on one host "
+                         "thread (tests/test_fmm_scheduler_host.py harness), hints carried along")
     ap.add_argument("--device-source-every", type=int, default=0,
                     help="also iterate the kernel's own source, compiled for the host "
                          "(tests/test_fmm_device_code_host.py), on every N-th rebuild input")
@@ -52,6 +55,28 @@ def main():
         legacy = os.environ.get("LSML_ORACLE_RULE_R2") == "0"
         dev_lib = ctypes.CDLL(build_host_lib(tempfile.mkdtemp(), legacy))
     n_dev = 0
+    sched_lib = None
+    if args.scheduler_source:
+        import ctypes
+        import re
+        import subprocess
+        import tempfile
+        from test_fmm_scheduler_host import HostScheduler
+        src = open(os.path.join(ROOT, "lsml_b200", "csrc", "fmm.cu")).read()
+        regions = re.findall(r"// \[host-(?:test|sched):begin\][^\n]*\n(.*?)// \[host-(?:test|sched):end\]",
+                             src, re.S)
+        native = os.path.join(ROOT, "tests", "native")
+        tmpd = tempfile.mkdtemp()
+        with open(os.path.join(tmpd, "s.cpp"), "w") as f:
+            f.write('#include "cuda_host_shim.h"\nnamespace lsml {\n' + "\n".join(regions) +
+                    open(os.path.join(native, "fmm_sched_driver.inc")).read())
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused",
+                               "-shared", "-fPIC", "-I", native, os.path.join(tmpd, "s.cpp"),
+                               "-o", os.path.join(tmpd, "s.so")])
+        sched_lib = ctypes.CDLL(os.path.join(tmpd, "s.so"))
+        sched_lib.hs_create.restype = ctypes.c_void_p
+        sched_lib.hs_rebuild.restype = ctypes.c_long
+    n_sched = 0
     shape, band, dx = (args.size,) * 3, 3.0, np.ones(3)
     CHUNK = 16          # items are generated 16 at a time
     g = np.indices(shape).astype(np.float64)
@@ -98,6 +123,12 @@ def main():
         hist = [np.zeros(512, dtype=np.int64) for _ in range(2)]
         gen = [np.array([b * 37], dtype=np.int64) for _ in range(2)]
         prev = None
+        hs = None
+        if sched_lib is not None:
+            hs = HostScheduler(sched_lib, shape, 1, dx)
+            hs.set_gen(b * 37)
+            hs.set_order(b % 3)
+            hs.rebuild(u[None], band, None)          # the band of u0 (dense search), as the engine does
         for it in range(args.iters):
             if not mask.any():
                 break
@@ -139,14 +170,27 @@ def main():
                                         band=band)
                     log.write("DEVSRC item %d it %d sweeps %d\n" % (b, it, sweeps))
                     log.flush()
+            if hs is not None:
+                d, m, sweeps, ctr = hs.rebuild(u[None], band, prev)
+                n_sched += 1
+                if (sweeps <= 0 or (ctr[3] & 15) or not np.array_equal(m[0], wm)
+                        or not np.array_equal(d[0], np.where(np.isfinite(wd), wd, 0.0))):
+                    n_bad += 1
+                    np.savez_compressed(os.path.join(args.out, "case_w%d_b%d_it%d_SCHED.npz"
+                                                     % (args.worker, b, it)), u=u, prev=prev, dx=dx,
+                                        band=band)
+                    log.write("SCHED item %d it %d sweeps %d ctr %s\n" % (b, it, sweeps, ctr.tolist()))
+                    log.flush()
             dist, mask = wd, wm
-        log.write("item %d done: rebuilds %d bad %d worst sweeps %d device-source checks %d\n"
-                  % (b, n_reb, n_bad, worst, n_dev))
+        if hs is not None:
+            hs.close()
+        log.write("item %d done: rebuilds %d bad %d worst sweeps %d scheduler-source rebuilds %d "
+                  "device-source checks %d\n" % (b, n_reb, n_bad, worst, n_sched, n_dev))
         log.flush()
         if time.time() > t_end:
             break
-    log.write("END rebuilds %d bad %d worst sweeps %d device-source checks %d\n"
-              % (n_reb, n_bad, worst, n_dev))
+    log.write("END rebuilds %d bad %d worst sweeps %d scheduler-source rebuilds %d "
+              "device-source checks %d\n" % (n_reb, n_bad, worst, n_sched, n_dev))
     log.close()
 
 
