@@ -152,3 +152,21 @@ def test_ring_overflow_falls_back_to_scanning_the_candidate_list(oracle, sched_l
         prev = np.flatnonzero(m.ravel())
     hs.close()
     assert fell_back == 6
+
+
+def test_reference_known_answers_through_the_scheduler_source(oracle, sched_lib):
+    """lsml/util/test/test_distance_transform.py:11-21 (1-D, band 1) and a full-distance (band 0)
+    3-D case on the scheduler source."""
+    hs = HostScheduler(sched_lib, (5,), 1, [1.0])
+    d, m, sweeps, ctr = hs.rebuild(np.r_[-1, -1, 1, -1, -1.][None], 1.0)
+    hs.close()
+    assert sweeps > 0 and ctr[3] & 15 == 0
+    assert (d[0] == np.r_[0., -0.5, 0.5, -0.5, 0.]).all()
+    assert (m[0] == np.r_[False, True, True, True, False]).all()
+    arr = np.ones((4, 5, 6))
+    arr[2] = -1
+    hs = HostScheduler(sched_lib, arr.shape, 1, [1, 1, 1.])
+    d, m, sweeps, ctr = hs.rebuild(arr[None], 0.0)
+    hs.close()
+    wd, wm = oracle.fmm_distance(arr, np.ones(3), 0.0)
+    assert sweeps > 0 and m.all() and np.array_equal(d[0], wd)
