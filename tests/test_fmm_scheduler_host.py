@@ -170,3 +170,15 @@ def test_reference_known_answers_through_the_scheduler_source(oracle, sched_lib)
     hs.close()
     wd, wm = oracle.fmm_distance(arr, np.ones(3), 0.0)
     assert sweeps > 0 and m.all() and np.array_equal(d[0], wd)
+
+
+def test_edge_cases_through_the_scheduler_source(sched_lib):
+    """distance_transform.py:36-47: all-zero input -> full mask, zero distances; single-sign
+    input -> empty mask (the items are skipped from their exact sign counts)."""
+    hs = HostScheduler(sched_lib, (4, 5, 6), 3, [1, 1, 1.])
+    us = np.stack([np.zeros((4, 5, 6)), np.ones((4, 5, 6)), -np.ones((4, 5, 6))])
+    d, m, sweeps, ctr = hs.rebuild(us, 0.0)
+    hs.close()
+    assert sweeps >= 0 and ctr[3] & 15 == 0
+    assert m[0].all() and (d[0] == 0).all()
+    assert not m[1].any() and not m[2].any()
