@@ -41,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_ITERS = 50
+_DIAG = {}          # objects the watchdog inspects when a run hangs
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu captures
 NCU_TRAFFIC_MARCH_BYTES = 16.951296e6 + 5.875200e6
 NCU_TRAFFIC_STENCIL_BYTES = 354.348800e6 + 122.087424e6
@@ -343,6 +344,7 @@ def run_other_workload(args):
     from lsml_b200.core.regressors import export_regressor
     from lsml_b200.core.sharding import shard_range
     wl = args.workload
+    t_start = time.perf_counter()
     if wl == "c5":
         from sklearn.linear_model import LinearRegression
         from lsml_b200.core.slab import SlabVolume, TorchCollective
@@ -407,22 +409,33 @@ def run_other_workload(args):
             if args.features == "gestalt32":
                 specs = gestalt32_specs()
         nd = len(shape)
+        vlog = (lambda m: print("[rank %d %7.1f s] %s" % (rank, time.perf_counter() - t_start, m),
+                                file=sys.stderr, flush=True)) if args.verbose else (lambda m: None)
+        vlog("items generated")
         eng = BandEngine(shape, hi - lo, dx=np.ones(nd), band=BAND, specs=specs, device=device)
+        _DIAG["engine"] = eng
         eng.load_images(imgs, normalize=True)
+        torch.cuda.synchronize(); vlog("images loaded, planes computed")
         g = np.indices(shape).astype(np.float64)
         rc = np.sqrt(sum((g[a] - shape[a] / 2.0) ** 2 for a in range(nd)))
         u0 = torch.from_numpy(np.where(rc < r_init, 1.0, -1.0)).to(device).expand(
             (hi - lo,) + tuple(shape)).contiguous()
         eng.set_level_sets(u0)
+        torch.cuda.synchronize(); vlog("initial band: %d voxels, counters %r" % (eng.n_band, eng.fmm_counters()))
         X = eng.compute_features().cpu().numpy()
         y = X[:, 1] + 0.2 * np.random.RandomState(1).standard_normal(X.shape[0])
         reg = export_regressor(_fit_forest(X, y, 5), device)     # one forest reused every iteration
+        vlog("forest trained")
 
         def one_pass():
             eng.set_level_sets(u0)
             tot = 0
-            for _ in range(iters):
+            for it in range(iters):
                 tot += eng.step(reg, 0.4)
+                if args.verbose:
+                    torch.cuda.synchronize()
+                    vlog("iteration %d: band %d, %r" % (it, eng.n_band, eng.fmm_counters()))
+            eng.check_converged()
             return tot
         units_are_global = False
         desc = ("%s: %d synthetic %s items (%d on this rank, one engine per GPU), RF-100 velocity, "
@@ -497,6 +510,18 @@ def main():
         def _abort():
             print("bench.py: watchdog fired after %.0f s -- aborting (exit 124)" % args.watchdog,
                   file=sys.stderr, flush=True)
+            try:      # where is the host, and (from a second stream) where is the band rebuild?
+                import faulthandler
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                eng = _DIAG.get("engine")
+                if eng is not None and getattr(eng, "_ws_fmm", None) is not None:
+                    import torch
+                    with torch.cuda.stream(torch.cuda.Stream(device=eng.device)):
+                        st = eng._fmm_status.to("cpu", non_blocking=False).tolist()
+                    print("fmm status {failed, barriers, live sweep, rix, begin, end}: %r" % (st,),
+                          file=sys.stderr, flush=True)
+            except Exception as exc:            # diagnostics only
+                print("watchdog diagnostics failed: %r" % (exc,), file=sys.stderr, flush=True)
             os._exit(124)
         timer = threading.Timer(args.watchdog, _abort)
         timer.daemon = True

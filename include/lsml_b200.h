@@ -230,6 +230,15 @@ int lsml_fmm_counters(long long total, void *workspace, long long *out, void *st
  * their start times in ns (HOST out[64]) */
 int lsml_fmm_sweep_sizes(long long total, void *workspace, long long *out, void *stream);
 
+/* Status words a host layer can read without a call: the workspace holds the rebuild counters at
+ * byte offset lsml_fmm_counters_offset(total); at lsml_fmm_status_offset() bytes into them lie
+ * int64 {failed_rebuilds (rebuilds since workspace_init that hit the sweep limit before their
+ * fixed point -- must stay 0), barriers of the last march, live sweep, live rix, live begin,
+ * live end (published before every grid-wide sweep; readable from a second stream while a march
+ * runs)}. */
+long long lsml_fmm_counters_offset(long long total);
+long long lsml_fmm_status_offset(void);
+
 /* ---- either side of the path -------------------------------------------------- */
 /* u0 = 2*ball - 1 with ball = (radius - |idx*dx - location*dx|) > 0
  * (lsml/initializer/provided/ball.py:13-31, initializer_base.py:56).  location: HOST double[ndim]

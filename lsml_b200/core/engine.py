@@ -387,6 +387,12 @@ class BandEngine:
         if self._ws_fmm is None:
             nbytes = int(_lib.lib.lsml_fmm_workspace_bytes(_lib.c_i64(self.total)))
             self._ws_fmm = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.lib.lsml_fmm_counters_offset.restype = _lib.c_i64
+            _lib.lib.lsml_fmm_status_offset.restype = _lib.c_i64
+            off = (int(_lib.lib.lsml_fmm_counters_offset(_lib.c_i64(self.total))) +
+                   int(_lib.lib.lsml_fmm_status_offset()))
+            # int64 view {failed_rebuilds, barriers, live sweep, rix, begin, end} (lsml_b200.h)
+            self._fmm_status = self._ws_fmm[off:off + 48].view(torch.int64)
             self.mask.zero_()
             _lib.check(_lib.lib.lsml_fmm_workspace_init(
                 _lib.c_i64(self.total), _lib.ptr(self._ws_fmm), self._stream()), "fmm_init")
@@ -400,6 +406,17 @@ class BandEngine:
                 "fmm_rebuild")
         self._compact()
         self._band_is_rebuilt = True
+
+    def check_converged(self):
+        """Raise if any band rebuild since the workspace was created ended at its sweep limit
+        instead of its fixed point (the mask of such a rebuild is not the reference's).  One
+        host read; call it once per segmentation, not per iteration."""
+        if self._ws_fmm is None:
+            return
+        failed = int(self._fmm_status[0].item())
+        if failed:
+            raise _lib.LsmlError("band rebuild: %d rebuild(s) stopped at the sweep limit before "
+                                 "reaching their fixed point" % failed)
 
     def fmm_counters(self):
         out = (ctypes.c_longlong * 8)()
@@ -502,10 +519,12 @@ class BandEngine:
             # `segment` rebuilds the iterates from.  The rebuild below compacts into the OTHER
             # index buffer, so this view stays valid until the next iteration's rebuild.
             self._last_idx = self.band_idx[:nb]
+            # (the view keeps the storage alive if the rebuild below has to grow the buffers)
+            self._last_new_u = self.new_u[:nb]
             if record:
                 if self.history is None:
                     self.history = []
-                self.history.append((self._last_idx.clone(), self.new_u[:nb].clone()))
+                self.history.append((self._last_idx.clone(), self._last_new_u.clone()))
             self.band_voxel_iterations += nb
             if rebuild:
                 self._rebuild_band(from_band=True)

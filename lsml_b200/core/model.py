@@ -296,6 +296,7 @@ class LevelSetMachineLearning:
                 slope = numpy.linalg.lstsq(xs, hist, rcond=None)[0][0]
                 if slope < validation_history_tol:
                     break
+        eng.check_converged()
         self.scores = {k: numpy.array(v) for k, v in self.scores.items()}
         self._is_fitted = True
         if save_filename:
@@ -403,10 +404,11 @@ class LevelSetMachineLearning:
             us[i + 1] = us[i]
             if nb:
                 # the sparse record of this iteration: band indices and their new values
-                us[i + 1].ravel()[eng._last_idx.cpu().numpy()] = eng.new_u[:nb].cpu().numpy()
+                us[i + 1].ravel()[eng._last_idx.cpu().numpy()] = eng._last_new_u.cpu().numpy()
             if verbose:
                 print(print_string.format(i + 1))
             after(i + 1)
+        eng.check_converged()
         if return_scores:
             return us, numpy.array(scores)
         return us
@@ -427,6 +429,7 @@ class LevelSetMachineLearning:
             n_iters = self._n_iters(iterate_until_validation_max)
         for i in range(n_iters):
             eng.step(self._device_model(i, eng.device), self._step)
+        eng.check_converged()
         if _return_engine:
             return eng
         return eng.u, eng.mask.bool()

@@ -107,6 +107,12 @@ struct FmmCounters {      // device-resident
     i64 fill[256];        // entries parked per level so far
     i64 sizes[32];        // work-set size of the first 32 grid-wide sweeps (diagnostic)
     i64 stamps[32];       // %globaltimer (ns) at the start of those sweeps (diagnostic)
+    // ---- status the host layer reads ONCE per segmentation (never reset by a rebuild)
+    i64 failed_rebuilds;  // marches that ended without reaching their fixed point (sweep limits)
+    i64 barriers;         // grid barriers of the last march (diagnostic)
+    i64 live[4];          // {sweep, rix, begin, end} published by thread 0 before every grid-wide
+                          // step: readable from another stream while a march is running (hang
+                          // diagnosis, tools/c4_probe.py)
 };
 // [host-sched:end]
 
@@ -932,6 +938,14 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     i64 begin = ctr->resume_begin, end = begin + vtail[rix % 3u];   // queued by seed / requeue
     bool scan = vovf[2] != 0;          // ... which report overflow into slot 2
     i64 nreplay = 0;
+    // Every CTA must have taken its snapshot of the start state before any CTA mutates it: a
+    // small first work set sends CTA 0 straight into its single-CTA sweeps, which zero
+    // tail3[rix % 3] from their second sweep on -- a CTA scheduled a few microseconds late
+    // would then read end == begin, declare convergence and leave without ever reaching the
+    // grid barrier the others wait at.  All later loop-exit tests only read values published
+    // before a barrier (or monotone ones: fill[sweep] is final before sweep `sweep` starts,
+    // last_bucket only grows and is compared while nothing is being processed).
+    grid.sync();
     while (barriers < FMM_MAX_SWEEPS && sweep < FMM_SWEEP_LIMIT) {
         i64 nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;       // bucket of this sweep
         if (end == begin && nbk == 0 && !scan) {
@@ -943,6 +957,8 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
         if (tid == 0) {
             vovf[(barriers + 1) % 3] = 0;
             vtail[(rix + 2u) % 3u] = 0;
+            volatile i64* live = ctr->live;
+            live[0] = (i64)sweep; live[1] = (i64)rix; live[2] = begin; live[3] = end;
             if (barriers < 32) {
                 ctr->sizes[barriers] = scan ? -1 : end - begin + nbk;
                 unsigned long long now;
@@ -1074,6 +1090,8 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     if (tid == 0) {
         ctr->sweeps = (i64)sweep - 1;
         ctr->converged = converged ? 1 : 0;
+        if (!converged && finalize) ctr->failed_rebuilds += 1;
+        ctr->barriers = barriers;
         ctr->prev_init = ctr->n_init;
         ctr->prev_cand = nc;
         ctr->resume_sweep = (i64)sweep;
@@ -1425,6 +1443,12 @@ int fmm_counters_ptr(i64 total, void* workspace, const i64** out) {
 
 // byte offset of FmmCounters::sizes inside the counters (diagnostics)
 i64 fmm_counters_sizes_offset() { return (i64)offsetof(FmmCounters, sizes); }
+i64 fmm_counters_failed_offset() { return (i64)offsetof(FmmCounters, failed_rebuilds); }
+// byte offset of the counters inside a workspace for `total` voxels
+i64 fmm_counters_offset(i64 total) {
+    return total * (i64)(sizeof(double) + sizeof(Aux) + sizeof(i64)) +
+           2 * ring_capacity(total) * (i64)sizeof(i64);
+}
 i64 fmm_counters_stamps_offset() { return (i64)offsetof(FmmCounters, stamps); }
 
 }  // namespace lsml

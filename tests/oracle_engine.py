@@ -55,6 +55,9 @@ class OracleEngine:
             self._rebuild(b)
         self._compact()
 
+    def check_converged(self):
+        pass
+
     def distance(self):
         return torch.from_numpy(self._dist.copy())
 
@@ -78,6 +81,7 @@ class OracleEngine:
                                              rebuild=False)
             self.u[b] = torch.from_numpy(u)
         self.new_u = self.u.reshape(-1)[self._last_idx].clone()
+        self._last_new_u = self.new_u
         for b in range(self.batch):
             self._rebuild(b)
         self._compact()
