@@ -45,6 +45,16 @@ typedef unsigned char u8;
  * noise.  The distances themselves stay float64. */
 static inline float qmag(double d) { return (float)fabs(d); }
 
+/* Ablation switches (tests/tools/band_gap_report.py --ablate): each bit turns ONE of the four
+ * deliberate departures from upstream scikit-fmm back into upstream's behaviour, so that the gap
+ * to oracle/skfmm_literal.c can be attributed.  0 (the default) is the marcher the product
+ * matches; nothing but the report ever sets it. */
+enum { ABL_KEY64 = 1, ABL_NO_CAUSALITY = 2, ABL_KEEP_V2 = 4, ABL_BREAK = 8 };
+static int g_ablate = 0;
+void orc_fmm_set_ablation(int flags) { g_ablate = flags; }
+/* ordering magnitude: float32-rounded (default) or the float64 value itself */
+static inline double omag(double d) { return (g_ablate & ABL_KEY64) ? fabs(d) : (double)qmag(d); }
+
 /* Contributor rule: a second neighbour of OPPOSITE sign lies across the
  * interface -- its magnitude says nothing about causality -- and is exempt from the causality
  * test and from eviction.  With it the marcher's freeze values are monotone in freeze order, which
@@ -179,7 +189,7 @@ static long nb(const fmm_t *m, long i, int axis, int step) {
  * (scikit-fmm's own tie behaviour depends on its heap internals and is not reproducible
  * without its source; a total order makes the result well defined.) */
 static int key_less(const fmm_t *m, long i, long j) {
-    float a = qmag(m->dist[i]), b = qmag(m->dist[j]);
+    double a = omag(m->dist[i]), b = omag(m->dist[j]);
     return (a < b) || (a == b && i < j);
 }
 static void heap_swap(fmm_t *m, long a, long b) {
@@ -267,19 +277,20 @@ static double fmm_solve(int ndim, const double *idx2, const double *v1in, const 
             int causal = 1;
             for (int ax = 0; ax < ndim; ++ax) {
                 if (!active[ax]) continue;
-                if (qmag(r) <= qmag(v1[ax])) causal = 0;
-                if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && qmag(r) <= qmag(v2[ax])) causal = 0;
+                if (omag(r) <= omag(v1[ax])) causal = 0;
+                if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && omag(r) <= omag(v2[ax])) causal = 0;
             }
-            if (causal) return r;
+            if (causal || (g_ablate & ABL_NO_CAUSALITY)) return r;
         }
+        if (g_ablate & ABL_NO_CAUSALITY) return -b / (2.0 * a);   /* upstream's det < 0 fallback */
         /* remove the contributor farthest from the interface: a value2 demotes its axis to
          * first order, a value1 drops the axis (first maximum in the order ax0.v2, ax0.v1, ...) */
         int worst = -1, worst_is_v2 = 0;
-        float wv = -1.0f;
+        double wv = -1.0;
         for (int ax = 0; ax < ndim; ++ax) {
             if (!active[ax]) continue;
-            if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && qmag(v2[ax]) > wv) { wv = qmag(v2[ax]); worst = ax; worst_is_v2 = 1; }
-            if (qmag(v1[ax]) > wv) { wv = qmag(v1[ax]); worst = ax; worst_is_v2 = 0; }
+            if (v2[ax] < DBL_MAX && !across(v1[ax], v2[ax]) && omag(v2[ax]) > wv) { wv = omag(v2[ax]); worst = ax; worst_is_v2 = 1; }
+            if (omag(v1[ax]) > wv) { wv = omag(v1[ax]); worst = ax; worst_is_v2 = 0; }
         }
         if (worst_is_v2) v2[worst] = DBL_MAX;
         else { active[worst] = 0; nactive--; }
@@ -291,7 +302,7 @@ static double fmm_solve(int ndim, const double *idx2, const double *v1in, const 
  * away must not be farther from the interface than the direct neighbour, in the signed sense
  * (a voxel on the other side of the interface always qualifies). */
 static int second_order_ok(double d2, double v1) {
-    return v1 == 0.0 || d2 * v1 < 0 || qmag(d2) <= qmag(v1);
+    return v1 == 0.0 || d2 * v1 < 0 || omag(d2) <= omag(v1);
 }
 
 static double fmm_update(const fmm_t *m, long i) {
@@ -301,9 +312,9 @@ static double fmm_update(const fmm_t *m, long i) {
         for (int j = -1; j < 2; j += 2) {
             long n = nb(m, i, ax, j);
             if (n != -1 && m->flag[n] == FROZEN &&
-                (v1[ax] == DBL_MAX || qmag(m->dist[n]) < qmag(v1[ax]))) {
+                (v1[ax] == DBL_MAX || omag(m->dist[n]) < omag(v1[ax]))) {
                 v1[ax] = m->dist[n];
-                v2[ax] = DBL_MAX;
+                if (!(g_ablate & ABL_KEEP_V2)) v2[ax] = DBL_MAX;
                 long n2 = nb(m, i, ax, 2 * j);
                 if (n2 != -1 && m->flag[n2] == FROZEN && second_order_ok(m->dist[n2], v1[ax]))
                     v2[ax] = m->dist[n2];
@@ -383,7 +394,11 @@ long orc_fmm_distance(int ndim, const int *shape, const double *phi, const doubl
         /* outside the band: never frozen.  scikit-fmm breaks out of its loop here; with heap
          * order decided on rounded keys (qmag) a later pop can tie with this one and still be
          * inside the band, so the loop continues (nothing is pushed from a discarded voxel). */
-        if (narrow != 0 && fabs(m.dist[x]) > narrow) { m.flag[x] = NARROW; continue; }
+        if (narrow != 0 && fabs(m.dist[x]) > narrow) {
+            m.flag[x] = NARROW;
+            if (g_ablate & ABL_BREAK) break;
+            continue;
+        }
         m.flag[x] = FROZEN;
         nfrozen++;
         for (int ax = 0; ax < ndim; ++ax)

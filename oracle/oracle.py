@@ -50,6 +50,7 @@ def _lib():
             build()
         _LIB = ctypes.CDLL(str(path))
         _LIB.orc_fmm_distance.restype = ctypes.c_long
+        _LIB.orc_skfmm_literal_distance.restype = ctypes.c_long
         _LIB.orc_marching_squares_length.restype = ctypes.c_double
     return _LIB
 
@@ -129,8 +130,12 @@ def gradient_centered(arr, mask=None, dx=None, normalize=False, use_reference=Fa
 # --------------------------------------------------------------------------------------------
 # a14: distance transform / band mask
 # --------------------------------------------------------------------------------------------
-def fmm_distance(phi, dx=None, narrow=0.0):
-    """skfmm.distance restatement: returns (dist, frozen) with dist 0 where not frozen."""
+def fmm_distance(phi, dx=None, narrow=0.0, literal=False):
+    """skfmm.distance restatement: returns (dist, frozen) with dist 0 where not frozen.
+    ``literal``: the upstream-literal marcher of oracle/skfmm_literal.c (float64 heap keys with
+    scikit-fmm's own heap mechanics, no causality test, break at the band edge, value2 kept)
+    instead of the marcher the product is bit-exact to -- the measuring stick of
+    tools/band_gap_report.py, never a golden source."""
     phi = np.ascontiguousarray(phi, dtype=np.float64)
     dx = (np.ones(phi.ndim) if dx is None else np.asarray(dx, dtype=np.float64)).copy()
     if dx.ndim == 0:
@@ -138,9 +143,10 @@ def fmm_distance(phi, dx=None, narrow=0.0):
     shape = np.asarray(phi.shape, dtype=np.int32)
     dist = np.zeros_like(phi)
     frozen = np.zeros(phi.shape, dtype=np.uint8)
-    n = _lib().orc_fmm_distance(ctypes.c_int(phi.ndim), _p(shape, _c_int_p), _p(phi, _c_dbl_p),
-                                _p(dx, _c_dbl_p), ctypes.c_double(float(narrow)),
-                                _p(dist, _c_dbl_p), _p(frozen, _c_u8_p))
+    fn = _lib().orc_skfmm_literal_distance if literal else _lib().orc_fmm_distance
+    n = fn(ctypes.c_int(phi.ndim), _p(shape, _c_int_p), _p(phi, _c_dbl_p),
+           _p(dx, _c_dbl_p), ctypes.c_double(float(narrow)),
+           _p(dist, _c_dbl_p), _p(frozen, _c_u8_p))
     if n < 0:
         raise ValueError("the array phi contains no zero contour (no zero level set)")
     return dist, frozen.astype(bool)
@@ -156,7 +162,7 @@ def skfmm_distance(phi, dx=1.0, narrow=0.0, **_):
     return np.ma.MaskedArray(dist, ~frozen)
 
 
-def distance_transform(arr, band, dx):
+def distance_transform(arr, band, dx, literal=False):
     """lsml/util/distance_transform.py:5-59 (edge cases :36-47, band==0 :54-57)."""
     arr = np.asarray(arr, dtype=np.float64)
     if (arr == 0).all():
@@ -166,7 +172,7 @@ def distance_transform(arr, band, dx):
         mask = np.zeros(arr.shape, dtype=bool)
         sign = np.sign(arr.ravel()[0])
         return sign * np.full(arr.shape, np.inf), mask
-    dist, frozen = fmm_distance(arr, dx, band)
+    dist, frozen = fmm_distance(arr, dx, band, literal=literal)
     return dist, frozen
 
 

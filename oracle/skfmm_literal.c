@@ -25,8 +25,14 @@
  *                 value2 is (re)assigned only when the voxel two cells away qualifies -- a value2
  *                 found for the first direction SURVIVES when the second direction supplies the
  *                 smaller value1 without a qualifying second neighbour (upstream quirk, kept).
- *   quadratic     solveQuadratic: c -= 1; det = b^2 - 4ac; det > 0 ? root by the sign of phi
- *                 (phi > DBL_EPSILON takes +sqrt) : 0.  No causality test of any kind.
+ *   quadratic     solveQuadratic: c -= 1; det = b^2 - 4ac; det >= 0: root by the sign of phi
+ *                 (phi > DBL_EPSILON takes +sqrt).  det < 0: the releases since 2019 throw
+ *                 "Negative discriminant in distance marcher quadratic" and updatePointOrderTwo
+ *                 catches it and returns "the position of the minimum as a more reasonable
+ *                 approximation", -b / (2a); older releases returned 0 there (the caller then
+ *                 leaves the voxel alone -- except initalizeNarrow, which pushes the 0 and so
+ *                 freezes a spurious zero).  orc_skfmm_literal_set_old_det(1) selects the older
+ *                 behaviour.  No causality test of any kind in either.
  *   march         baseMarcher::solve: pop; `if (narrow != 0 && fabs(value) > narrow) break;`
  *                 freeze; update the four-per-axis stencil exactly in upstream's order (direct
  *                 neighbour, then the "jump over a frozen point" second-order update, per
@@ -147,6 +153,9 @@ static long get_n(const lm_t *m, long current, int dim, int dir, int flag) {
 
 #define L_MASK 3 /* no voxel is ever masked on this path */
 
+static int g_old_det = 0;
+void orc_skfmm_literal_set_old_det(int on) { g_old_det = on; }
+
 /* distanceMarcher::updatePointOrderTwo + solveQuadratic */
 static double update_point(const lm_t *m, long i) {
     const double aa = 9.0 / 4.0, one_third = 1.0 / 3.0;
@@ -179,11 +188,12 @@ static double update_point(const lm_t *m, long i) {
     }
     c -= 1;
     double det = b * b - 4 * a * c;
-    if (det > 0) {
+    if (g_old_det ? det > 0 : det >= 0) {
         if (m->phi[i] > DBL_EPSILON) return (-b + sqrt(det)) / 2.0 / a;
         return (-b - sqrt(det)) / 2.0 / a;
     }
-    return 0.0;
+    if (g_old_det || a == 0) return 0.0;
+    return -b / (2.0 * a);
 }
 
 /* Same contract as orc_fmm_distance: dist_out = signed distance (0 where never frozen),
