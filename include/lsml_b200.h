@@ -138,18 +138,52 @@ int lsml_assemble_features(int nfeat, const int *kind, const int *a, const int *
 int lsml_linear_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
                         const double *scale, const double *coef, double intercept, double *out,
                         void *stream);
-/* nodes: 8-byte packed nodes (see regress.cu); tree_base: int[n_trees + 1], first node of each
- * tree followed by the total node count; divisor = n_estimators */
+/* nodes: 32-byte super nodes (an internal node and its two children per entry, see regress.cu;
+ * 32-byte aligned); leaves: float64 leaf values; root_ref: unsigned[n_trees], the root super
+ * node of each tree or -- root_is_leaf[t] != 0 -- the leaf index of a single-leaf tree;
+ * divisor = n_estimators */
 int lsml_forest_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
-                        const double *scale, const void *nodes, const int *tree_base,
-                        const uint8_t *root_is_leaf, int n_trees, double divisor, double *out,
-                        void *stream);
+                        const double *scale, const void *nodes, const double *leaves,
+                        const unsigned *root_ref, const uint8_t *root_is_leaf, int n_trees,
+                        double divisor, double *out, void *stream);
 /* sizes: HOST int[n_layers+1]; W, b: HOST arrays of n_layers DEVICE pointers;
  * act: 0 identity, 1 relu, 2 tanh, 3 logistic */
 int lsml_mlp_predict(const double *X, const long long *n_band, const double *mean,
                      const double *scale, int n_layers, const int *sizes,
                      const double *const *W, const double *const *b, int act, double *out,
                      void *stream);
+
+/* The same three regressors with the FEATURE PROGRAM as their input instead of a materialised
+ * matrix: row b of the virtual matrix is FeatureMap(...)[band voxel b] (feature_map.py:53-80),
+ * gathered from the image planes and per-item scalars inside the kernel and never written to
+ * memory.  This is what the evolution loop (model.py:384-388) runs.  kind/a/b, shape, dx: HOST
+ * arrays as for lsml_assemble_features; the other pointers are DEVICE arrays. */
+typedef struct lsml_band_source {
+    int nfeat;
+    const int *kind, *a, *b;
+    int ndim;
+    const int *shape;
+    long long batch;
+    const double *dx;
+    const long long *band_idx;
+    const double *planes;
+    long long plane_stride;
+    const double *item_feat;
+    const double *com;
+    int origin0;          /* first axis-0 plane of a slab's local grid in the whole volume, else 0 */
+} lsml_band_source;
+int lsml_linear_predict_band(const lsml_band_source *src, const long long *n_band,
+                             const double *mean, const double *scale, const double *coef,
+                             double intercept, double *out, void *stream);
+int lsml_forest_predict_band(const lsml_band_source *src, const long long *n_band,
+                             const double *mean, const double *scale, const void *nodes,
+                             const double *leaves, const unsigned *root_ref,
+                             const uint8_t *root_is_leaf, int n_trees, double divisor, double *out,
+                             void *stream);
+int lsml_mlp_predict_band(const lsml_band_source *src, const long long *n_band, const double *mean,
+                          const double *scale, int n_layers, const int *sizes,
+                          const double *const *W, const double *const *b, int act, double *out,
+                          void *stream);
 
 /* ---- banded update u[mask] += step*v*|Du|_upwind (model.py:390-394) ------------------------- */
 /* new_u[b] receives the updated value of band voxel b; with apply != 0 it is also scattered

@@ -58,6 +58,15 @@ def ptr(t):
     return c_p(t.ctypes.data)
 
 
+class BandSource(ctypes.Structure):
+    """``lsml_band_source`` of include/lsml_b200.h: the feature program plus the device buffers
+    it reads, handed to the ``lsml_*_predict_band`` entry points."""
+    _fields_ = [("nfeat", ctypes.c_int), ("kind", c_p), ("a", c_p), ("b", c_p),
+                ("ndim", ctypes.c_int), ("shape", c_p), ("batch", c_i64), ("dx", c_p),
+                ("band_idx", c_p), ("planes", c_p), ("plane_stride", c_i64),
+                ("item_feat", c_p), ("com", c_p), ("origin0", ctypes.c_int)]
+
+
 def current_stream():
     import torch
     return c_p(torch.cuda.current_stream().cuda_stream)

@@ -197,7 +197,12 @@ class BandEngine:
             self.mask = torch.zeros(full, dtype=torch.uint8, device=d)
             self.planes = torch.zeros((max(len(self.program.planes), 1),) + full, dtype=f64, device=d)
             self.stats = torch.zeros((self.batch, 8), dtype=torch.int64, device=d)
+            # band size / indices: two buffers each, swapped on every compaction, so that the
+            # band an iteration ran on (its sparse record, and the start set of the next rebuild)
+            # stays valid without a copy
             self.n_band_dev = torch.zeros(1, dtype=i64, device=d)
+            self._n_band_prev_dev = torch.zeros(1, dtype=i64, device=d)
+            self.units_dev = torch.zeros(1, dtype=i64, device=d)   # sum of band sizes stepped
             self.item_offsets = torch.zeros(self.batch + 1, dtype=i64, device=d)
             self.band_idx = torch.zeros(1, dtype=i64, device=d)
             self._band_idx_prev = torch.zeros(1, dtype=i64, device=d)
@@ -223,10 +228,9 @@ class BandEngine:
             self._ws_fmm = None       # allocated on the first band rebuild
         self._weights = {}            # (sigma, order) -> (device weights, radius)
         self._tmp_plane = None
-        self.n_band = 0
-        self._cap = 0
+        self._n_band_host = 0         # host copy of n_band_dev, None = not read back yet
         self.X = self.vel = self.new_u = None
-        self.band_voxel_iterations = 0
+        self._src = None              # lsml_band_source handed to the fused velocity kernels
         self.history = None           # list of (band_idx, new_u) per iteration when recording
         self.last_fmm_counters = None
         self._band_is_rebuilt = False
@@ -247,16 +251,38 @@ class BandEngine:
         return {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v)))
                 for k, v in (self.timers or {}).items()}
 
-    def _ensure_capacity(self, n):
-        if n <= self._cap:
-            return
-        cap = min(self.total, max(int(n * 1.5) + 1024, 4096))
-        cap = max(cap, n)
-        d, f64 = self.device, torch.float64
-        self.X = torch.empty((cap, max(self.program.nfeat, 1)), dtype=f64, device=d)
-        self.vel = torch.zeros(cap, dtype=f64, device=d)
-        self.new_u = torch.empty(cap, dtype=f64, device=d)
-        self._cap = cap
+    # The band size lives on the device (n_band_dev); every kernel of an iteration reads it
+    # there, so `step` never waits for the host.  The host copy is fetched on demand.
+    @property
+    def n_band(self):
+        if self._n_band_host is None:
+            self._n_band_host = int(self.n_band_dev.item())
+        return self._n_band_host
+
+    @n_band.setter
+    def n_band(self, value):
+        self._n_band_host = None if value is None else int(value)
+
+    @property
+    def band_voxel_iterations(self):
+        """Sum of the band sizes of all iterations stepped so far (one host read)."""
+        return int(self.units_dev.item())
+
+    def _ensure_band_buffers(self):
+        """Per-band-voxel velocity and updated value: sized for the largest possible band (the
+        whole grid: band == 0, or u == 0 everywhere), so that no iteration has to know its band
+        size on the host."""
+        if self.vel is None:
+            self.vel = torch.zeros(self.total, dtype=torch.float64, device=self.device)
+            self.new_u = torch.empty(self.total, dtype=torch.float64, device=self.device)
+
+    def _ensure_X(self, n):
+        """The materialised feature matrix (FeatureMap.__call__, fit): only on request."""
+        n = max(int(n), 1)
+        if self.X is None or self.X.shape[0] < n:
+            cap = min(self.total, max(int(n * 1.25) + 1024, 4096))
+            self.X = torch.empty((max(cap, n), max(self.program.nfeat, 1)), dtype=torch.float64,
+                                 device=self.device)
 
     # ------------------------------------------------------------------ images
     def load_images(self, imgs, normalize=True):
@@ -439,16 +465,17 @@ class BandEngine:
         return dist
 
     def _compact(self):
-        # two index buffers, swapped on every compaction: the previous band's indices stay valid
-        # (they are the sparse record of the iteration that just ran) without a copy
+        # two index / count buffers, swapped on every compaction: the previous band stays valid
+        # (it is the sparse record of the iteration that just ran) without a copy
         self.band_idx, self._band_idx_prev = self._band_idx_prev, self.band_idx
+        self.n_band_dev, self._n_band_prev_dev = self._n_band_prev_dev, self.n_band_dev
         if self.band_idx.numel() < self.total:
             # capacity: the band can be the whole grid (band == 0 or u == 0 everywhere)
             self.band_idx = torch.empty(self.total, dtype=torch.int64, device=self.device)
         with self._phase("compact"):
             self._compact_launch()
-        self.n_band = int(self.n_band_dev.item())      # one host sync per iteration (capacity)
-        self._ensure_capacity(self.n_band)
+        self._n_band_host = None                       # read back only when somebody asks
+        self._ensure_band_buffers()
 
     def _compact_launch(self):
         _lib.check(_lib.lib.lsml_compact_mask(
@@ -457,11 +484,10 @@ class BandEngine:
             _lib.ptr(self._ws_compact), self._stream()), "compact_mask")
 
     # ------------------------------------------------------------------ features
-    def compute_features(self):
-        """FeatureMap on the current band -> X[:n_band] (band order)."""
+    def _item_level_features(self):
+        """Everything a feature column needs besides the voxel itself: level-set dependent
+        planes, band statistics, boundary measure, the per-item scalars and centres of mass."""
         pr = self.program
-        if self.n_band == 0 or pr.nfeat == 0:
-            return self.X[:0] if self.X is not None else None
         npl = len(pr.planes)
         stride = self.total
         if pr.needs_u_planes:
@@ -482,30 +508,59 @@ class BandEngine:
             _lib.c_i64(self.batch), self._dx_c, ctypes.c_int(max(npl, 1)), _lib.ptr(self.stats),
             _lib.ptr(self.band_mean), _lib.ptr(self.band_std), _lib.ptr(self.boundary),
             _lib.ptr(self.item_feat), _lib.ptr(self.com), self._stream()), "item_features")
+
+    def compute_features(self):
+        """FeatureMap on the current band -> X[:n_band] (band order), materialised: for
+        ``FeatureMap.__call__`` and for the regression matrix of ``fit``.  The evolution loop
+        does not come here (see :meth:`step`)."""
+        pr = self.program
+        nb = self.n_band
+        if nb == 0 or pr.nfeat == 0:
+            self._ensure_X(1)
+            return self.X[:0]
+        self._ensure_X(nb)
+        self._item_level_features()
         _lib.check(_lib.lib.lsml_assemble_features(
             ctypes.c_int(pr.nfeat), pr.kind, pr.a, pr.b, ctypes.c_int(self.ndim), self._shape_c,
             _lib.c_i64(self.batch), self._dx_c, _lib.ptr(self.band_idx), _lib.ptr(self.n_band_dev),
-            _lib.ptr(self.planes), _lib.c_i64(stride), _lib.ptr(self.item_feat),
+            _lib.ptr(self.planes), _lib.c_i64(self.total), _lib.ptr(self.item_feat),
             _lib.ptr(self.com), _lib.ptr(self.X), self._stream()), "assemble_features")
-        return self.X[:self.n_band]
+        return self.X[:nb]
+
+    def band_source(self, origin0=0):
+        """``lsml_band_source``: the feature program and the device buffers it reads, for the
+        fused velocity kernels (no materialised matrix)."""
+        pr = self.program
+        if self._src is None:
+            self._src = _lib.BandSource(
+                nfeat=pr.nfeat, kind=ctypes.cast(pr.kind, ctypes.c_void_p),
+                a=ctypes.cast(pr.a, ctypes.c_void_p), b=ctypes.cast(pr.b, ctypes.c_void_p),
+                ndim=self.ndim, shape=ctypes.cast(self._shape_c, ctypes.c_void_p),
+                batch=self.batch, dx=ctypes.cast(self._dx_c, ctypes.c_void_p),
+                band_idx=0, planes=self.planes.data_ptr(), plane_stride=self.total,
+                item_feat=self.item_feat.data_ptr(), com=self.com.data_ptr(), origin0=0)
+        self._src.band_idx = self.band_idx.data_ptr()       # swapped on every compaction
+        self._src.origin0 = int(origin0)
+        return self._src
 
     # ------------------------------------------------------------------ one iteration
     def step(self, regressor, step, rebuild=True, record=False):
-        """One evolution iteration of every item.  Returns the number of band voxels updated."""
+        """One evolution iteration of every item (lsml/core/model.py:381-397).  Nothing in here
+        waits for the device: the band size stays in HBM, the velocity kernel evaluates the
+        feature columns itself (no feature matrix), and an empty band (`if mask.any()`,
+        model.py:381) simply makes every launch a no-op.  ``record``: keep a copy of this
+        iteration's sparse record (band indices, new values) in ``self.history`` -- that one
+        needs the band size on the host."""
         with torch.cuda.device(self.device):
-            nb = self.n_band
-            if nb == 0:                       # `if mask.any()` (model.py:381): nothing to do
-                if record and self.history is not None:
-                    self.history.append(None)
-                return 0
             reg = export_regressor(regressor, self.device)
             if reg.n_features != self.program.nfeat:
                 raise ValueError("regressor expects {} features, feature map has {}".format(
                     reg.n_features, self.program.nfeat))
+            self._ensure_band_buffers()
             with self._phase("features"):
-                self.compute_features()
+                self._item_level_features()
             with self._phase("predict"):
-                reg.predict_into(self.X, self.n_band_dev, self.vel)
+                reg.predict_band(self.band_source(), self.n_band_dev, self.vel)
             # u[mask] += step*v*|Du| and, in the same scatter, the exact {u > 0} statistics of the
             # new u (no dense recount)
             with self._phase("update"):
@@ -515,19 +570,19 @@ class BandEngine:
                     _lib.ptr(self.n_band_dev), ctypes.c_double(float(step)),
                     _lib.ptr(self.new_u), _lib.c_p(0), _lib.ptr(self.stats), self._stream()),
                     "band_update")
-            # band indices of THIS iteration; together with new_u[:nb] this is the sparse record
-            # `segment` rebuilds the iterates from.  The rebuild below compacts into the OTHER
-            # index buffer, so this view stays valid until the next iteration's rebuild.
-            self._last_idx = self.band_idx[:nb]
-            # (the view keeps the storage alive if the rebuild below has to grow the buffers)
-            self._last_new_u = self.new_u[:nb]
+            self.units_dev.add_(self.n_band_dev)
             if record:
+                nb = self.n_band
                 if self.history is None:
                     self.history = []
-                self.history.append((self._last_idx.clone(), self._last_new_u.clone()))
-            self.band_voxel_iterations += nb
+                self.history.append((self.band_idx[:nb].clone(), self.new_u[:nb].clone())
+                                    if nb else None)
             if rebuild:
                 self._rebuild_band(from_band=True)
             else:
                 self._band_is_rebuilt = False     # u moved on; the band no longer brackets it
-            return nb
+
+    def last_record(self, nb):
+        """(band indices, new values) of the iteration :meth:`step` just ran, ``nb`` being the
+        band size BEFORE that step; views, valid until the next step."""
+        return self._band_idx_prev[:nb], self.new_u[:nb]

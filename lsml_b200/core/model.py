@@ -400,11 +400,12 @@ class LevelSetMachineLearning:
         after(0)
         for i in range(n_iters):
             nb = eng.n_band
-            eng.step(self._device_model(i, eng.device), self._step)
             us[i + 1] = us[i]
-            if nb:
+            if nb:                # `if mask.any()` (model.py:381)
+                eng.step(self._device_model(i, eng.device), self._step)
                 # the sparse record of this iteration: band indices and their new values
-                us[i + 1].ravel()[eng._last_idx.cpu().numpy()] = eng._last_new_u.cpu().numpy()
+                idx, val = eng.last_record(nb)
+                us[i + 1].ravel()[idx.cpu().numpy()] = val.cpu().numpy()
             if verbose:
                 print(print_string.format(i + 1))
             after(i + 1)

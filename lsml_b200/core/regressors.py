@@ -37,6 +37,11 @@ class DeviceRegressor:
     def predict_into(self, X, n_band, out):
         raise NotImplementedError
 
+    def predict_band(self, src, n_band, out):
+        """Velocity of every band voxel with the feature program ``src`` (a
+        :class:`lsml_b200._lib.BandSource`) as the input: no materialised matrix."""
+        raise NotImplementedError
+
     def predict(self, X):
         """Convenience: X CUDA tensor (B, F) -> CUDA tensor (B,)."""
         X = X.contiguous()
@@ -59,6 +64,12 @@ class LinearDeviceRegressor(DeviceRegressor):
             _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
             _lib.ptr(self.scale), _lib.ptr(self.coef), ctypes.c_double(self.intercept),
             _lib.ptr(out), _lib.current_stream()), "linear_predict")
+
+    def predict_band(self, src, n_band, out):
+        _lib.check(_lib.lib.lsml_linear_predict_band(
+            ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean),
+            _lib.ptr(self.scale), _lib.ptr(self.coef), ctypes.c_double(self.intercept),
+            _lib.ptr(out), _lib.current_stream()), "linear_predict_band")
 
 
 def _round_down_to_f32(thr):
@@ -121,7 +132,69 @@ def pack_trees(trees, n_features):
             np.asarray(root_leaf, dtype=np.uint8))
 
 
+def pack_supernodes(nodes, bases, root_is_leaf):
+    """The single-node packing of :func:`pack_trees` -> the layout the kernels walk (regress.cu):
+
+    ``snodes`` uint32[S, 8]: one 32-byte super node per internal node of EVEN depth, holding that
+    node and its two children -- thresholds (node, left, right) as float32 bits, then
+    ``feature0 | featureL << 8 | featureR << 16 | flags << 24`` (flags bit 0 / 1: the left / right
+    child is a leaf; bits 2..5: grandchild LL, LR, RL, RR is a leaf), then four references: per
+    grandchild the index of its super node or of its leaf value; for a leaf child ``ref[2*side]``
+    is that child's leaf index.  ``leaves`` float64[L], ``root_ref`` uint32[T] (root super node, or
+    the leaf index of a single-leaf tree).  Two tree levels per fetch; same decisions, same leaf,
+    same float64 value as the single-node walk."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+    bases = np.asarray(bases, dtype=np.int64)
+    root_is_leaf = np.asarray(root_is_leaf, dtype=np.uint8)
+    n, T = nodes.shape[0], len(root_is_leaf)
+    meta = nodes[:, 1].astype(np.int64)
+    tree_of = np.repeat(np.arange(T), np.diff(bases))
+    left = bases[tree_of] + (meta & 0x3fffff)           # valid for internal nodes only
+    lleaf, rleaf = (meta >> 23) & 1, (meta >> 22) & 1
+    feat = (meta >> 24) & 0xff
+    is_leaf = np.zeros(n, dtype=bool)
+    depth = np.zeros(n, dtype=np.int64)
+    roots = bases[:-1]
+    is_leaf[roots] = root_is_leaf != 0
+    frontier = roots[root_is_leaf == 0]
+    while frontier.size:
+        L = left[frontier]
+        is_leaf[L], is_leaf[L + 1] = lleaf[frontier] != 0, rleaf[frontier] != 0
+        depth[L] = depth[L + 1] = depth[frontier] + 1
+        kids = np.concatenate([L, L + 1])
+        frontier = kids[~is_leaf[kids]]
+    sup = ~is_leaf & (depth % 2 == 0)
+    sid = np.cumsum(sup) - 1
+    lid = np.cumsum(is_leaf) - 1
+    leaves = np.ascontiguousarray(nodes[is_leaf]).view(np.float64).ravel().copy()
+    S = np.flatnonzero(sup)
+    out = np.zeros((S.size, 8), dtype=np.uint32)
+    out[:, 0] = nodes[S, 0]
+    ff = feat[S].copy()
+    flags = lleaf[S] | (rleaf[S] << 1)
+    for side in (0, 1):
+        child = left[S] + side
+        cl = is_leaf[child]
+        # leaf child: its leaf index in ref[2 * side]
+        out[cl, 4 + 2 * side] = lid[child[cl]]
+        ci = child[~cl]
+        out[~cl, 1 + side] = nodes[ci, 0]
+        ff[~cl] |= feat[ci] << (8 * (1 + side))
+        for gs in (0, 1):
+            g = left[ci] + gs
+            gl = is_leaf[g]
+            out[~cl, 4 + 2 * side + gs] = np.where(gl, lid[g], sid[g])
+            flags[~cl] |= gl.astype(np.int64) << (2 + 2 * side + gs)
+    out[:, 3] = (ff | (flags << 24)).astype(np.uint32)
+    root_ref = np.where(root_is_leaf != 0, lid[roots], sid[roots]).astype(np.uint32)
+    return out, leaves, root_ref, root_is_leaf.copy()
+
+
 class ForestDeviceRegressor(DeviceRegressor):
+    """``nodes`` / ``tree_base`` / ``root_is_leaf`` are the canonical single-node export
+    (:func:`pack_trees`, also what the golden fixtures store); the kernels walk the super-node
+    layout derived from it on first use."""
+
     def __init__(self, trees, n_features, divisor, scaler, device):
         super().__init__(n_features, scaler, device)
         nodes, bases, root_leaf = pack_trees(trees, n_features)
@@ -131,14 +204,38 @@ class ForestDeviceRegressor(DeviceRegressor):
         self.tree_base = _dev(bases, device)
         self.root_is_leaf = _dev(root_leaf, device)
         self.divisor = float(divisor)
+        self._super = self._pack_super(nodes, bases, root_leaf)
+
+    def _pack_super(self, nodes, bases, root_leaf):
+        sn, leaves, root_ref, _ = pack_supernodes(nodes, bases, root_leaf)
+        if sn.shape[0] == 0:
+            sn = np.zeros((1, 8), dtype=np.uint32)
+        # torch's allocator hands out 512-byte aligned blocks: the 32-byte alignment holds
+        return (_dev(sn, self.device), _dev(leaves, self.device), _dev(root_ref, self.device))
+
+    def _layout(self):
+        if getattr(self, "_super", None) is None:      # built around exported arrays (fixtures)
+            self._super = self._pack_super(self.nodes.cpu().numpy(), self.tree_base.cpu().numpy(),
+                                           self.root_is_leaf.cpu().numpy())
+        return self._super
 
     def predict_into(self, X, n_band, out):
+        sn, leaves, root_ref = self._layout()
         _lib.check(_lib.lib.lsml_forest_predict(
             _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
-            _lib.ptr(self.scale), _lib.ptr(self.nodes), _lib.ptr(self.tree_base),
+            _lib.ptr(self.scale), _lib.ptr(sn), _lib.ptr(leaves), _lib.ptr(root_ref),
             _lib.ptr(self.root_is_leaf), ctypes.c_int(self.n_trees),
             ctypes.c_double(self.divisor), _lib.ptr(out), _lib.current_stream()),
             "forest_predict")
+
+    def predict_band(self, src, n_band, out):
+        sn, leaves, root_ref = self._layout()
+        _lib.check(_lib.lib.lsml_forest_predict_band(
+            ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean),
+            _lib.ptr(self.scale), _lib.ptr(sn), _lib.ptr(leaves), _lib.ptr(root_ref),
+            _lib.ptr(self.root_is_leaf), ctypes.c_int(self.n_trees),
+            ctypes.c_double(self.divisor), _lib.ptr(out), _lib.current_stream()),
+            "forest_predict_band")
 
 
 _ACT = {"identity": 0, "relu": 1, "tanh": 2, "logistic": 3}
@@ -154,14 +251,25 @@ class MlpDeviceRegressor(DeviceRegressor):
         self.sizes = [coefs[0].shape[0]] + [w.shape[1] for w in coefs]
         self.act = _ACT[activation]
 
-    def predict_into(self, X, n_band, out):
+    def _layers(self):
         n = len(self.W)
         Wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in self.W])
         bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in self.b])
+        return n, Wp, bp
+
+    def predict_into(self, X, n_band, out):
+        n, Wp, bp = self._layers()
         _lib.check(_lib.lib.lsml_mlp_predict(
             _lib.ptr(X), _lib.ptr(n_band), _lib.ptr(self.mean), _lib.ptr(self.scale),
             ctypes.c_int(n), _lib.int_array(self.sizes), Wp, bp, ctypes.c_int(self.act),
             _lib.ptr(out), _lib.current_stream()), "mlp_predict")
+
+    def predict_band(self, src, n_band, out):
+        n, Wp, bp = self._layers()
+        _lib.check(_lib.lib.lsml_mlp_predict_band(
+            ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean), _lib.ptr(self.scale),
+            ctypes.c_int(n), _lib.int_array(self.sizes), Wp, bp, ctypes.c_int(self.act),
+            _lib.ptr(out), _lib.current_stream()), "mlp_predict_band")
 
 
 def export_regressor(model, device="cuda"):

@@ -315,7 +315,7 @@ class SlabRank:
         e.n_band = int(e.n_band_dev.item())
         e.item_offsets[0] = 0
         e.item_offsets[1] = e.n_band
-        e._ensure_capacity(max(e.n_band, 1))
+        e._ensure_band_buffers()
 
     # -------------------------------------------------------------------------------- features
     def band_sums(self, mode, mean):
@@ -339,19 +339,26 @@ class SlabRank:
             _lib.c_i64(1), e._dx_c, ctypes.c_int(max(npl, 1)), _lib.ptr(stats_global),
             _lib.ptr(e.band_mean), _lib.ptr(e.band_std), _lib.ptr(e.boundary),
             _lib.ptr(e.item_feat), _lib.ptr(e.com), e._stream()), "item_features")
+
+    def feature_matrix(self):
+        """The materialised (n_band, F) matrix of the owned band (tests / training only; the
+        evolution step evaluates the columns inside the velocity kernel)."""
+        e, pr = self.eng, self.eng.program
+        e._ensure_X(e.n_band)
         if e.n_band:
             _lib.check(_lib.lib.lsml_assemble_features_origin(
                 ctypes.c_int(pr.nfeat), pr.kind, pr.a, pr.b, ctypes.c_int(3), e._shape_c,
                 _lib.c_i64(1), e._dx_c, _lib.ptr(e.band_idx), _lib.ptr(e.n_band_dev),
                 _lib.ptr(e.planes), _lib.c_i64(e.total), _lib.ptr(e.item_feat), _lib.ptr(e.com),
                 _lib.ptr(e.X), ctypes.c_int(self.origin0), e._stream()), "assemble_features")
+        return e.X[:e.n_band]
 
     def predict_and_update(self, regressor, step):
         e = self.eng
         if not e.n_band:
             return
         reg = export_regressor(regressor, self.device)
-        reg.predict_into(e.X, e.n_band_dev, e.vel)
+        reg.predict_band(e.band_source(origin0=self.origin0), e.n_band_dev, e.vel)
         _lib.check(_lib.lib.lsml_band_update_stats(
             ctypes.c_int(3), e._shape_c, _lib.c_i64(1), e._dx_c, _lib.ptr(e.u), _lib.ptr(e.vel),
             _lib.ptr(e.band_idx), _lib.ptr(e.n_band_dev), ctypes.c_double(float(step)),

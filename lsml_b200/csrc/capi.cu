@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <atomic>
 #include "lsml_internal.h"
+#include "band_features.cuh"
 #include "../../include/lsml_b200.h"
 
 namespace lsml {
@@ -291,17 +292,63 @@ int lsml_linear_predict(const double* X, const long long* n_band, int nfeat, con
     return linear_predict(X, n_band, nfeat, mean, scale, coef, intercept, out, (cudaStream_t)stream);
 }
 int lsml_forest_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
-                        const double* scale, const void* nodes, const int* tree_base,
-                        const uint8_t* root_is_leaf, int n_trees, double divisor, double* out,
-                        void* stream) {
-    return forest_predict(X, n_band, nfeat, mean, scale, nodes, tree_base, root_is_leaf, n_trees,
-                          divisor, out, (cudaStream_t)stream);
+                        const double* scale, const void* nodes, const double* leaves,
+                        const unsigned* root_ref, const uint8_t* root_is_leaf, int n_trees,
+                        double divisor, double* out, void* stream) {
+    return forest_predict(X, n_band, nfeat, mean, scale, nodes, leaves, root_ref, root_is_leaf,
+                          n_trees, divisor, out, (cudaStream_t)stream);
 }
 int lsml_mlp_predict(const double* X, const long long* n_band, const double* mean,
                      const double* scale, int n_layers, const int* sizes,
                      const double* const* W, const double* const* b, int act, double* out,
                      void* stream) {
     return mlp_predict(X, n_band, mean, scale, n_layers, sizes, W, b, act, out, (cudaStream_t)stream);
+}
+
+// the feature program as the source of the regressor's inputs (no materialised matrix)
+static int band_source(const lsml_band_source* src, BandFeatures& bf) {
+    if (src == nullptr) { set_error("band source is NULL"); return 1; }
+    const int ndim = src->ndim;
+    const int* shape = src->shape;
+    const long long batch = src->batch;
+    const double* dx = src->dx;
+    GEOM(g);
+    FeatProgram prog;
+    if (fill_program(prog, src->nfeat, src->kind, src->a, src->b)) return 1;
+    for (int f = 0; f < src->nfeat; ++f)
+        if (src->kind[f] == 8 /* FK_COM_RAY */ && (src->origin0 != 0 || ndim < 2)) {
+            set_error("COMRaySample needs the whole 2-D/3-D image on one device");
+            return 1;
+        }
+    bf = make_band_features(prog, g, src->band_idx, src->planes, src->plane_stride,
+                            src->item_feat, src->com, src->origin0);
+    return 0;
+}
+int lsml_linear_predict_band(const lsml_band_source* src, const long long* n_band,
+                             const double* mean, const double* scale, const double* coef,
+                             double intercept, double* out, void* stream) {
+    BandFeatures bf;
+    if (band_source(src, bf)) return 1;
+    return linear_predict_band(bf, n_band, mean, scale, coef, intercept, out, (cudaStream_t)stream);
+}
+int lsml_forest_predict_band(const lsml_band_source* src, const long long* n_band,
+                             const double* mean, const double* scale, const void* nodes,
+                             const double* leaves, const unsigned* root_ref,
+                             const uint8_t* root_is_leaf, int n_trees, double divisor, double* out,
+                             void* stream) {
+    BandFeatures bf;
+    if (band_source(src, bf)) return 1;
+    return forest_predict_band(bf, n_band, mean, scale, nodes, leaves, root_ref, root_is_leaf,
+                               n_trees, divisor, out, (cudaStream_t)stream);
+}
+int lsml_mlp_predict_band(const lsml_band_source* src, const long long* n_band, const double* mean,
+                          const double* scale, int n_layers, const int* sizes,
+                          const double* const* W, const double* const* b, int act, double* out,
+                          void* stream) {
+    BandFeatures bf;
+    if (band_source(src, bf)) return 1;
+    return mlp_predict_band(bf, n_band, mean, scale, n_layers, sizes, W, b, act, out,
+                            (cudaStream_t)stream);
 }
 int lsml_band_update(int ndim, const int* shape, long long batch, const double* dx, double* u,
                      const double* vel, const long long* band_idx, const long long* n_band,

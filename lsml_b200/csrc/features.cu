@@ -16,7 +16,7 @@
 //   item_features_kernel  turns the raw sums into the per-item ("global") feature values
 //   assemble_kernel       writes the (B, F) feature matrix in band order (feature_map.py:53-80)
 #include "lsml_internal.h"
-#include "com_ray.cuh"
+#include "band_features.cuh"
 
 namespace lsml {
 
@@ -286,52 +286,9 @@ contour_length_kernel(const double* __restrict__ u, int m, int n, double sr, dou
     if (threadIdx.x == 0) partial[(i64)item * gridDim.x + blockIdx.x] = t;
 }
 
-// [host-test:begin] (tests/test_feature_kernels_host.py compiles this region with g++: the two
-// kernels below have no block-level cooperation, so one host "thread" can run them as they are)
-// ---------------------------------------------------------------------------------------------
-// per-item ("global") feature values
-// ---------------------------------------------------------------------------------------------
-enum FeatKind {
-    FK_PLANE = 0,       // a = plane index (local)
-    FK_DIST_COM = 1,    // local
-    FK_BAND_MEAN = 2,   // a = plane index
-    FK_BAND_STD = 3,    // a = plane index
-    FK_SIZE = 4,
-    FK_BOUNDARY = 5,
-    FK_ISOPERIMETRIC = 6,
-    FK_MOMENT = 7,      // a = axis (0..ndim-1), b = order (1 or 2)
-    FK_COM_RAY = 8,     // a = plane index of the raw image, b = sample j | (n_samples << 16) (local)
-};
-
-struct FeatProgram {
-    int nfeat;
-    int kind[64];
-    int a[64];
-    int b[64];
-};
-
-struct ItemGeom {
-    int ndim;
-    int pad;           // 3 - ndim
-    double dx[3];      // padded
-    double pdx;        // prod(dx) over real axes, multiplied left to right
-    int origin0;       // index of the local grid's first axis-0 plane in the whole volume (slabs)
-    int n0;            // extent of the (padded) first axis
-};
-
-// moment of `order` along padded axis ax from the exact integer sums
-__device__ double moment_from_stats(const u64* st, int ax, int order, double dx, double pdx) {
-    const double cnt = (double)st[0];
-    const double measure = cnt * pdx;                       // Size: (u>0).sum()*prod(dx)
-    if (order == 1) return ((double)st[1 + ax] * dx) * pdx / measure;   // shape.py:227-228
-    // order 2: sum (x - c)^2 with c the centroid = (N*Sxx - Sx^2)/N exactly (128-bit integers)
-    const unsigned __int128 N = st[0], Sx = st[1 + ax], Sxx = st[4 + ax];
-    const unsigned __int128 num = N * Sxx - Sx * Sx;
-    const double numd = (double)(u64)(num >> 64) * 18446744073709551616.0 + (double)(u64)num;
-    const double ssd = (numd / cnt) * (dx * dx);
-    return ssd * pdx / measure;
-}
-
+// [host-test:begin] (tests/test_feature_kernels_host.py compiles this region with g++, after the
+// marked region of band_features.cuh: the two kernels below have no block-level cooperation, so
+// one host "thread" can run them as they are)
 __global__ void item_features_kernel(FeatProgram prog, ItemGeom geo, i64 batch, int nplanes,
                                      const u64* __restrict__ stats,
                                      const double* __restrict__ band_mean,
@@ -374,48 +331,14 @@ __global__ void item_features_kernel(FeatProgram prog, ItemGeom geo, i64 batch, 
 // feature index fastest => fully coalesced 8-byte stores of the row-major matrix.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-assemble_kernel(FeatProgram prog, ItemGeom geo, int n1, int n2, i64 voxels,
-                const i64* __restrict__ band_idx, const i64* __restrict__ n_band,
-                const double* __restrict__ planes, i64 plane_stride,
-                const double* __restrict__ item_feat, const double* __restrict__ com,
-                double* __restrict__ X) {
+assemble_kernel(BandFeatures src, const i64* __restrict__ n_band, double* __restrict__ X) {
     const i64 nb = *n_band;
-    const i64 total = nb * prog.nfeat;
+    const i64 total = nb * src.prog.nfeat;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (i64)gridDim.x * blockDim.x) {
-        const i64 b = t / prog.nfeat;
-        const int f = (int)(t - b * prog.nfeat);
-        const i64 g = __ldg(band_idx + b);
-        const i64 item = g / voxels;
-        double v;
-        const int kind = prog.kind[f];
-        if (kind == FK_PLANE) {
-            v = __ldg(planes + (i64)prog.a[f] * plane_stride + g);
-        } else if (kind == FK_DIST_COM) {
-            const i64 loc = g - item * voxels;
-            const int k = (int)(loc % n2);
-            const i64 r = loc / n2;
-            const int j = (int)(r % n1), i = (int)(r / n1);
-            const double* c = com + item * 3;
-            // numpy.linalg.norm(mesh - com, axis=0): ((d0^2 + d1^2) + d2^2) over the real axes
-            double acc = 0.0;
-            if (geo.ndim == 3) { const double d = (i + geo.origin0) * geo.dx[0] - c[0]; acc = d * d; }
-            if (geo.ndim >= 2) { const double d = j * geo.dx[1] - c[1]; acc = geo.ndim == 2 ? d * d : acc + d * d; }
-            { const double d = k * geo.dx[2] - c[2]; acc = geo.ndim == 1 ? d * d : acc + d * d; }
-            v = sqrt(acc);
-        } else if (kind == FK_COM_RAY) {
-            // COMRaySample (image.py:147-171): the raw image along the voxel -> centroid ray
-            const i64 loc = g - item * voxels;
-            const i64 r = loc / n2;
-            const int idx[3] = {(int)(r / n1) + geo.origin0, (int)(r % n1), (int)(loc % n2)};
-            const int ext[3] = {geo.n0, n1, n2};
-            v = com_ray_sample(planes + (i64)prog.a[f] * plane_stride + item * voxels, geo.ndim,
-                               ext, geo.dx, com + item * 3, idx, prog.b[f] & 0xffff,
-                               prog.b[f] >> 16);
-        } else {
-            v = item_feat[item * prog.nfeat + f];
-        }
-        X[t] = v;
+        const i64 b = t / src.prog.nfeat;
+        const int f = (int)(t - b * src.prog.nfeat);
+        X[t] = band_feature(src, voxel_ref(src, __ldg(src.band_idx + b)), f);
     }
 }
 // [host-test:end]
@@ -591,16 +514,27 @@ int item_features(const FeatProgram& prog, const Geom& g, int nplanes, const u64
     return 0;
 }
 
+BandFeatures make_band_features(const FeatProgram& prog, const Geom& g, const i64* band_idx,
+                                const double* planes, i64 plane_stride, const double* item_feat,
+                                const double* com, int origin0) {
+    BandFeatures src;
+    src.prog = prog;
+    src.geo.ndim = g.ndim; src.geo.pad = 3 - g.ndim;
+    for (int a = 0; a < 3; ++a) src.geo.dx[a] = g.dx[a];
+    src.geo.pdx = 1.0; src.geo.origin0 = origin0; src.geo.n0 = g.n[0];
+    src.n1 = g.n[1]; src.n2 = g.n[2]; src.voxels = g.voxels;
+    src.band_idx = band_idx; src.planes = planes; src.plane_stride = plane_stride;
+    src.item_feat = item_feat; src.com = com;
+    return src;
+}
+
 int assemble_features(const FeatProgram& prog, const Geom& g, const i64* band_idx,
                       const i64* n_band, const double* planes, i64 plane_stride,
                       const double* item_feat, const double* com, double* X, int origin0,
                       cudaStream_t s) {
-    ItemGeom geo;
-    geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
-    for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
-    geo.pdx = 1.0; geo.origin0 = origin0; geo.n0 = g.n[0];
-    assemble_kernel<<<LSML_SMS * 8, 256, 0, s>>>(prog, geo, g.n[1], g.n[2], g.voxels, band_idx,
-                                                  n_band, planes, plane_stride, item_feat, com, X);
+    const BandFeatures src = make_band_features(prog, g, band_idx, planes, plane_stride, item_feat,
+                                                com, origin0);
+    assemble_kernel<<<LSML_SMS * 8, 256, 0, s>>>(src, n_band, X);
     LSML_LAUNCH_CHECK("assemble_kernel");
     return 0;
 }
@@ -609,7 +543,7 @@ int assemble_features(const FeatProgram& prog, const Geom& g, const i64* band_id
 
 namespace lsml {
 
-static int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a, const int* b) {
+int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a, const int* b) {
     if (nfeat < 0 || nfeat > 64) { set_error("feature program: 0..64 columns (got %d)", nfeat); return 1; }
     p.nfeat = nfeat;
     for (int f = 0; f < nfeat; ++f) {

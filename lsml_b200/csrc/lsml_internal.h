@@ -50,17 +50,32 @@ int band_sums(i64 voxels, i64 batch, const double* planes, i64 plane_stride, int
               const i64* band_idx, const i64* item_offsets, int mode, const double* mean,
               double* sums, void* workspace, cudaStream_t s);
 
-// regress.cu
+// regress.cu (X: materialised (B, F) matrix; *_band: the feature program is the source)
+struct BandFeatures;
+int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a, const int* b);
+BandFeatures make_band_features(const FeatProgram& prog, const Geom& g, const i64* band_idx,
+                                const double* planes, i64 plane_stride, const double* item_feat,
+                                const double* com, int origin0);
 int linear_predict(const double* X, const i64* n_band, int F, const double* mean,
                    const double* scale, const double* coef, double intercept, double* out,
                    cudaStream_t s);
+int linear_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                        const double* scale, const double* coef, double intercept, double* out,
+                        cudaStream_t s);
 int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
-                   const double* scale, const void* nodes, const int* tree_base,
-                   const u8* root_is_leaf, int n_trees, double divisor, double* out,
-                   cudaStream_t s);
+                   const double* scale, const void* nodes, const double* leaves,
+                   const unsigned* root_ref, const u8* root_is_leaf, int n_trees, double divisor,
+                   double* out, cudaStream_t s);
+int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                        const double* scale, const void* nodes, const double* leaves,
+                        const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
+                        double divisor, double* out, cudaStream_t s);
 int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
                 int n_layers, const int* sizes, const double* const* W, const double* const* b,
                 int act, double* out, cudaStream_t s);
+int mlp_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                     const double* scale, int n_layers, const int* sizes, const double* const* W,
+                     const double* const* b, int act, double* out, cudaStream_t s);
 
 // update.cu
 int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx,

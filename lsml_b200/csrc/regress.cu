@@ -1,4 +1,4 @@
-// regress.cu -- inference of the host-trained regressor on the band feature matrix
+// regress.cu -- inference of the host-trained regressor on the band voxels
 // (call sites lsml/core/model.py:388, fit_job_handler.py:504).
 //
 // The models are trained on the host by scikit-learn and exported to flat arrays by
@@ -11,20 +11,29 @@
 //                              leaf values summed in tree order in float64, then / n_trees.
 //   MLPRegressor               relu/tanh/logistic/identity hidden layers, identity output.
 //
-// Forest layout: 8-byte nodes, children adjacent (right = left + 1):
-//   internal  { float thr; u32 meta = feature<<24 | left_is_leaf<<23 | right_is_leaf<<22 | left }
-//   leaf      { double value }            (the parent's meta says which interpretation applies)
-// A 100-tree forest of ~600-node trees is ~480 KB: L2-resident, partly L1-resident.  The
-// traversal is latency-bound pointer chasing (not HBM-bound); one thread per band voxel with
-// the voxel's float32 features staged in shared memory as [feature][thread] (conflict-free).
-// Measured alternative (round 1, tools/forest_probe.py, 270k x 16, RF-100): walking the forest
-// tree by tree with the current tree staged in shared memory and 4 voxels per thread was 2x
-// SLOWER (738 us vs 388 us): the plain kernel runs at full occupancy (64 warps/SM) and is bound
-// by L1 tag throughput on divergent node fetches, which the staged version only replaces by
-// shared-memory bank conflicts at a quarter of the occupancy.  Walking 2 or 4 trees per thread
-// at once (independent chains for latency hiding) was also slower (578 / 543 us): the limit is
-// the number of divergent L1 sectors per warp-load, not the latency of a single chain.
+// Where the features come from (FeatSrc): either a materialised (B, F) matrix X (the C ABI's
+// lsml_*_predict, FeatureMap / fit), or -- the evolution loop -- the feature PROGRAM itself
+// (band_features.cuh): every kernel then gathers its voxel's columns from the image planes and
+// the per-item scalars, standardises them in registers and never reads or writes X
+// ("algorithmic minimum: not materialised, fused into K4").  Both sources yield
+// bit-identical values: X[b][f] IS band_feature(b, f).
+//
+// Forest layout: 32-byte "super nodes" holding an internal node AND its two children (two tree
+// levels per fetch; one 256-bit load per lane and level pair):
+//   { float thr[3] (node, left child, right child);
+//     u32 features (3 x 8 bit) | flags << 24: bit 0/1 = left/right child is a leaf,
+//                                             bits 2..5 = grandchild LL, LR, RL, RR is a leaf;
+//     u32 ref[4]: per grandchild the index of its super node, or of its leaf value; for a leaf
+//                 child, ref[2 * side] is that child's leaf index }
+// plus one float64 array of leaf values.  The traversal is latency / L1-tag bound pointer chasing
+// (not HBM-bound); one thread per band voxel with the voxel's float32 features staged in shared
+// memory as [feature][thread] (conflict-free).  Super nodes halve the number of dependent,
+// fully divergent fetches per tree walk compared with the 8-byte single nodes of round 1.
+// Measured alternatives (round 1, tools/forest_probe.py, 270k x 16, RF-100): the current tree
+// staged in shared memory with 4 voxels per thread was 2x SLOWER, 2 or 4 trees in flight per
+// thread also slower: the limit is the number of divergent L1 sectors per warp-load.
 #include "lsml_internal.h"
+#include "band_features.cuh"
 
 namespace lsml {
 
@@ -33,69 +42,111 @@ struct Scaler {
     const double* scale;
 };
 
-__device__ __forceinline__ double scaled(const double* __restrict__ X, i64 row, int f, int F,
-                                         const Scaler& sc) {
-    double x = __ldg(X + row * F + f);
+struct FeatSrc {
+    const double* X;      // (B, F) row-major, or null => evaluate the program
+    int F;
+    BandFeatures bf;
+};
+
+__device__ __forceinline__ double scale_value(double x, int f, const Scaler& sc) {
     if (sc.mean != nullptr) x = (x - __ldg(sc.mean + f)) / __ldg(sc.scale + f);
     return x;
 }
 
+// standardised feature f of band row b (v: the decoded voxel when the program is the source)
+__device__ __forceinline__ double scaled(const FeatSrc& src, i64 b, const VoxelRef& v, int f,
+                                         const Scaler& sc) {
+    const double x = src.X != nullptr ? __ldg(src.X + b * src.F + f) : band_feature(src.bf, v, f);
+    return scale_value(x, f, sc);
+}
+
+__device__ __forceinline__ VoxelRef row_ref(const FeatSrc& src, i64 b) {
+    if (src.X != nullptr) return VoxelRef{0, 0, 0, 0, 0};
+    return voxel_ref(src.bf, __ldg(src.bf.band_idx + b));
+}
+
 // --------------------------------------------------------------------------------- linear
 __global__ void __launch_bounds__(256)
-linear_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_band, int F,
-                      Scaler sc, const double* __restrict__ coef, double intercept,
+linear_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc,
+                      const double* __restrict__ coef, double intercept,
                       double* __restrict__ out) {
     const i64 nb = *n_band;
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
          b += (i64)gridDim.x * blockDim.x) {
+        const VoxelRef v = row_ref(src, b);
         double acc = 0.0;
-        for (int f = 0; f < F; ++f) acc += scaled(X, b, f, F, sc) * __ldg(coef + f);
+        for (int f = 0; f < src.F; ++f) acc += scaled(src, b, v, f, sc) * __ldg(coef + f);
         out[b] = acc + intercept;
     }
 }
 
 // --------------------------------------------------------------------------------- forest
+struct __align__(32) SuperNode {
+    float thr[3];
+    unsigned ff;          // feature0 | featureL << 8 | featureR << 16 | flags << 24
+    unsigned ref[4];
+};
+
 struct ForestView {
-    const uint2* nodes;        // 8-byte nodes of all trees back to back
-    const int* tree_base;      // [n_trees + 1] first node of each tree, then the node count
+    const SuperNode* nodes;    // super nodes of all trees
+    const double* leaves;      // leaf values of all trees
+    const unsigned* root_ref;  // [n_trees] root super node, or the leaf index of a single-leaf tree
     const u8* root_is_leaf;    // [n_trees]
     int n_trees;
     double divisor;            // n_estimators for forests, 1 for a single tree
 };
 
+__device__ __forceinline__ SuperNode load_node(const SuperNode* p) {
+    SuperNode r;
+    unsigned long long a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    r.thr[0] = __uint_as_float((unsigned)a); r.thr[1] = __uint_as_float((unsigned)(a >> 32));
+    r.thr[2] = __uint_as_float((unsigned)b); r.ff = (unsigned)(b >> 32);
+    r.ref[0] = (unsigned)c; r.ref[1] = (unsigned)(c >> 32);
+    r.ref[2] = (unsigned)d; r.ref[3] = (unsigned)(d >> 32);
+    return r;
+}
+
 constexpr int FOREST_THREADS = 128;
 
 __global__ void __launch_bounds__(FOREST_THREADS)
-forest_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_band, int F,
-                      Scaler sc, ForestView fv, double* __restrict__ out) {
+forest_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, ForestView fv,
+                      double* __restrict__ out) {
     extern __shared__ float feat[];   // [F][FOREST_THREADS]
     const i64 nb = *n_band;
     const i64 nblocks = (nb + FOREST_THREADS - 1) / FOREST_THREADS;
+    const int F = src.F;
     for (i64 blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const i64 b = blk * FOREST_THREADS + threadIdx.x;
         const bool live = b < nb;
         __syncthreads();
-        if (live)
+        if (live) {
+            const VoxelRef v = row_ref(src, b);
             for (int f = 0; f < F; ++f)
-                feat[f * FOREST_THREADS + threadIdx.x] = __double2float_rn(scaled(X, b, f, F, sc));
+                feat[f * FOREST_THREADS + threadIdx.x] = __double2float_rn(scaled(src, b, v, f, sc));
+        }
         __syncthreads();
         if (!live) continue;
+        const float* my = feat + threadIdx.x;
         double acc = 0.0;
         for (int t = 0; t < fv.n_trees; ++t) {
-            const uint2* tree = fv.nodes + __ldg(fv.tree_base + t);
-            int idx = 0;
+            unsigned ref = __ldg(fv.root_ref + t);
             bool leaf = __ldg(fv.root_is_leaf + t) != 0;
             while (!leaf) {
-                const uint2 nd = __ldg(tree + idx);
-                const float thr = __uint_as_float(nd.x);
-                const unsigned meta = nd.y;
-                const float x = feat[(meta >> 24) * FOREST_THREADS + threadIdx.x];
-                const bool right = !(x <= thr);
-                idx = (int)(meta & 0x3fffffu) + (right ? 1 : 0);
-                leaf = right ? ((meta >> 22) & 1u) : ((meta >> 23) & 1u);
+                const SuperNode nd = load_node(fv.nodes + ref);
+                const unsigned flags = nd.ff >> 24;
+                const bool r0 = !(my[(nd.ff & 0xffu) * FOREST_THREADS] <= nd.thr[0]);
+                if ((flags >> (r0 ? 1 : 0)) & 1u) {          // that child is a leaf
+                    ref = r0 ? nd.ref[2] : nd.ref[0];
+                    break;
+                }
+                const unsigned f1 = r0 ? (nd.ff >> 16) & 0xffu : (nd.ff >> 8) & 0xffu;
+                const bool r1 = !(my[f1 * FOREST_THREADS] <= (r0 ? nd.thr[2] : nd.thr[1]));
+                const unsigned lo = r1 ? nd.ref[1] : nd.ref[0], hi = r1 ? nd.ref[3] : nd.ref[2];
+                ref = r0 ? hi : lo;
+                leaf = (flags >> (2 + (r0 ? 2 : 0) + (r1 ? 1 : 0))) & 1u;
             }
-            const uint2 lv = __ldg(tree + idx);
-            acc += __hiloint2double((int)lv.y, (int)lv.x);
+            acc += __ldg(fv.leaves + ref);
         }
         out[b] = acc / fv.divisor;
     }
@@ -104,7 +155,10 @@ forest_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_ba
 // --------------------------------------------------------------------------------- MLP
 // One thread per band voxel; weights are read through the read-only path (L1-resident: a
 // (F x H) float64 layer with F=16, H=100 is 12.8 KB).  Activations ping-pong in shared memory
-// as [unit][thread].  act: 0 identity, 1 relu, 2 tanh, 3 logistic.
+// as [unit][thread].  act: 0 identity, 1 relu, 2 tanh, 3 logistic.  float64 on purpose: the
+// reference's MLPRegressor.predict is float64 and the velocities must agree to 1e-5 AFTER up to
+// hundreds of iterations; at F <= 64 and one hidden layer the dense work is ~2 x 10^4 flops per
+// voxel next to ~150 bytes of gathers -- tensor cores have nothing to win here.
 struct MlpView {
     int n_layers;              // number of weight matrices
     int sizes[9];              // sizes[0] = F, sizes[n_layers] = 1
@@ -124,8 +178,8 @@ __device__ __forceinline__ double mlp_act(double x, int act) {
 }
 
 __global__ void __launch_bounds__(MLP_THREADS)
-mlp_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_band, Scaler sc,
-                   MlpView mv, double* __restrict__ out) {
+mlp_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, MlpView mv,
+                   double* __restrict__ out) {
     extern __shared__ double actbuf[];   // 2 x [max_width][MLP_THREADS]
     double* cur = actbuf;
     double* nxt = actbuf + (size_t)mv.max_width * MLP_THREADS;
@@ -133,7 +187,8 @@ mlp_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_band,
     const int F = mv.sizes[0];
     for (i64 b = (i64)blockIdx.x * MLP_THREADS + threadIdx.x; b < nb;
          b += (i64)gridDim.x * MLP_THREADS) {
-        for (int f = 0; f < F; ++f) cur[f * MLP_THREADS + threadIdx.x] = scaled(X, b, f, F, sc);
+        const VoxelRef v = row_ref(src, b);
+        for (int f = 0; f < F; ++f) cur[f * MLP_THREADS + threadIdx.x] = scaled(src, b, v, f, sc);
         double* a = cur; double* o = nxt;
         for (int l = 0; l < mv.n_layers; ++l) {
             const int nin = mv.sizes[l], nout = mv.sizes[l + 1];
@@ -151,35 +206,53 @@ mlp_predict_kernel(const double* __restrict__ X, const i64* __restrict__ n_band,
 }
 
 // --------------------------------------------------------------------------------- launchers
-int linear_predict(const double* X, const i64* n_band, int F, const double* mean,
-                   const double* scale, const double* coef, double intercept, double* out,
-                   cudaStream_t s) {
+static FeatSrc matrix_source(const double* X, int F) {
+    FeatSrc src;
+    src.X = X; src.F = F;
+    src.bf = BandFeatures{};
+    return src;
+}
+static FeatSrc program_source(const BandFeatures& bf) {
+    FeatSrc src;
+    src.X = nullptr; src.F = bf.prog.nfeat; src.bf = bf;
+    return src;
+}
+
+static int linear_launch(const FeatSrc& src, const i64* n_band, const double* mean,
+                         const double* scale, const double* coef, double intercept, double* out,
+                         cudaStream_t s) {
     Scaler sc{mean, scale};
-    linear_predict_kernel<<<LSML_SMS * 8, 256, 0, s>>>(X, n_band, F, sc, coef, intercept, out);
+    linear_predict_kernel<<<LSML_SMS * 8, 256, 0, s>>>(src, n_band, sc, coef, intercept, out);
     LSML_LAUNCH_CHECK("linear_predict_kernel");
     return 0;
 }
 
-int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
-                   const double* scale, const void* nodes, const int* tree_base,
-                   const u8* root_is_leaf, int n_trees, double divisor, double* out,
-                   cudaStream_t s) {
-    if (F > 255) { set_error("forest: at most 255 features"); return 1; }
+static int forest_launch(const FeatSrc& src, const i64* n_band, const double* mean,
+                         const double* scale, const void* nodes, const double* leaves,
+                         const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
+                         double divisor, double* out, cudaStream_t s) {
+    if (src.F > 255) { set_error("forest: at most 255 features"); return 1; }
+    if ((reinterpret_cast<uintptr_t>(nodes) & 31u) != 0) {
+        set_error("forest: super nodes must be 32-byte aligned");
+        return 1;
+    }
     Scaler sc{mean, scale};
-    ForestView fv{static_cast<const uint2*>(nodes), tree_base, root_is_leaf, n_trees, divisor};
-    const size_t smem = (size_t)F * FOREST_THREADS * sizeof(float);
+    ForestView fv{static_cast<const SuperNode*>(nodes), leaves, root_ref, root_is_leaf, n_trees,
+                  divisor};
+    const size_t smem = (size_t)src.F * FOREST_THREADS * sizeof(float);
     if (smem > 48 * 1024)
         LSML_CUDA(cudaFuncSetAttribute(forest_predict_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    forest_predict_kernel<<<LSML_SMS * 16, FOREST_THREADS, smem, s>>>(X, n_band, F, sc, fv, out);
+    forest_predict_kernel<<<LSML_SMS * 16, FOREST_THREADS, smem, s>>>(src, n_band, sc, fv, out);
     LSML_LAUNCH_CHECK("forest_predict_kernel");
     return 0;
 }
 
-int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
-                int n_layers, const int* sizes, const double* const* W, const double* const* b,
-                int act, double* out, cudaStream_t s) {
+static int mlp_launch(const FeatSrc& src, const i64* n_band, const double* mean,
+                      const double* scale, int n_layers, const int* sizes, const double* const* W,
+                      const double* const* b, int act, double* out, cudaStream_t s) {
     if (n_layers < 1 || n_layers > 8) { set_error("mlp: 1..8 layers supported"); return 1; }
+    if (sizes[0] != src.F) { set_error("mlp: %d inputs, feature source has %d", sizes[0], src.F); return 1; }
     Scaler sc{mean, scale};
     MlpView mv;
     mv.n_layers = n_layers; mv.act = act; mv.max_width = 0;
@@ -193,9 +266,47 @@ int mlp_predict(const double* X, const i64* n_band, const double* mean, const do
     if (smem > 48 * 1024)
         LSML_CUDA(cudaFuncSetAttribute(mlp_predict_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_predict_kernel<<<LSML_SMS * 4, MLP_THREADS, smem, s>>>(X, n_band, sc, mv, out);
+    mlp_predict_kernel<<<LSML_SMS * 4, MLP_THREADS, smem, s>>>(src, n_band, sc, mv, out);
     LSML_LAUNCH_CHECK("mlp_predict_kernel");
     return 0;
+}
+
+int linear_predict(const double* X, const i64* n_band, int F, const double* mean,
+                   const double* scale, const double* coef, double intercept, double* out,
+                   cudaStream_t s) {
+    return linear_launch(matrix_source(X, F), n_band, mean, scale, coef, intercept, out, s);
+}
+int linear_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                        const double* scale, const double* coef, double intercept, double* out,
+                        cudaStream_t s) {
+    return linear_launch(program_source(bf), n_band, mean, scale, coef, intercept, out, s);
+}
+
+int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
+                   const double* scale, const void* nodes, const double* leaves,
+                   const unsigned* root_ref, const u8* root_is_leaf, int n_trees, double divisor,
+                   double* out, cudaStream_t s) {
+    return forest_launch(matrix_source(X, F), n_band, mean, scale, nodes, leaves, root_ref,
+                         root_is_leaf, n_trees, divisor, out, s);
+}
+int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                        const double* scale, const void* nodes, const double* leaves,
+                        const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
+                        double divisor, double* out, cudaStream_t s) {
+    return forest_launch(program_source(bf), n_band, mean, scale, nodes, leaves, root_ref,
+                         root_is_leaf, n_trees, divisor, out, s);
+}
+
+int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
+                int n_layers, const int* sizes, const double* const* W, const double* const* b,
+                int act, double* out, cudaStream_t s) {
+    return mlp_launch(matrix_source(X, sizes[0]), n_band, mean, scale, n_layers, sizes, W, b, act,
+                      out, s);
+}
+int mlp_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                     const double* scale, int n_layers, const int* sizes, const double* const* W,
+                     const double* const* b, int act, double* out, cudaStream_t s) {
+    return mlp_launch(program_source(bf), n_band, mean, scale, n_layers, sizes, W, b, act, out, s);
 }
 
 }  // namespace lsml

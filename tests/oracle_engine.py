@@ -58,6 +58,9 @@ class OracleEngine:
     def check_converged(self):
         pass
 
+    def last_record(self, nb):
+        return self._last_idx[:nb], self.new_u[:nb]
+
     def distance(self):
         return torch.from_numpy(self._dist.copy())
 
@@ -81,7 +84,6 @@ class OracleEngine:
                                              rebuild=False)
             self.u[b] = torch.from_numpy(u)
         self.new_u = self.u.reshape(-1)[self._last_idx].clone()
-        self._last_new_u = self.new_u
         for b in range(self.batch):
             self._rebuild(b)
         self._compact()

@@ -135,6 +135,53 @@ def test_pack_trees_round_trip():
     assert np.array_equal(acc / len(root), rf.predict(Xt))
 
 
+def test_pack_supernodes_round_trip():
+    """The 32-byte super-node layout the kernels walk (two tree levels per fetch) reaches the same
+    leaves as scikit-learn, including depth-1 / depth-2 / single-leaf trees."""
+    from sklearn.ensemble import ExtraTreesRegressor, RandomForestRegressor
+    from sklearn.tree import DecisionTreeRegressor
+    from lsml_b200.core.regressors import pack_supernodes, pack_trees
+    rs = np.random.RandomState(0)
+    X = rs.randn(600, 6)
+    y = X[:, 0] * 2 + np.sin(X[:, 1]) + 0.1 * rs.randn(600)
+
+    def walk(sn, leaves, root_ref, root_leaf, X32):
+        out = np.zeros(len(X32))
+        for t in range(len(root_ref)):
+            for i in range(len(X32)):
+                ref, leaf = int(root_ref[t]), bool(root_leaf[t])
+                while not leaf:
+                    nd = sn[ref]
+                    thr, ff = nd[:3].view(np.float32), int(nd[3])
+                    flags = ff >> 24
+                    r0 = not (X32[i, ff & 0xff] <= thr[0])
+                    if (flags >> int(r0)) & 1:
+                        ref = int(nd[4 + 2 * int(r0)])
+                        break
+                    f1 = (ff >> 16) & 0xff if r0 else (ff >> 8) & 0xff
+                    r1 = not (X32[i, f1] <= (thr[2] if r0 else thr[1]))
+                    g = 2 * int(r0) + int(r1)
+                    ref, leaf = int(nd[4 + g]), bool((flags >> (2 + g)) & 1)
+                out[i] += leaves[ref]
+        return out
+
+    models = [RandomForestRegressor(n_estimators=6, max_depth=7, random_state=0).fit(X, y),
+              RandomForestRegressor(n_estimators=5, max_samples=50, random_state=1).fit(X, y),
+              ExtraTreesRegressor(n_estimators=3, max_depth=9, random_state=2).fit(X, y),
+              DecisionTreeRegressor(max_depth=1).fit(X, y),
+              DecisionTreeRegressor(max_depth=2).fit(X, y),
+              DecisionTreeRegressor().fit(X, np.ones(600))]          # a single leaf
+    Xt = rs.randn(120, 6)
+    Xt[:40] = X[:40]
+    for m in models:
+        trees = [e.tree_ for e in m.estimators_] if hasattr(m, "estimators_") else [m.tree_]
+        nodes, bases, root = pack_trees(trees, 6)
+        sn, leaves, root_ref, root_leaf = pack_supernodes(nodes, bases, root)
+        assert sn.dtype == np.uint32 and sn.shape[1] == 8 and leaves.dtype == np.float64
+        got = walk(sn, leaves, root_ref, root_leaf, Xt.astype(np.float32)) / len(trees)
+        assert np.array_equal(got, m.predict(Xt)), type(m).__name__
+
+
 def test_fit_host_logic_matches_reference_statements():
     """The host-side pieces of `fit` that decide WHICH data is used, against literal
     transcriptions of the reference's statements (datasets_handler.py:312-362; the reference's

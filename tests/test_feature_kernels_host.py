@@ -21,10 +21,14 @@ CSRC = os.path.join(ROOT, "lsml_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def host_lib(tmp_path_factory):
-    src = open(os.path.join(CSRC, "features.cu")).read()
-    regions = re.findall(r"// \[host-test:begin\][^\n]*\n(.*?)// \[host-test:end\]", src, re.S)
-    assert len(regions) == 1
-    text = ('#include "cuda_host_shim.h"\n#include "com_ray.cuh"\nnamespace lsml {\n' + regions[0] +
+    regions = []
+    for name in ("band_features.cuh", "features.cu"):    # band_feature(), then the two kernels
+        src = open(os.path.join(CSRC, name)).read()
+        found = re.findall(r"// \[host-test:begin\][^\n]*\n(.*?)// \[host-test:end\]", src, re.S)
+        assert len(found) == 1, name
+        regions += found
+    text = ('#include "cuda_host_shim.h"\n#include "com_ray.cuh"\nnamespace lsml {\n' +
+            "\n".join(regions) +
             open(os.path.join(HERE, "native", "features_host_driver.inc")).read())
     out = tmp_path_factory.mktemp("features_host")
     cpp, so = str(out / "features_host.cpp"), str(out / "features_host.so")

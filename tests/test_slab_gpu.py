@@ -48,7 +48,8 @@ def test_slab_evolution_identical_to_single_gpu(shape, world, dx):
     assert np.array_equal(slab.gather("mask"), one.mask[0].cpu().numpy())
     max_rounds = slab.rebuild_rounds
     for it in range(6):
-        nb1 = one.step(reg, 0.4)
+        nb1 = one.n_band
+        one.step(reg, 0.4)
         nb2 = slab.step(reg, 0.4)
         max_rounds = max(max_rounds, slab.rebuild_rounds)
         assert nb1 == nb2, (it, nb1, nb2)

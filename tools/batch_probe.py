@@ -52,7 +52,7 @@ for rep in range(2):
     a.record(); tot = 0
     iters = 10
     for it in range(iters):
-        tot += eng.step(dreg, 0.4)
+        tot += eng.n_band; eng.step(dreg, 0.4)
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     print("rep %d: %s x %s, %d iterations: %.2f ms/iteration, %d band voxel iterations, %.1f M bvi/s"

@@ -37,7 +37,7 @@ for rep in range(2):
     a.record()
     tot = 0
     for it in range(iters):
-        tot += eng.step(dreg, bench.STEP)
+        tot += eng.n_band; eng.step(dreg, bench.STEP)
     b.record(); torch.cuda.synchronize()
     print("rep %d: %d iterations, %d band voxel iterations, %.1f us/iteration (device), %.1f us/iteration (host wall)"
           % (rep, iters, tot, a.elapsed_time(b) * 1e3 / iters, (time.perf_counter() - t0) * 1e6 / iters))
