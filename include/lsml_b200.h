@@ -133,6 +133,22 @@ int lsml_assemble_features(int nfeat, const int *kind, const int *a, const int *
                            const double *planes, long long plane_stride,
                            const double *item_feat, const double *com, double *X, void *stream);
 
+/* Moments of order > 2 (shape.py:214-230 takes any order >= 1): from exact per-axis histograms of
+ * {u > 0}; writes item_feat[item*nfeat + cols[q]] for the ncols requested (axis, order) pairs.
+ * Call after lsml_item_features (needs com); cols/axes/orders are DEVICE int arrays. */
+long long lsml_axis_moments_workspace_bytes(int ndim, const int *shape, long long batch);
+int lsml_axis_moments(int ndim, const int *shape, long long batch, const double *dx,
+                      const double *u, const unsigned long long *stats, const double *com,
+                      int ncols, const int *cols, const int *axes, const int *orders, int nfeat,
+                      double *item_feat, void *workspace, void *stream);
+
+/* BoundarySize, ndim = 3 (shape.py:88-89: skimage marching_cubes_lewiner + mesh_surface_area):
+ * area[item] = surface area of {u = 0} in physical units, a marching-cubes reduction without a
+ * mesh (csrc/mcubes.cu; third-party algorithm, parity unpinned beyond test_shape.py:59-107). */
+long long lsml_surface_area_workspace_bytes(int ndim, const int *shape, long long batch);
+int lsml_surface_area(int ndim, const int *shape, long long batch, const double *u,
+                      const double *dx, double *area, void *workspace, void *stream);
+
 /* ---- regressor inference (model.py:388; parameters exported from scikit-learn) -------------- */
 /* mean/scale: StandardScaler parameters or NULL. */
 int lsml_linear_predict(const double *X, const long long *n_band, int nfeat, const double *mean,

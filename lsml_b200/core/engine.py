@@ -74,6 +74,7 @@ class FeatureProgram:
         self.planes = []          # ("sample" | "edge", sigma)
         kind, a, b = [], [], []
         self.needs_boundary = False
+        self.hi_moments = []      # (column, axis, order) of the Moments columns of order > 2
         self.needs_band_stats = False
         self.needs_u_planes = False
         self.user_planes = {}     # plane index -> callable(img, dx)
@@ -100,10 +101,10 @@ class FeatureProgram:
             elif k == "moments":
                 for axis in spec[1]:
                     for order in spec[2]:
-                        if order not in (1, 2):
-                            raise NotImplementedError(
-                                "Moments of order %r: only orders 1 and 2 have a device kernel"
-                                % (order,))
+                        if int(order) != order or not 1 <= order <= 64:
+                            raise ValueError("Moments order should be an integer in 1..64")
+                        if order > 2:       # exact per-axis histograms + lsml_axis_moments
+                            self.hi_moments.append((len(kind), int(axis), int(order)))
                         kind.append(FK_MOMENT); a.append(int(axis)); b.append(int(order))
             elif k == "dist_to_com":
                 kind.append(FK_DIST_COM); a.append(0); b.append(0)
@@ -135,10 +136,9 @@ class FeatureProgram:
                 raise NotImplementedError(
                     "no device kernel registered for feature spec %r (there is no CPU "
                     "fallback)" % (spec,))
-        if self.needs_boundary and ndim != 2:
-            raise NotImplementedError(
-                "BoundarySize / IsoperimetricRatio: only the 2-D (marching squares) kernel "
-                "exists; the 3-D Lewiner marching-cubes area is not implemented")
+        if self.needs_boundary and ndim not in (2, 3):
+            raise ValueError("Boundary size is only defined for dimensions 2 and 3; "
+                             "ndim provided = {}".format(ndim))
         self.nfeat = len(kind)
         if self.nfeat > 64:
             raise ValueError("at most 64 feature columns")
@@ -219,11 +219,24 @@ class BandEngine:
             self._ws_band = torch.empty(max(8, int(_lib.lib.lsml_band_stats_workspace_bytes(
                 _lib.c_i64(self.voxels), _lib.c_i64(self.batch), ctypes.c_int(npl)))),
                 dtype=torch.uint8, device=d)
-            if self.program.needs_boundary:
+            if self.program.needs_boundary and self.ndim == 2:
                 _lib.lib.lsml_contour_workspace_bytes.restype = _lib.c_i64
                 self._ws_contour = torch.empty(int(_lib.lib.lsml_contour_workspace_bytes(
                     ctypes.c_int(self.shape[0]), ctypes.c_int(self.shape[1]),
                     _lib.c_i64(self.batch))), dtype=torch.uint8, device=d)
+            elif self.program.needs_boundary:
+                _lib.lib.lsml_surface_area_workspace_bytes.restype = _lib.c_i64
+                self._ws_contour = torch.empty(max(8, int(_lib.lib.lsml_surface_area_workspace_bytes(
+                    ctypes.c_int(3), self._shape_c, _lib.c_i64(self.batch)))),
+                    dtype=torch.uint8, device=d)
+            if self.program.hi_moments:
+                _lib.lib.lsml_axis_moments_workspace_bytes.restype = _lib.c_i64
+                self._ws_moments = torch.empty(int(_lib.lib.lsml_axis_moments_workspace_bytes(
+                    ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch))),
+                    dtype=torch.uint8, device=d)
+                hm = np.asarray(self.program.hi_moments, dtype=np.int32)
+                self._hm_cols, self._hm_axes, self._hm_orders = (
+                    torch.from_numpy(np.ascontiguousarray(hm[:, q])).to(d) for q in range(3))
             _lib.lib.lsml_fmm_workspace_bytes.restype = _lib.c_i64
             self._ws_fmm = None       # allocated on the first band rebuild
         self._weights = {}            # (sigma, order) -> (device weights, radius)
@@ -499,15 +512,23 @@ class BandEngine:
                 _lib.ptr(self.item_offsets), _lib.ptr(self.band_mean), _lib.ptr(self.band_std),
                 _lib.ptr(self._ws_band), self._stream()), "band_stats")
         if pr.needs_boundary:
-            _lib.check(_lib.lib.lsml_contour_length(
+            fn = _lib.lib.lsml_contour_length if self.ndim == 2 else _lib.lib.lsml_surface_area
+            _lib.check(fn(
                 ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), _lib.ptr(self.u),
                 self._dx_c, _lib.ptr(self.boundary), _lib.ptr(self._ws_contour), self._stream()),
-                "contour_length")
+                "boundary_size")
         _lib.check(_lib.lib.lsml_item_features(
             ctypes.c_int(pr.nfeat), pr.kind, pr.a, pr.b, ctypes.c_int(self.ndim), self._shape_c,
             _lib.c_i64(self.batch), self._dx_c, ctypes.c_int(max(npl, 1)), _lib.ptr(self.stats),
             _lib.ptr(self.band_mean), _lib.ptr(self.band_std), _lib.ptr(self.boundary),
             _lib.ptr(self.item_feat), _lib.ptr(self.com), self._stream()), "item_features")
+        if pr.hi_moments:
+            _lib.check(_lib.lib.lsml_axis_moments(
+                ctypes.c_int(self.ndim), self._shape_c, _lib.c_i64(self.batch), self._dx_c,
+                _lib.ptr(self.u), _lib.ptr(self.stats), _lib.ptr(self.com),
+                ctypes.c_int(len(pr.hi_moments)), _lib.ptr(self._hm_cols), _lib.ptr(self._hm_axes),
+                _lib.ptr(self._hm_orders), ctypes.c_int(pr.nfeat), _lib.ptr(self.item_feat),
+                _lib.ptr(self._ws_moments), self._stream()), "axis_moments")
 
     def compute_features(self):
         """FeatureMap on the current band -> X[:n_band] (band order), materialised: for

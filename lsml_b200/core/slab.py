@@ -177,6 +177,13 @@ class SlabRank:
                 raise NotImplementedError(
                     "COMRaySample reads the image along a ray through the whole volume and is "
                     "not available on slab-decomposed volumes")
+            if spec[0] in ("boundary_size", "isoperimetric"):
+                raise NotImplementedError(
+                    "BoundarySize / IsoperimetricRatio are not available on slab-decomposed "
+                    "volumes (the marching-cubes area of the cut planes would need a halo pass)")
+            if spec[0] == "moments" and any(o > 2 for o in spec[2]):
+                raise NotImplementedError(
+                    "Moments of order > 2 are not available on slab-decomposed volumes")
             if spec[0] in ("smooth_u", "user_plane"):
                 raise NotImplementedError(
                     "feature spec %r is not available on slab-decomposed volumes (it needs a "

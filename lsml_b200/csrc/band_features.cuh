@@ -51,6 +51,7 @@ __device__ __forceinline__ double moment_from_stats(const u64* st, int ax, int o
     const double cnt = (double)st[0];
     const double measure = cnt * pdx;                       // Size: (u>0).sum()*prod(dx)
     if (order == 1) return ((double)st[1 + ax] * dx) * pdx / measure;   // shape.py:227-228
+    if (order > 2) return 0.0;     // filled in afterwards by hi_moment_kernel (features.cu)
     // order 2: sum (x - c)^2 with c the centroid = (N*Sxx - Sx^2)/N exactly (128-bit integers)
     const unsigned __int128 N = st[0], Sx = st[1 + ax], Sxx = st[4 + ax];
     const unsigned __int128 num = N * Sxx - Sx * Sx;

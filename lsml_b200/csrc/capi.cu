@@ -286,6 +286,31 @@ int lsml_band_sums(long long voxels, long long batch, const double* planes,
     return band_sums(voxels, batch, planes, plane_stride, nplanes, band_idx, item_offsets, mode,
                      mean, sums, workspace, (cudaStream_t)stream);
 }
+long long lsml_axis_moments_workspace_bytes(int ndim, const int* shape, long long batch) {
+    const double* dx = nullptr;
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return -1;
+    return axis_moments_workspace_bytes(g);
+}
+int lsml_axis_moments(int ndim, const int* shape, long long batch, const double* dx,
+                      const double* u, const unsigned long long* stats, const double* com,
+                      int ncols, const int* cols, const int* axes, const int* orders, int nfeat,
+                      double* item_feat, void* workspace, void* stream) {
+    GEOM(g);
+    return axis_moments(g, u, stats, com, ncols, cols, axes, orders, nfeat, item_feat, workspace,
+                        (cudaStream_t)stream);
+}
+long long lsml_surface_area_workspace_bytes(int ndim, const int* shape, long long batch) {
+    const double* dx = nullptr;
+    Geom g;
+    if (make_geom(g, ndim, shape, batch, dx)) return -1;
+    return surface_area_workspace_bytes(g);
+}
+int lsml_surface_area(int ndim, const int* shape, long long batch, const double* u,
+                      const double* dx, double* area, void* workspace, void* stream) {
+    GEOM(g);
+    return surface_area(g, u, area, workspace, (cudaStream_t)stream);
+}
 int lsml_linear_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
                         const double* scale, const double* coef, double intercept, double* out,
                         void* stream) {

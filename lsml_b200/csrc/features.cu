@@ -178,6 +178,71 @@ global_stats_kernel(const double* __restrict__ u, int n0, int n1, int n2, u64* _
 }
 
 // ---------------------------------------------------------------------------------------------
+// Moments of order > 2 (shape.py:214-230 accepts any order >= 1).  The moment of order k along
+// axis a is sum_{u>0} (i_a dx_a - c_a)^k * prod(dx) / measure: the summand depends on the voxel only
+// through its index along that axis, so the EXACT per-axis histograms n_a[i] = #{u > 0, index_a
+// = i} (integer atomics: deterministic) carry everything; the moment is then a sum over at most
+// n_a bins.  Orders 1 and 2 never come here (exact integer statistics, maintained incrementally).
+// ---------------------------------------------------------------------------------------------
+constexpr int AH_ROWS_PER_CTA = 64;
+
+__global__ void __launch_bounds__(256)
+axis_hist_kernel(const double* __restrict__ u, int n0, int n1, int n2,
+                 unsigned long long* __restrict__ hist /* [item][n0 + n1 + n2] */) {
+    extern __shared__ unsigned sh[];          // n0 + n1 + n2 counters of this CTA
+    const int item = blockIdx.y;
+    const int nh = n0 + n1 + n2;
+    for (int t = threadIdx.x; t < nh; t += blockDim.x) sh[t] = 0u;
+    __syncthreads();
+    const i64 rows_per_item = (i64)n0 * n1;
+    const i64 row0 = (i64)blockIdx.x * AH_ROWS_PER_CTA;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int rr = warp; rr < AH_ROWS_PER_CTA; rr += nwarps) {
+        const i64 row = row0 + rr;
+        if (row >= rows_per_item) break;
+        const int i = (int)(row / n1), j = (int)(row % n1);
+        const double* p = u + ((i64)item * rows_per_item + row) * n2;
+        unsigned cnt = 0u;
+        for (int k = lane; k < n2; k += 32)
+            if (__ldg(p + k) > 0.0) { ++cnt; atomicAdd(&sh[n0 + n1 + k], 1u); }
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) { atomicAdd(&sh[i], cnt); atomicAdd(&sh[n0 + j], cnt); }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nh; t += blockDim.x)
+        if (sh[t]) atomicAdd(hist + (i64)item * nh + t, (unsigned long long)sh[t]);
+}
+
+// one warp per (item, requested column): item_feat[item][col] = moment of `order` along `axis`
+__global__ void __launch_bounds__(32)
+hi_moment_kernel(const unsigned long long* __restrict__ hist, int n0, int n1, int n2, ItemGeom geo,
+                 const u64* __restrict__ stats, const double* __restrict__ com, int ncols,
+                 const int* __restrict__ cols, const int* __restrict__ axes,
+                 const int* __restrict__ orders, int nfeat, double* __restrict__ item_feat) {
+    const i64 item = blockIdx.x / ncols;
+    const int q = (int)(blockIdx.x % ncols);
+    const int ax = geo.pad + axes[q], order = orders[q];
+    const int ext[3] = {n0, n1, n2};
+    const int off = ax == 0 ? 0 : (ax == 1 ? n0 : n0 + n1);
+    const unsigned long long* h = hist + item * (i64)(n0 + n1 + n2) + off;
+    const double c = com[item * 3 + ax];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < ext[ax]; i += 32) {
+        const unsigned long long n = h[i];
+        if (n == 0) continue;
+        const double x = (double)(i + (ax == 0 ? geo.origin0 : 0)) * geo.dx[ax] - c;   // mesh - com
+        double pw = x;
+        for (int e = 1; e < order; ++e) pw *= x;
+        acc += pw * (double)n;
+    }
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) {
+        const double measure = (double)stats[item * 8] * geo.pdx;
+        item_feat[item * nfeat + cols[q]] = acc * geo.pdx / measure;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // band sums of P image planes, per item.  planes: (P, batch*voxels).  Deterministic two-stage:
 // slice s of item i covers band positions [off_i + s*L, off_i + (s+1)*L), L = ceil(n_i/slices).
 // mode 0: sum x -> partial ; mode 1: sum (x - mean[item][p])^2
@@ -548,8 +613,8 @@ int fill_program(FeatProgram& p, int nfeat, const int* kind, const int* a, const
     p.nfeat = nfeat;
     for (int f = 0; f < nfeat; ++f) {
         p.kind[f] = kind[f]; p.a[f] = a[f]; p.b[f] = b[f];
-        if (kind[f] == FK_MOMENT && (b[f] < 1 || b[f] > 2)) {
-            set_error("Moments: only orders 1 and 2 are implemented on the device (got %d)", b[f]);
+        if (kind[f] == FK_MOMENT && (b[f] < 1 || b[f] > 64)) {
+            set_error("Moments order should be greater than or equal to 1 (and <= 64; got %d)", b[f]);
             return 1;
         }
         if (kind[f] == FK_COM_RAY && ((b[f] >> 16) < 1 || (b[f] & 0xffff) >= 2 * (b[f] >> 16))) {
@@ -585,6 +650,42 @@ int assemble_features_c(int nfeat, const int* kind, const int* a, const int* b, 
     }
     return assemble_features(p, g, band_idx, n_band, planes, plane_stride, item_feat, com, X,
                              origin0, s);
+}
+
+i64 axis_moments_workspace_bytes(const Geom& g) {
+    return (i64)sizeof(unsigned long long) * g.batch * (g.n[0] + g.n[1] + g.n[2]);
+}
+
+// Moments of order > 2 into their columns of item_feat (after item_features has filled com).
+// cols / axes / orders: DEVICE int arrays of length ncols.
+int axis_moments(const Geom& g, const double* u, const u64* stats, const double* com, int ncols,
+                 const int* cols, const int* axes, const int* orders, int nfeat, double* item_feat,
+                 void* workspace, cudaStream_t s) {
+    if (ncols <= 0) return 0;
+    if (g.batch > 65535) { set_error("axis_moments: at most 65535 items per call"); return 1; }
+    const int nh = g.n[0] + g.n[1] + g.n[2];
+    if ((size_t)nh * sizeof(unsigned) > 200 * 1024) { set_error("axis_moments: grid too large"); return 1; }
+    unsigned long long* hist = static_cast<unsigned long long*>(workspace);
+    LSML_CUDA(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * g.batch * nh, s));
+    const i64 rows = (i64)g.n[0] * g.n[1];
+    const unsigned ctas = (unsigned)((rows + AH_ROWS_PER_CTA - 1) / AH_ROWS_PER_CTA);
+    const size_t smem = (size_t)nh * sizeof(unsigned);
+    if (smem > 48 * 1024)
+        LSML_CUDA(cudaFuncSetAttribute(axis_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    axis_hist_kernel<<<dim3(ctas, (unsigned)g.batch), 256, smem, s>>>(u, g.n[0], g.n[1], g.n[2], hist);
+    LSML_LAUNCH_CHECK("axis_hist_kernel");
+    ItemGeom geo;
+    geo.ndim = g.ndim; geo.pad = 3 - g.ndim;
+    double pdx = 1.0;
+    for (int a = 0; a < 3; ++a) geo.dx[a] = g.dx[a];
+    for (int a = geo.pad; a < 3; ++a) pdx = (a == geo.pad) ? g.dx[a] : pdx * g.dx[a];
+    geo.pdx = pdx; geo.origin0 = 0; geo.n0 = g.n[0];
+    hi_moment_kernel<<<(unsigned)(g.batch * ncols), 32, 0, s>>>(hist, g.n[0], g.n[1], g.n[2], geo,
+                                                                stats, com, ncols, cols, axes,
+                                                                orders, nfeat, item_feat);
+    LSML_LAUNCH_CHECK("hi_moment_kernel");
+    return 0;
 }
 
 }  // namespace lsml

@@ -103,6 +103,15 @@ i64 fmm_counters_stamps_offset();
 i64 fmm_counters_failed_offset();
 i64 fmm_counters_offset(i64 total);
 
+i64 axis_moments_workspace_bytes(const Geom& g);
+int axis_moments(const Geom& g, const double* u, const u64* stats, const double* com, int ncols,
+                 const int* cols, const int* axes, const int* orders, int nfeat, double* item_feat,
+                 void* workspace, cudaStream_t s);
+
+// mcubes.cu
+i64 surface_area_workspace_bytes(const Geom& g);
+int surface_area(const Geom& g, const double* u, double* area, void* workspace, cudaStream_t s);
+
 // misc.cu
 int ball_init(const Geom& g, double* u, const double* location, double radius,
               const double* centres_dev, const double* radii_dev, cudaStream_t s);

@@ -23,8 +23,9 @@ class Size(BaseShapeFeature):
 
 
 class BoundarySize(BaseShapeFeature):
-    """ Size of the zero level set: curve length in 2-D (:35-89).  The 3-D surface area
-    (Lewiner marching cubes of scikit-image) has no device kernel yet. """
+    """ Size of the zero level set (:35-89): curve length in 2-D (marching squares), surface area
+    in 3-D (marching cubes as a reduction, csrc/mcubes.cu; the reference's scikit-image Lewiner
+    variant is a third-party algorithm: parity unpinned beyond test_shape.py:59-107). """
     locality = GLOBAL_FEATURE_TYPE
 
     def __init__(self, ndim=2):

@@ -532,3 +532,139 @@ double orc_marching_squares_length(int m_, int n_, const double *u, const double
     free(segs);
     return total;
 }
+
+/* ==========================================================================================
+ * Surface area of the zero level set by marching cubes (BoundarySize ndim=3, shape.py:88-89:
+ * skimage.measure.marching_cubes_lewiner(u, 0., spacing=dx) + mesh_surface_area).
+ *
+ * THIRD PARTY, ABSENT, UNPINNED: scikit-image is not installed here, its Lewiner lookup tables
+ * (33 topological cases, ~2000 table rows) are not under /root/reference and cannot be restated
+ * from memory.  What is restated is the geometry those tables encode wherever it is unambiguous,
+ * plus Lewiner's FACE test for the ambiguous faces; the interior ("tunnel") test of cases 4, 6, 7,
+ * 10, 12, 13 and the extra centre vertex some of their sub-cases use are NOT reproduced.  PARITY
+ * UNPINNED beyond lsml/feature/provided/test/test_shape.py:59-107 (sphere area 4 pi to 0 places,
+ * sphericity 1 to 2 places).  skimage also converts the volume to float32 first; this restatement
+ * stays in float64.
+ *
+ * Specification (the device kernel lsml_b200/csrc/mcubes.cu implements the same one, written
+ * independently):
+ *   - cube corner (d0,d1,d2) in {0,1}^3 is INSIDE when u > 0;
+ *   - edge along axis a at the other two coordinates (dp,dq), p<q, has id 4a + 2 dp + dq; a cut
+ *     edge carries the vertex corner_lo + t e_a, t = u_lo / (u_lo - u_hi), scaled by dx;
+ *   - on each of the 6 faces the cut edges are paired into segments: two cut edges -> one segment;
+ *     four (corners alternate in sign) -> the asymptotic decider: the inside corners are joined
+ *     through the face iff (product of the two inside values) > (product of the two outside
+ *     values), and then each OUTSIDE corner is cut off by a segment between its two edges;
+ *     otherwise each inside corner is cut off;
+ *   - every cut edge lies on two faces, so the segments close into loops; each loop is
+ *     triangulated as a fan from its vertex with the lowest edge id, walking towards the
+ *     neighbour found first (faces in the order axis 0 lo, axis 0 hi, axis 1 lo, ...);
+ *   - triangle area = 0.5 * sqrt((cx^2 + cy^2) + cz^2) of the cross product of (p_i - p_0) and
+ *     (p_{i+1} - p_0); the areas are added in loop / fan order per cube, cubes in flat order.
+ * ======================================================================================== */
+static int mc_edge_id(int axis, int dp, int dq) { return 4 * axis + 2 * dp + dq; }
+
+static double mc_cube_area(const double v[2][2][2], const double *dx) {
+    int inside[2][2][2], any_in = 0, any_out = 0;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
+        inside[a][b][c] = v[a][b][c] > 0;
+        if (inside[a][b][c]) any_in = 1; else any_out = 1;
+    }
+    if (!any_in || !any_out) return 0.0;
+    double pos[12][3];
+    int cut[12];
+    for (int e = 0; e < 12; ++e) cut[e] = 0;
+    for (int axis = 0; axis < 3; ++axis)
+        for (int dp = 0; dp < 2; ++dp) for (int dq = 0; dq < 2; ++dq) {
+            int lo[3], hi[3], p = axis == 0 ? 1 : 0, q = axis == 2 ? 1 : 2;
+            lo[axis] = 0; hi[axis] = 1; lo[p] = hi[p] = dp; lo[q] = hi[q] = dq;
+            double vl = v[lo[0]][lo[1]][lo[2]], vh = v[hi[0]][hi[1]][hi[2]];
+            int e = mc_edge_id(axis, dp, dq);
+            if ((vl > 0) != (vh > 0)) {
+                cut[e] = 1;
+                double t = vl / (vl - vh);
+                for (int k = 0; k < 3; ++k) pos[e][k] = (double)lo[k] * dx[k];
+                pos[e][axis] = t * dx[axis];
+            }
+        }
+    int nb[12][2], nnb[12];
+    for (int e = 0; e < 12; ++e) nnb[e] = 0;
+#define MC_LINK(E, F) do { nb[E][nnb[E]++] = (F); nb[F][nnb[F]++] = (E); } while (0)
+    for (int axis = 0; axis < 3; ++axis)
+        for (int s = 0; s < 2; ++s) {
+            int p = axis == 0 ? 1 : 0, q = axis == 2 ? 1 : 2;
+            /* corners of the face in cyclic order (dp,dq) = 00, 01, 11, 10 and the face edge
+             * BETWEEN corner i and corner i+1 */
+            const int cp[4] = {0, 0, 1, 1}, cq[4] = {0, 1, 1, 0};
+            int fe[4], in4[4];
+            double val[4];
+            for (int i = 0; i < 4; ++i) {
+                int c[3];
+                c[axis] = s; c[p] = cp[i]; c[q] = cq[i];
+                val[i] = v[c[0]][c[1]][c[2]];
+                in4[i] = val[i] > 0;
+            }
+            /* edge 0: along q at dp=0; edge 1: along p at dq=1; edge 2: along q at dp=1;
+             * edge 3: along p at dq=0.  Edge ids need the (other two axes) coordinates in
+             * increasing axis order. */
+            for (int i = 0; i < 4; ++i) {
+                int along = (i % 2 == 0) ? q : p;
+                int c[3];
+                c[axis] = s;
+                if (along == q) c[p] = (i == 0) ? 0 : 1; else c[q] = (i == 1) ? 1 : 0;
+                int o1 = along == 0 ? 1 : 0, o2 = along == 2 ? 1 : 2;
+                fe[i] = mc_edge_id(along, c[o1], c[o2]);
+            }
+            int ncut = 0;
+            for (int i = 0; i < 4; ++i) ncut += cut[fe[i]];
+            if (ncut == 2) {
+                int a = -1, b = -1;
+                for (int i = 0; i < 4; ++i) if (cut[fe[i]]) { if (a < 0) a = fe[i]; else b = fe[i]; }
+                MC_LINK(a, b);
+            } else if (ncut == 4) {
+                /* corner i touches face edges i-1 and i */
+                double pin = 1.0, pout = 1.0;
+                for (int i = 0; i < 4; ++i) { if (in4[i]) pin *= val[i]; else pout *= val[i]; }
+                int cut_off_inside = !(pin > pout);
+                for (int i = 0; i < 4; ++i)
+                    if (in4[i] == cut_off_inside) MC_LINK(fe[(i + 3) % 4], fe[i]);
+            }
+        }
+#undef MC_LINK
+    int seen[12];
+    for (int e = 0; e < 12; ++e) seen[e] = 0;
+    double area = 0.0;
+    for (int e0 = 0; e0 < 12; ++e0) {
+        if (!cut[e0] || seen[e0] || nnb[e0] != 2) continue;
+        seen[e0] = 1;
+        int prev = e0, cur = nb[e0][0], last = -1;
+        while (cur != e0) {
+            seen[cur] = 1;
+            if (last >= 0) {
+                double a[3], b[3];
+                for (int k = 0; k < 3; ++k) { a[k] = pos[last][k] - pos[e0][k]; b[k] = pos[cur][k] - pos[e0][k]; }
+                double cx = a[1] * b[2] - a[2] * b[1];
+                double cy = a[2] * b[0] - a[0] * b[2];
+                double cz = a[0] * b[1] - a[1] * b[0];
+                area += 0.5 * sqrt((cx * cx + cy * cy) + cz * cz);
+            }
+            last = cur;
+            int nxt = nb[cur][0] == prev ? nb[cur][1] : nb[cur][0];
+            prev = cur; cur = nxt;
+        }
+    }
+    return area;
+}
+
+double orc_marching_cubes_area(int n0, int n1, int n2, const double *u, const double *dx) {
+    double total = 0.0;
+    for (long i = 0; i + 1 < n0; ++i)
+        for (long j = 0; j + 1 < n1; ++j)
+            for (long k = 0; k + 1 < n2; ++k) {
+                double v[2][2][2];
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c)
+                    v[a][b][c] = u[((i + a) * n1 + (j + b)) * n2 + (k + c)];
+                total += mc_cube_area(v, dx);
+            }
+    return total;
+}

@@ -52,6 +52,7 @@ def _lib():
         _LIB.orc_fmm_distance.restype = ctypes.c_long
         _LIB.orc_skfmm_literal_distance.restype = ctypes.c_long
         _LIB.orc_marching_squares_length.restype = ctypes.c_double
+        _LIB.orc_marching_cubes_area.restype = ctypes.c_double
     return _LIB
 
 
@@ -250,11 +251,16 @@ def com_ray_columns(u, img, mask, dx, n_samples):
 
 
 def boundary_size(u, dx):
-    """BoundarySize (shape.py:56-89).  2-D only here (3-D needs Lewiner marching cubes)."""
-    if u.ndim != 2:
-        raise NotImplementedError("oracle: surface area (marching_cubes_lewiner) not restated")
+    """BoundarySize (shape.py:56-89): marching-squares length (2-D), marching-cubes area (3-D;
+    orc_marching_cubes_area -- scikit-image's Lewiner variant is absent: parity unpinned)."""
     u = np.ascontiguousarray(u, dtype=np.float64)
     dx = np.asarray(dx, dtype=np.float64).copy()
+    if u.ndim == 3:
+        return float(_lib().orc_marching_cubes_area(
+            ctypes.c_int(u.shape[0]), ctypes.c_int(u.shape[1]), ctypes.c_int(u.shape[2]),
+            _p(u, _c_dbl_p), _p(dx, _c_dbl_p)))
+    if u.ndim != 2:
+        raise ValueError("Boundary size is only defined for dimensions 2 and 3")
     return float(_lib().orc_marching_squares_length(
         ctypes.c_int(u.shape[0]), ctypes.c_int(u.shape[1]), _p(u, _c_dbl_p), _p(dx, _c_dbl_p),
         ctypes.c_int(1)))

@@ -10,7 +10,7 @@ same calls, same assertions, with ``lsml.*`` replaced by a ``pkg`` fixture.  ``p
 Tests that never reach a kernel (validation, equality, balance_mask, seeds) run against
 ``lsml_b200`` on the CPU as well.  Left out, with the reason: ``test_datasets_handler.py`` (HDF5
 store, out of scope), the 3-D
-``BoundarySize`` / ``IsoperimetricRatio`` tests (Lewiner marching cubes: not implemented,
+``BoundarySize`` / ``IsoperimetricRatio`` tests (marching cubes: the b200 leg only,
 asserted as such).  The 3-D grids of test_shape.py are subsampled by 2 per axis on the CPU
 (reference) leg to keep it to seconds; the GPU leg uses the reference's sizes.
 """
@@ -353,16 +353,28 @@ def test_boundary_size_and_isoperimetric_2d(pkg):
     almost(1, ratio[0, 0], places=3)
 
 
-def test_boundary_size_3d_is_declared_missing(pkg):
-    """test_shape.py:59-74, 92-107: the Lewiner marching-cubes area has no device kernel yet; the
-    drop-in says so instead of computing something else."""
+def test_boundary_size_and_isoperimetric_3d(pkg):
+    """test_shape.py:59-74, 92-107 (sphere area 4 pi to 0 places, sphericity 1 to 2 places; the
+    reference's meshgrid / dx ordering quirk is kept: arrays are (len(y), len(x), len(z)) while dx
+    is passed as [dx, dy, dz])."""
     if pkg.name == "reference":
         pytest.skip("scikit-image (marching_cubes_lewiner) is not installed")
-    w = np.ones((8, 8, 8))
-    w[:4] = -1
-    for cls in (pkg.shape.BoundarySize, pkg.shape.IsoperimetricRatio):
-        with pytest.raises(NotImplementedError):
-            cls(ndim=3)(u=w, mask=_first_voxel_mask(w.shape), dx=[1, 1, 1])
+    sub = pkg.sub3d
+    x, dx = np.linspace(-2, 2, (501 - 1) // sub + 1, retstep=True)
+    y, dy = np.linspace(-2, 2, (401 - 1) // sub + 1, retstep=True)
+    z, dz = np.linspace(-2, 2, (601 - 1) // sub + 1, retstep=True)
+    xx, yy, zz = np.meshgrid(x, y, z)
+    w = 1 - np.sqrt(xx ** 2 + yy ** 2 + zz ** 2)
+    area = pkg.shape.BoundarySize(ndim=3)(u=w, mask=_first_voxel_mask(w.shape), dx=[dx, dy, dz])
+    almost(4 * np.pi, area[0, 0, 0], places=0)
+    x, dx = np.linspace(-2, 2, (201 - 1) // sub + 1, retstep=True)
+    y, dy = np.linspace(-2, 2, (201 - 1) // sub + 1, retstep=True)
+    z, dz = np.linspace(-2, 2, (901 - 1) // sub + 1, retstep=True)
+    xx, yy, zz = np.meshgrid(x, y, z)
+    w = 1 - np.sqrt(xx ** 2 + yy ** 2 + zz ** 2)
+    ratio = pkg.shape.IsoperimetricRatio(ndim=3)(u=w, mask=_first_voxel_mask(w.shape),
+                                                  dx=[dx, dy, dz])
+    almost(1, ratio[0, 0, 0], places=2 if sub == 1 else 1)
 
 
 def test_moments_2d(pkg):
