@@ -157,11 +157,15 @@ int lsml_linear_predict(const double *X, const long long *n_band, int nfeat, con
 /* nodes: 32-byte super nodes (an internal node and its two children per entry, see regress.cu;
  * 32-byte aligned); leaves: float64 leaf values; root_ref: unsigned[n_trees], the root super
  * node of each tree or -- root_is_leaf[t] != 0 -- the leaf index of a single-leaf tree;
- * divisor = n_estimators */
+ * divisor = n_estimators.  nodes8 / tree_base / max_nodes (optional, NULL / 0): the same forest
+ * as 8-byte single nodes, int[n_trees + 1] first node of each tree then the node count, and the
+ * size of the largest tree -- forests of small trees (max_nodes <= 2048) are then walked from
+ * shared memory, tree by tree (regress.cu: forest_staged_kernel). */
 int lsml_forest_predict(const double *X, const long long *n_band, int nfeat, const double *mean,
                         const double *scale, const void *nodes, const double *leaves,
                         const unsigned *root_ref, const uint8_t *root_is_leaf, int n_trees,
-                        double divisor, double *out, void *stream);
+                        double divisor, const void *nodes8, const int *tree_base, int max_nodes,
+                        double *out, void *stream);
 /* sizes: HOST int[n_layers+1]; W, b: HOST arrays of n_layers DEVICE pointers;
  * act: 0 identity, 1 relu, 2 tanh, 3 logistic */
 int lsml_mlp_predict(const double *X, const long long *n_band, const double *mean,
@@ -194,7 +198,8 @@ int lsml_linear_predict_band(const lsml_band_source *src, const long long *n_ban
 int lsml_forest_predict_band(const lsml_band_source *src, const long long *n_band,
                              const double *mean, const double *scale, const void *nodes,
                              const double *leaves, const unsigned *root_ref,
-                             const uint8_t *root_is_leaf, int n_trees, double divisor, double *out,
+                             const uint8_t *root_is_leaf, int n_trees, double divisor,
+                             const void *nodes8, const int *tree_base, int max_nodes, double *out,
                              void *stream);
 int lsml_mlp_predict_band(const lsml_band_source *src, const long long *n_band, const double *mean,
                           const double *scale, int n_layers, const int *sizes,

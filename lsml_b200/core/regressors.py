@@ -204,6 +204,7 @@ class ForestDeviceRegressor(DeviceRegressor):
         self.tree_base = _dev(bases, device)
         self.root_is_leaf = _dev(root_leaf, device)
         self.divisor = float(divisor)
+        self.max_nodes = int(np.diff(bases).max()) if len(bases) > 1 else 0
         self._super = self._pack_super(nodes, bases, root_leaf)
 
     def _pack_super(self, nodes, bases, root_leaf):
@@ -215,7 +216,9 @@ class ForestDeviceRegressor(DeviceRegressor):
 
     def _layout(self):
         if getattr(self, "_super", None) is None:      # built around exported arrays (fixtures)
-            self._super = self._pack_super(self.nodes.cpu().numpy(), self.tree_base.cpu().numpy(),
+            bases = self.tree_base.cpu().numpy()
+            self.max_nodes = int(np.diff(bases).max()) if len(bases) > 1 else 0
+            self._super = self._pack_super(self.nodes.cpu().numpy(), bases,
                                            self.root_is_leaf.cpu().numpy())
         return self._super
 
@@ -225,7 +228,8 @@ class ForestDeviceRegressor(DeviceRegressor):
             _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
             _lib.ptr(self.scale), _lib.ptr(sn), _lib.ptr(leaves), _lib.ptr(root_ref),
             _lib.ptr(self.root_is_leaf), ctypes.c_int(self.n_trees),
-            ctypes.c_double(self.divisor), _lib.ptr(out), _lib.current_stream()),
+            ctypes.c_double(self.divisor), _lib.ptr(self.nodes), _lib.ptr(self.tree_base),
+            ctypes.c_int(self.max_nodes), _lib.ptr(out), _lib.current_stream()),
             "forest_predict")
 
     def predict_band(self, src, n_band, out):
@@ -234,7 +238,8 @@ class ForestDeviceRegressor(DeviceRegressor):
             ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean),
             _lib.ptr(self.scale), _lib.ptr(sn), _lib.ptr(leaves), _lib.ptr(root_ref),
             _lib.ptr(self.root_is_leaf), ctypes.c_int(self.n_trees),
-            ctypes.c_double(self.divisor), _lib.ptr(out), _lib.current_stream()),
+            ctypes.c_double(self.divisor), _lib.ptr(self.nodes), _lib.ptr(self.tree_base),
+            ctypes.c_int(self.max_nodes), _lib.ptr(out), _lib.current_stream()),
             "forest_predict_band")
 
 

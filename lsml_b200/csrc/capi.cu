@@ -319,9 +319,10 @@ int lsml_linear_predict(const double* X, const long long* n_band, int nfeat, con
 int lsml_forest_predict(const double* X, const long long* n_band, int nfeat, const double* mean,
                         const double* scale, const void* nodes, const double* leaves,
                         const unsigned* root_ref, const uint8_t* root_is_leaf, int n_trees,
-                        double divisor, double* out, void* stream) {
+                        double divisor, const void* nodes8, const int* tree_base, int max_nodes,
+                        double* out, void* stream) {
     return forest_predict(X, n_band, nfeat, mean, scale, nodes, leaves, root_ref, root_is_leaf,
-                          n_trees, divisor, out, (cudaStream_t)stream);
+                          n_trees, divisor, nodes8, tree_base, max_nodes, out, (cudaStream_t)stream);
 }
 int lsml_mlp_predict(const double* X, const long long* n_band, const double* mean,
                      const double* scale, int n_layers, const int* sizes,
@@ -359,12 +360,14 @@ int lsml_linear_predict_band(const lsml_band_source* src, const long long* n_ban
 int lsml_forest_predict_band(const lsml_band_source* src, const long long* n_band,
                              const double* mean, const double* scale, const void* nodes,
                              const double* leaves, const unsigned* root_ref,
-                             const uint8_t* root_is_leaf, int n_trees, double divisor, double* out,
+                             const uint8_t* root_is_leaf, int n_trees, double divisor,
+                             const void* nodes8, const int* tree_base, int max_nodes, double* out,
                              void* stream) {
     BandFeatures bf;
     if (band_source(src, bf)) return 1;
     return forest_predict_band(bf, n_band, mean, scale, nodes, leaves, root_ref, root_is_leaf,
-                               n_trees, divisor, out, (cudaStream_t)stream);
+                               n_trees, divisor, nodes8, tree_base, max_nodes, out,
+                               (cudaStream_t)stream);
 }
 int lsml_mlp_predict_band(const lsml_band_source* src, const long long* n_band, const double* mean,
                           const double* scale, int n_layers, const int* sizes,

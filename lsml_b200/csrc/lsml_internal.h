@@ -65,11 +65,13 @@ int linear_predict_band(const BandFeatures& bf, const i64* n_band, const double*
 int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
                    const double* scale, const void* nodes, const double* leaves,
                    const unsigned* root_ref, const u8* root_is_leaf, int n_trees, double divisor,
-                   double* out, cudaStream_t s);
+                   const void* nodes8, const int* tree_base, int max_nodes, double* out,
+                   cudaStream_t s);
 int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
                         const double* scale, const void* nodes, const double* leaves,
                         const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
-                        double divisor, double* out, cudaStream_t s);
+                        double divisor, const void* nodes8, const int* tree_base, int max_nodes,
+                        double* out, cudaStream_t s);
 int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
                 int n_layers, const int* sizes, const double* const* W, const double* const* b,
                 int act, double* out, cudaStream_t s);

@@ -29,9 +29,16 @@
 // (not HBM-bound); one thread per band voxel with the voxel's float32 features staged in shared
 // memory as [feature][thread] (conflict-free).  Super nodes halve the number of dependent,
 // fully divergent fetches per tree walk compared with the 8-byte single nodes of round 1.
-// Measured alternatives (round 1, tools/forest_probe.py, 270k x 16, RF-100): the current tree
-// staged in shared memory with 4 voxels per thread was 2x SLOWER, 2 or 4 trees in flight per
-// thread also slower: the limit is the number of divergent L1 sectors per warp-load.
+// Measured (round 2, tools/forest_probe.py: 285 k band voxels x 16 features, RF-100 of 599-node
+// trees, B200): super nodes 531 us; 8-byte single nodes, one level per fetch, 582 us; every lane
+// advancing through the forest at its own pace (no idling on the warp's deepest lane) 568 us;
+// the current tree staged in shared memory (cp.async, double-buffered) with 2 / 4 voxels per
+// thread 560 / 599 us (kept below: forest_staged_kernel, LSML_FOREST_VARIANT=staged2|staged4).
+// Five different node paths, one time: ncu (profiles/r2_ncu_forest.txt) shows 257 M warp
+// instructions, issue slots 41 % busy, 48 % of the warp slots occupied on average (8.9 k warps
+// on 9.5 k slots: one wave whose length is its slowest warp), 22 of 32 lanes active -- the
+// walk is bound by instruction issue x occupancy, not by where the nodes live.
+#include <cstdlib>
 #include "lsml_internal.h"
 #include "band_features.cuh"
 
@@ -109,6 +116,16 @@ __device__ __forceinline__ SuperNode load_node(const SuperNode* p) {
 
 constexpr int FOREST_THREADS = 128;
 
+// the canonical 8-byte single-node export (regressors.py: pack_trees)
+struct StagedForestView {
+    const uint2* nodes;        // all trees back to back
+    const int* tree_base;      // [n_trees + 1]
+    const u8* root_is_leaf;    // [n_trees]
+    int n_trees;
+    int max_nodes;             // largest tree
+    double divisor;
+};
+
 __global__ void __launch_bounds__(FOREST_THREADS)
 forest_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, ForestView fv,
                       double* __restrict__ out) {
@@ -149,6 +166,105 @@ forest_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Fo
             acc += __ldg(fv.leaves + ref);
         }
         out[b] = acc / fv.divisor;
+    }
+}
+
+// Forests whose trees are small (RandomForest with max_samples, the configuration of the
+// reference's examples: <= ~600 nodes, 4.8 KB per tree): the CTA walks the forest tree by tree
+// with the CURRENT tree staged in shared memory (cp.async, double-buffered: tree t+1 streams in
+// while tree t is walked) and V voxels per thread, i.e. V independent pointer chases per thread
+// to hide the shared-memory latency.  A divergent node fetch then costs the bank conflicts of a
+// 64-bit shared load (~3-4 wavefronts per warp) instead of up to 32 L1 tag lookups.  Nodes are
+// the canonical 8-byte single nodes (children adjacent; the parent's word says which child is a
+// leaf; a leaf holds its float64 value), see lsml_b200/core/regressors.py: pack_trees.
+typedef StagedForestView StagedForest;
+
+constexpr int STAGED_THREADS = 256;
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <int V>
+__global__ void __launch_bounds__(STAGED_THREADS)
+forest_staged_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, StagedForest fv,
+                     double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PER_CTA = V * STAGED_THREADS;
+    uint2* tree_buf[2];
+    tree_buf[0] = reinterpret_cast<uint2*>(smem_raw);
+    tree_buf[1] = tree_buf[0] + fv.max_nodes;
+    float* feat = reinterpret_cast<float*>(tree_buf[1] + fv.max_nodes);     // [F][PER_CTA]
+    const i64 nb = *n_band;
+    const i64 nblocks = (nb + PER_CTA - 1) / PER_CTA;
+    const int F = src.F;
+    for (i64 blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        __syncthreads();                          // previous block's walks are done with smem
+        // tree 0 starts streaming while the features are gathered
+        {
+            const int b0 = __ldg(fv.tree_base), n0 = __ldg(fv.tree_base + 1) - b0;
+            for (int k = threadIdx.x; k < n0; k += STAGED_THREADS) cp_async8(tree_buf[0] + k, fv.nodes + b0 + k);
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const i64 b = blk * PER_CTA + v * STAGED_THREADS + threadIdx.x;
+            if (b < nb) {
+                const VoxelRef vr = row_ref(src, b);
+                for (int f = 0; f < F; ++f)
+                    feat[f * PER_CTA + v * STAGED_THREADS + threadIdx.x] =
+                        __double2float_rn(scaled(src, b, vr, f, sc));
+            }
+        }
+        double acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.0;
+        cp_async_commit_wait_all();
+        __syncthreads();
+        for (int t = 0; t < fv.n_trees; ++t) {
+            const uint2* tree = tree_buf[t & 1];
+            if (t + 1 < fv.n_trees) {             // stream the next tree into the other buffer
+                const int b1 = __ldg(fv.tree_base + t + 1), n1 = __ldg(fv.tree_base + t + 2) - b1;
+                uint2* dst = tree_buf[(t + 1) & 1];
+                for (int k = threadIdx.x; k < n1; k += STAGED_THREADS) cp_async8(dst + k, fv.nodes + b1 + k);
+            }
+            const bool root_leaf = __ldg(fv.root_is_leaf + t) != 0;
+            int idx[V];
+            unsigned live = 0u;                   // chains still descending
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                idx[v] = 0;
+                const i64 b = blk * PER_CTA + v * STAGED_THREADS + threadIdx.x;
+                if (b < nb && !root_leaf) live |= 1u << v;
+            }
+            while (live) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if (!((live >> v) & 1u)) continue;
+                    const uint2 nd = tree[idx[v]];
+                    const unsigned meta = nd.y;
+                    const float x = feat[(meta >> 24) * PER_CTA + v * STAGED_THREADS + threadIdx.x];
+                    const bool right = !(x <= __uint_as_float(nd.x));
+                    idx[v] = (int)(meta & 0x3fffffu) + (right ? 1 : 0);
+                    if (right ? ((meta >> 22) & 1u) : ((meta >> 23) & 1u)) live &= ~(1u << v);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const uint2 lv = tree[idx[v]];    // (a dead lane reads node 0: harmless)
+                acc[v] += __hiloint2double((int)lv.y, (int)lv.x);
+            }
+            cp_async_commit_wait_all();
+            __syncthreads();                      // tree t+1 complete, tree t's buffer free
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const i64 b = blk * PER_CTA + v * STAGED_THREADS + threadIdx.x;
+            if (b < nb) out[b] = acc[v] / fv.divisor;
+        }
     }
 }
 
@@ -227,11 +343,57 @@ static int linear_launch(const FeatSrc& src, const i64* n_band, const double* me
     return 0;
 }
 
+// variant selection (probes): LSML_FOREST_VARIANT = "staged2" / "staged4" runs the shared-memory
+// kernel with 2 / 4 voxels per thread instead of the super-node kernel
+static int forest_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LSML_FOREST_VARIANT");
+        v = 0;
+        if (e && e[0] == 'g') v = 1;
+        if (e && e[0] == 's') v = (e[6] == '4') ? 4 : 2;
+    }
+    return v;
+}
+
+template <int V>
+static int staged_launch(const FeatSrc& src, const i64* n_band, const Scaler& sc,
+                         const StagedForest& fv, double* out, cudaStream_t s, bool* done) {
+    const size_t smem = 2 * (size_t)fv.max_nodes * sizeof(uint2) +
+                        (size_t)src.F * V * STAGED_THREADS * sizeof(float);
+    *done = false;
+    if (smem > 100 * 1024) return 0;              // would leave < 2 CTAs per SM: not worth it
+    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (smem > 48 * 1024 && smem > configured[V]) {
+        LSML_CUDA(cudaFuncSetAttribute(forest_staged_kernel<V>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[V] = smem;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 2048 / STAGED_THREADS) per_sm = 2048 / STAGED_THREADS;
+    forest_staged_kernel<V><<<LSML_SMS * per_sm, STAGED_THREADS, smem, s>>>(src, n_band, sc, fv, out);
+    LSML_LAUNCH_CHECK("forest_staged_kernel");
+    *done = true;
+    return 0;
+}
+
 static int forest_launch(const FeatSrc& src, const i64* n_band, const double* mean,
                          const double* scale, const void* nodes, const double* leaves,
                          const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
-                         double divisor, double* out, cudaStream_t s) {
+                         double divisor, const void* nodes8, const int* tree_base, int max_nodes,
+                         double* out, cudaStream_t s) {
     if (src.F > 255) { set_error("forest: at most 255 features"); return 1; }
+    const int variant = forest_variant();
+    if (nodes8 != nullptr && tree_base != nullptr && max_nodes > 0 && max_nodes <= 2048 &&
+        (variant == 2 || variant == 4)) {
+        const Scaler sc8{mean, scale};
+        const StagedForest sf{static_cast<const uint2*>(nodes8), tree_base, root_is_leaf, n_trees,
+                              max_nodes, divisor};
+        bool done = false;
+        const int st = variant == 4 ? staged_launch<4>(src, n_band, sc8, sf, out, s, &done)
+                                    : staged_launch<2>(src, n_band, sc8, sf, out, s, &done);
+        if (st || done) return st;
+    }
     if ((reinterpret_cast<uintptr_t>(nodes) & 31u) != 0) {
         set_error("forest: super nodes must be 32-byte aligned");
         return 1;
@@ -285,16 +447,18 @@ int linear_predict_band(const BandFeatures& bf, const i64* n_band, const double*
 int forest_predict(const double* X, const i64* n_band, int F, const double* mean,
                    const double* scale, const void* nodes, const double* leaves,
                    const unsigned* root_ref, const u8* root_is_leaf, int n_trees, double divisor,
-                   double* out, cudaStream_t s) {
+                   const void* nodes8, const int* tree_base, int max_nodes, double* out,
+                   cudaStream_t s) {
     return forest_launch(matrix_source(X, F), n_band, mean, scale, nodes, leaves, root_ref,
-                         root_is_leaf, n_trees, divisor, out, s);
+                         root_is_leaf, n_trees, divisor, nodes8, tree_base, max_nodes, out, s);
 }
 int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
                         const double* scale, const void* nodes, const double* leaves,
                         const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
-                        double divisor, double* out, cudaStream_t s) {
+                        double divisor, const void* nodes8, const int* tree_base, int max_nodes,
+                        double* out, cudaStream_t s) {
     return forest_launch(program_source(bf), n_band, mean, scale, nodes, leaves, root_ref,
-                         root_is_leaf, n_trees, divisor, out, s);
+                         root_is_leaf, n_trees, divisor, nodes8, tree_base, max_nodes, out, s);
 }
 
 int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,

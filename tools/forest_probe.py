@@ -1,28 +1,41 @@
-"""Times forest inference alone on a synthetic band feature matrix (B x 16, RF-100)."""
-import os, sys, warnings
+"""Times the velocity kernel (feature program -> forest) on the bench's C3 state and checks it
+against scikit-learn.  LSML_FOREST_VARIANT = global | staged2 | staged4 selects the kernel
+(regress.cu); run once per variant:  python tools/forest_probe.py [n]"""
+import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sklearn.ensemble import RandomForestRegressor
-from sklearn.pipeline import Pipeline
-from sklearn.preprocessing import StandardScaler
+import bench
+from lsml_b200.core.engine import BandEngine
+from lsml_b200.core.model import _ball_u0
 from lsml_b200.core.regressors import export_regressor
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 270000
-rs = np.random.RandomState(0)
-X = rs.randn(B, 16); X[:, 8:] = np.cumsum(rs.randn(B, 8) * 0.01, axis=0)   # spatially coherent columns
-y = X[:, 0] + np.sin(3 * X[:, 9]) + 0.3 * rs.randn(B)
-sub = rs.choice(B, 20000, replace=False)
-with warnings.catch_warnings():
-    warnings.simplefilter("ignore")
-    reg = Pipeline([("s", StandardScaler()), ("r", RandomForestRegressor(n_estimators=100, max_samples=300, random_state=0))]).fit(X[sub], y[sub])
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 dev = torch.device("cuda")
-dreg = export_regressor(reg, dev)
-Xd = torch.from_numpy(X).to(dev)
-out = dreg.predict(Xd)
-want = reg.predict(X)
-print("max abs diff vs sklearn:", np.abs(out.cpu().numpy() - want).max(), "nodes", dreg.n_nodes)
-nb = torch.tensor([B], dtype=torch.int64, device=dev); o = torch.empty(B, dtype=torch.float64, device=dev)
+img, radius, c = bench.make_volume(n, 1234)
+eng = BandEngine((n, n, n), 1, dx=np.ones(3), band=3.0, specs=bench.SPECS, device=dev)
+eng.load_images(img[None], normalize=True)
+u0 = _ball_u0(eng, 0.5 * np.array([[n, n, n]], dtype=np.float64), [60.0 * n / 256]).clone()
+eng.set_level_sets(u0)
+nb = eng.n_band
+X = eng.compute_features().cpu().numpy()
+idx = eng.band_idx[:nb].cpu().numpy()
+y = bench.target_distance_on_band(idx, n, radius, c)
+host = bench._fit_forest(X, y, 7)
+reg = export_regressor(host, dev)
+eng._ensure_band_buffers()
+eng._item_level_features()
+def run():
+    reg.predict_band(eng.band_source(), eng.n_band_dev, eng.vel)
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
 ts = []
-for i in range(8):
+for _ in range(10):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); dreg.predict_into(Xd, nb, o); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b) * 1e3)
-print("forest predict %d x 16, 100 trees: %.1f us (median)" % (B, np.median(ts)))
+    a.record(); run(); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b) * 1e3)
+got = eng.vel[:nb].cpu().numpy()
+want = host.predict(X)
+print("variant %-8s band %d trees %d max_nodes %d: %.1f us (median of 10), equal to sklearn: %s"
+      % (os.environ.get("LSML_FOREST_VARIANT", "default"), nb, reg.n_trees, reg.max_nodes,
+         float(np.median(ts)), bool(np.array_equal(got, want))))
