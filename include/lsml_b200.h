@@ -133,6 +133,12 @@ int lsml_assemble_features(int nfeat, const int *kind, const int *a, const int *
                            const double *planes, long long plane_stride,
                            const double *item_feat, const double *com, double *X, void *stream);
 
+/* The dense float64 3-D gmag_os runs as a TMA plane pipeline (cp.async.bulk.tensor + mbarrier
+ * stages, csrc/stencil.cu) when the grid is eligible; on = 0 forces the register-marching
+ * generation instead, on = 1 re-enables it, on < 0 only queries.  Returns the previous setting.
+ * Both generations are bit-exact; the switch exists for A/B measurements and tests. */
+int lsml_stencil_use_tma(int on);
+
 /* Moments of order > 2 (shape.py:214-230 takes any order >= 1): from exact per-axis histograms of
  * {u > 0}; writes item_feat[item*nfeat + cols[q]] for the ncols requested (axis, order) pairs.
  * Call after lsml_item_features (needs com); cols/axes/orders are DEVICE int arrays. */

@@ -286,6 +286,8 @@ int lsml_band_sums(long long voxels, long long batch, const double* planes,
     return band_sums(voxels, batch, planes, plane_stride, nplanes, band_idx, item_offsets, mode,
                      mean, sums, workspace, (cudaStream_t)stream);
 }
+int lsml_stencil_use_tma(int on) { return stencil_use_tma(on); }
+
 long long lsml_axis_moments_workspace_bytes(int ndim, const int* shape, long long batch) {
     const double* dx = nullptr;
     Geom g;

@@ -11,6 +11,8 @@ template <typename T>
 int gradient_centered_dense(const Geom& g, const T* A, const u8* mask, T* grads, T* gmag,
                             int normalize, cudaStream_t s);
 
+int stencil_use_tma(int on);
+
 // compact.cu
 i64 compact_workspace_bytes(i64 total);
 int compact_mask(i64 total, const u8* mask, i64* band_idx, i64* n_band, void* workspace,

@@ -13,6 +13,7 @@
 // (a 256^2 f64 plane is 512 KB; L2 is 126 MB).  Each voxel of A is therefore fetched from
 // HBM once.  Masked-out voxels issue no loads at all (band masks touch ~2% of the grid).
 #include <cstdlib>
+#include <cuda.h>
 #include "common.cuh"
 
 namespace lsml {
@@ -456,6 +457,200 @@ gmag_os_marchv_kernel(const T* __restrict__ A, const u8* __restrict__ mask,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA plane pipeline (the 256^3 / 1024^3 float64 case; north_star: "shared-memory or TMA tile
+// staging, halos").
+//
+// ncu on the vectorised march above: 311 instructions per two-voxel iteration, issue slots 49 %
+// busy at 24 warps/SM, DRAM 39 % -- more than half of the instructions are 64-bit address
+// arithmetic, pointer bumps and the seven global loads per iteration.  Here NO consumer thread
+// computes a global load address: a CTA owns a (TJ x TK) column tile of a chunk of planes and
+// marches along axis 0 while one producer warp streams, per plane,
+//     the A tile WITH its one-voxel halo   (TJ+2) x (TK+4) doubles   cp.async.bulk.tensor.4d
+//     the nu tile                           TJ x TK doubles
+//     the mask tile                         TJ x TK bytes
+// into a ring of shared-memory stages through three tensor maps over (k, j, i, item); an
+// mbarrier per stage carries the byte count (full) and the consumers' release (empty), so the
+// eight consumer warps never meet at a block barrier.  Out-of-range halo cells are zero-filled
+// by the TMA unit and then overridden by the reference's border rule (b := f at index 0,
+// f := b at index n-1; masked_gradient.c:165-176) exactly as in the kernels above.  Every
+// stencil neighbour is a shared-memory load at a CONSTANT offset from one base register
+// (16-byte LDS for the pairs along k: the halo is two cells wide on the left to keep them
+// aligned).  A[i-1] and A[i] of the column stay in registers.  The arithmetic is the vectorised
+// kernel's (bit-exact, same range test and fallback).
+// ---------------------------------------------------------------------------------------------
+constexpr int TM_TJ = 8, TM_TK = 64;            // tile: 8 rows (one consumer warp each) x 64 voxels
+constexpr int TM_AW = TM_TK + 4;                // A row in smem: k0-2 .. k0+TK+1
+constexpr int TM_STAGES = 4;                    // nu / mask ring
+constexpr int TM_A_RING = TM_STAGES + 2;        // A planes i-1, i and the STAGES planes in flight
+constexpr int TM_CHUNK = 32;                    // planes per CTA
+constexpr int TM_A_BYTES = (TM_TJ + 2) * TM_AW * 8;      // 5440 bytes land per A tile ...
+constexpr int TM_A_SLOT = (TM_A_BYTES + 127) / 128 * 128;  // ... in 128-byte aligned ring slots
+constexpr int TM_NU_BYTES = TM_TJ * TM_TK * 8;           // 4096
+constexpr int TM_M_BYTES = TM_TJ * TM_TK;                // 512
+constexpr int TM_CONSUMERS = TM_TJ * 32;                 // 256 threads
+constexpr int TM_THREADS = TM_CONSUMERS + 32;            // + the producer warp
+constexpr size_t TM_SMEM = (size_t)TM_A_RING * TM_A_SLOT + (size_t)TM_STAGES * (TM_NU_BYTES + TM_M_BYTES) +
+                           2 * (TM_STAGES + 1) * 8 + 128;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LSML_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LSML_DONE;\n"
+        "bra LSML_WAIT;\n"
+        "LSML_DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const void* map, unsigned bar, int c0,
+                                            int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct TmaMaps {           // CUtensorMap is 128 bytes, 64-byte aligned
+    alignas(64) unsigned char a[128];
+    alignas(64) unsigned char nu[128];
+    alignas(64) unsigned char m[128];
+};
+
+template <bool EXACT, bool UNIT>
+__global__ void __launch_bounds__(TM_THREADS)
+gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* __restrict__ out,
+                   StencilParams p) {
+    extern __shared__ __align__(128) unsigned char tm_smem[];
+    // TMA destinations must be 128-byte aligned
+    unsigned char* sA = tm_smem + ((128u - (smem_u32(tm_smem) & 127u)) & 127u);   // A_RING A tiles
+    unsigned char* sNu = sA + TM_A_RING * TM_A_SLOT;               // STAGES nu tiles
+    unsigned char* sM = sNu + TM_STAGES * TM_NU_BYTES;                   // STAGES mask tiles
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sM + TM_STAGES * TM_M_BYTES);
+    // bars[0 .. STAGES): full, bars[STAGES .. 2 STAGES): empty, bars[2 STAGES]: prologue
+    const unsigned bar0 = smem_u32(bars);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned chunks = (unsigned)((p.n0 + TM_CHUNK - 1) / TM_CHUNK);
+    const int item = (int)(blockIdx.x / chunks), ci = (int)(blockIdx.x % chunks);
+    const int i0 = ci * TM_CHUNK, i1 = min(p.n0, i0 + TM_CHUNK), L = i1 - i0;
+    const int j0 = blockIdx.y * TM_TJ, k0 = blockIdx.z * TM_TK;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TM_STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);                          // full: the producer's expect_tx
+            mbar_init(bar0 + 8 * (TM_STAGES + s), TM_TJ);        // empty: one arrive per consumer warp
+        }
+        mbar_init(bar0 + 8 * 2 * TM_STAGES, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned stage_bytes = TM_A_BYTES + TM_NU_BYTES + (has_mask ? TM_M_BYTES : 0);
+    if (warp == TM_TJ) {
+        // ---------------------------------------------------------------- producer warp
+        if (lane == 0) {
+            // prologue: A planes i0-1 and i0 (ring slots 0 and 1)
+            const unsigned pro = bar0 + 8 * 2 * TM_STAGES;
+            mbar_expect_tx(pro, 2 * TM_A_BYTES);
+            tma_load_4d(smem_u32(sA), &maps.a, pro, k0 - 2, j0 - 1, i0 - 1, item);
+            tma_load_4d(smem_u32(sA + TM_A_SLOT), &maps.a, pro, k0 - 2, j0 - 1, i0, item);
+            for (int u = 0; u < L; ++u) {
+                const int s = u % TM_STAGES;
+                if (u >= TM_STAGES) mbar_wait(bar0 + 8 * (TM_STAGES + s), ((u / TM_STAGES) - 1) & 1);
+                const unsigned full = bar0 + 8 * s;
+                mbar_expect_tx(full, stage_bytes);
+                // A plane i0+u+1 -> ring slot (u+2) % A_RING (the slot of plane i0+u-STAGES-1, last
+                // read in iteration u-STAGES-1); nu / mask plane i0+u -> slot s
+                tma_load_4d(smem_u32(sA + ((u + 2) % TM_A_RING) * TM_A_SLOT), &maps.a, full,
+                            k0 - 2, j0 - 1, i0 + u + 1, item);
+                tma_load_4d(smem_u32(sNu + s * TM_NU_BYTES), &maps.nu, full, k0, j0, i0 + u, item);
+                if (has_mask)
+                    tma_load_4d(smem_u32(sM + s * TM_M_BYTES), &maps.m, full, k0, j0, i0 + u, item);
+            }
+        }
+        return;
+    }
+    // -------------------------------------------------------------------- consumer warps
+    const int ty = warp, tx = lane;
+    const int j = j0 + ty, k = k0 + 2 * tx;
+    const bool inside = j < p.n1 && k < p.n2;                 // (n2 is even: both voxels or none)
+    const bool jlo = j == 0, jhi = j == p.n1 - 1, klo = k == 0, khi = k + 2 == p.n2;
+    const bool border_jk = jlo | jhi | klo | khi;
+    // byte offset of this thread's centre pair inside an A tile / a nu tile / a mask tile
+    const unsigned oA = ((ty + 1) * TM_AW + 2 * tx + 2) * 8;
+    const unsigned oNu = (ty * TM_TK + 2 * tx) * 8;
+    const unsigned oM = ty * TM_TK + 2 * tx;
+    double* po = out + (((i64)item * p.n0 + i0) * p.n1 + j) * (i64)p.n2 + k;
+    mbar_wait(bar0 + 8 * 2 * TM_STAGES, 0);
+    double2 prv = *reinterpret_cast<const double2*>(sA + oA);
+    double2 cur = *reinterpret_cast<const double2*>(sA + TM_A_SLOT + oA);
+    for (int t = 0; t < L; ++t) {
+        const int s = t % TM_STAGES;
+        mbar_wait(bar0 + 8 * s, (t / TM_STAGES) & 1);
+        const unsigned char* tc = sA + ((t + 1) % TM_A_RING) * TM_A_SLOT;      // plane i
+        const unsigned char* tn = sA + ((t + 2) % TM_A_RING) * TM_A_SLOT;      // plane i+1
+        const double2 nxt = *reinterpret_cast<const double2*>(tn + oA);
+        unsigned m = 3u;
+        if (has_mask) {
+            const unsigned raw = *reinterpret_cast<const unsigned short*>(sM + s * TM_M_BYTES + oM);
+            m = ((raw & 0xffu) ? 1u : 0u) | ((raw & 0xff00u) ? 2u : 0u);
+        }
+        if (m && inside) {
+            const double2 jp = *reinterpret_cast<const double2*>(tc + oA + TM_AW * 8);
+            const double2 jm = *reinterpret_cast<const double2*>(tc + oA - TM_AW * 8);
+            const double left = *reinterpret_cast<const double*>(tc + oA - 8);
+            const double right = *reinterpret_cast<const double*>(tc + oA + 16);
+            const double2 nuv = *reinterpret_cast<const double2*>(sNu + s * TM_NU_BYTES + oNu);
+            const int i = i0 + t;
+            const bool ilo = i == 0, ihi = i == p.n0 - 1;
+            double res[2];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const double cc = v ? cur.y : cur.x;
+                double f0 = (v ? nxt.y : nxt.x) - cc, b0 = cc - (v ? prv.y : prv.x);
+                double f1 = (v ? jp.y : jp.x) - cc, b1 = cc - (v ? jm.y : jm.x);
+                double f2 = (v ? right : cur.y) - cc, b2 = cc - (v ? cur.x : left);
+                if (ilo) b0 = f0; else if (ihi) f0 = b0;                // uniform
+                if (border_jk) {                                        // rare threads only
+                    if (jlo) b1 = f1; else if (jhi) f1 = b1;
+                    if (v == 0 && klo) b2 = f2;
+                    if (v == 1 && khi) f2 = b2;
+                }
+                if (!UNIT) {
+                    f0 = scale_dx<double, EXACT>(f0, p.dx0, p.r0); b0 = scale_dx<double, EXACT>(b0, p.dx0, p.r0);
+                    f1 = scale_dx<double, EXACT>(f1, p.dx1, p.r1); b1 = scale_dx<double, EXACT>(b1, p.dx1, p.r1);
+                    f2 = scale_dx<double, EXACT>(f2, p.dx2, p.r2); b2 = scale_dx<double, EXACT>(b2, p.dx2, p.r2);
+                }
+                const bool neg = (v ? nuv.y : nuv.x) < 0.0;
+                const unsigned sgn = neg ? 0x80000000u : 0u;
+                double s4 = neg_part_sq4(flip_sign(b0, sgn)) + pos_part_sq4(flip_sign(f0, sgn));
+                s4 = (s4 + neg_part_sq4(flip_sign(b1, sgn))) + pos_part_sq4(flip_sign(f1, sgn));
+                s4 = (s4 + neg_part_sq4(flip_sign(b2, sgn))) + pos_part_sq4(flip_sign(f2, sgn));
+                double r = 0.5 * sqrt_nonneg(s4);
+                if (!scaled_sum_ok(s4)) r = gmag_os_exact<double>(b0, f0, b1, f1, b2, f2, neg);
+                res[v] = r;
+            }
+            if (m == 3u) *reinterpret_cast<double2*>(po) = make_double2(res[0], res[1]);
+            else if (m == 1u) po[0] = res[0];
+            else po[1] = res[1];
+        }
+        // this warp is done with stage s (its nu / mask tile, and the A plane i-1 behind it)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (TM_STAGES + s));
+        prv = cur; cur = nxt;
+        po += p.st0;
+    }
+}
+
 static bool marchv_eligible(const Geom& g, const void* a, const void* b, const void* c,
                             const void* m, int vec, size_t elem) {
     auto al = [&](const void* q, size_t n) { return q == nullptr || ((size_t)q % n) == 0; };
@@ -497,6 +692,92 @@ static void launch_shape(const Geom& g, dim3& grid, dim3& block, StencilParams& 
                 (unsigned)((g.n[2] + bx - 1) / bx));
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// tensor map over (k, j, i, item) of a dense (batch, n0, n1, n2) array with `elem`-byte elements
+static bool make_map(void* out, CUtensorMapDataType type, size_t elem, const void* base,
+                     const Geom& g, unsigned box_k, unsigned box_j) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.n[2], (cuuint64_t)g.n[1], (cuuint64_t)g.n[0],
+                                (cuuint64_t)g.batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.n[2] * elem, (cuuint64_t)g.st[0] * elem,
+                                   (cuuint64_t)g.voxels * elem};
+    const cuuint32_t box[4] = {box_k, box_j, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(reinterpret_cast<CUtensorMap*>(out), type, 4, const_cast<void*>(base), dims, strides,
+              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// A/B switch (probes and tests cover both generations of the kernel): lsml_stencil_use_tma()
+static bool g_stencil_tma = getenv("LSML_STENCIL_NO_TMA") == nullptr;
+int stencil_use_tma(int on) {
+    const int prev = g_stencil_tma ? 1 : 0;
+    if (on >= 0) g_stencil_tma = on != 0;
+    return prev;
+}
+
+// float64 3-D grids whose rows are 16-byte multiples: the TMA plane pipeline.  *done = false when
+// the grid is not eligible (the caller falls back to the register-marching kernels).
+static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
+                       double* out, const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
+    *done = false;
+    const bool off = !g_stencil_tma;
+    auto al16 = [](const void* q) { return ((size_t)q & 15) == 0; };
+    if (off || g.ndim != 3 || g.n[2] % 2 != 0 || g.n[2] < 64 || g.n[1] < 8 || !al16(A) ||
+        !al16(nu) || !al16(out) || (mask && !al16(mask)) || (mask && g.n[2] % 16 != 0) ||
+        g.batch > 65535)
+        return 0;
+    TmaMaps maps;
+    if (!make_map(maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, g, TM_AW, TM_TJ + 2) ||
+        !make_map(maps.nu, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, nu, g, TM_TK, TM_TJ) ||
+        (mask && !make_map(maps.m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, g, TM_TK, TM_TJ)))
+        return 0;
+    const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
+    const i64 chunks = (g.n[0] + TM_CHUNK - 1) / TM_CHUNK;
+    const dim3 grid((unsigned)(g.batch * chunks), (unsigned)((g.n[1] + TM_TJ - 1) / TM_TJ),
+                    (unsigned)((g.n[2] + TM_TK - 1) / TM_TK));
+    static bool configured = false;
+    if (!configured) {
+        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+        configured = true;
+    }
+    const int has_mask = mask != nullptr;
+    if (unit) gmag_os_tma_kernel<true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
+    else if (exact) gmag_os_tma_kernel<true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
+    else gmag_os_tma_kernel<false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
+    LSML_LAUNCH_CHECK("gmag_os_tma_kernel");
+    *done = true;
+    return 0;
+}
+static int gmag_os_tma(const Geom&, const float*, const u8*, const float*, float*,
+                       const StencilParams&, bool, cudaStream_t, bool* done) {
+    *done = false;            // float32: the vectorised march (4 voxels per thread)
+    return 0;
+}
+
 template <typename T>
 int gmag_os_dense(const Geom& g, const T* A, const u8* mask, const T* nu, T* out,
                   cudaStream_t s) {
@@ -505,6 +786,11 @@ int gmag_os_dense(const Geom& g, const T* A, const u8* mask, const T* nu, T* out
     launch_shape(g, grid, block, p);
     const bool exact = g.rdx[0] != 0.0 && g.rdx[1] != 0.0 && g.rdx[2] != 0.0;
     if (g.st[0] >= (i64)1 << 31) { set_error("grid plane too large for 32-bit strides"); return 1; }
+    {
+        bool done = false;
+        const int st = gmag_os_tma(g, A, mask, nu, out, p, exact, s, &done);
+        if (st || done) return st;
+    }
     if (marchv_eligible(g, A, nu, out, mask, VecOf<T>::N, sizeof(T))) {
         const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
         dim3 mg, mb;

@@ -78,6 +78,25 @@ def test_reference_test_suite_properties():
     assert np.abs(got - want).mean() <= 1e-8
 
 
+def test_tma_pipeline_on_batches(oracle):
+    """Items of a batch are the 4th tensor-map coordinate: halos never leak across items."""
+    import torch
+    from lsml_b200 import _lib
+    from lsml_b200.gradient import masked_gradient as mg
+    assert _lib.lib.lsml_stencil_use_tma(-1) == 1
+    rs = np.random.RandomState(17)
+    arr = rs.randn(3, 37, 26, 80)
+    nu = rs.randn(*arr.shape)
+    t = lambda a: torch.from_numpy(a).cuda()
+    for mask in (None, rs.rand(*arr.shape) > 0.4):
+        got = mg.gradient_magnitude_osher_sethian(t(arr), t(nu), mask=None if mask is None else t(mask),
+                                                  dx=np.array([1.0, 2.0, 0.5]), batched=True)
+        for b in range(arr.shape[0]):
+            want = oracle.gmag_os(arr[b], nu[b], None if mask is None else mask[b],
+                                  np.array([1.0, 2.0, 0.5]))
+            assert np.array_equal(got[b].cpu().numpy(), want), b
+
+
 def test_device_tensor_path_and_batch(oracle):
     import torch
     from lsml_b200.gradient import masked_gradient as mg
@@ -131,14 +150,26 @@ def test_band_compaction_matches_numpy_order(shape, batch, density):
     assert np.array_equal(offsets.cpu().numpy(), np.r_[0, np.cumsum(per_item)])
 
 
+@pytest.fixture(params=["tma", "march"])
+def generation(request):
+    """Both generations of the dense float64 3-D kernel: the TMA plane pipeline and the
+    register-marching kernels it falls back to (lsml_stencil_use_tma)."""
+    from lsml_b200 import _lib
+    prev = _lib.lib.lsml_stencil_use_tma(1 if request.param == "tma" else 0)
+    yield request.param
+    _lib.lib.lsml_stencil_use_tma(prev)
+
+
 @pytest.mark.parametrize("shape,dx", [((20, 17, 64), None), ((19, 24, 128), (1.0, 1.0, 1.0)),
                                       ((18, 9, 96), (0.5, 2.0, 4.0)), ((21, 16, 72), (0.7, 1.3, 1.1)),
-                                      ((35, 8, 64), None), ((2, 2, 64), None)])
-def test_vectorised_march_kernel_bit_exact_all_inputs(oracle, shape, dx):
-    """The 16-byte vectorised 3-D kernel (even last axis >= 64) evaluates the upwind sum in a
-    scaled form; it must still be bit-identical to the reference for ordinary values, with and
-    without masks, and for the values where the scaled form is not exact by itself (subnormal
-    squares, infinities, NaNs, exact zeros), which take the kernel's exact slow path."""
+                                      ((35, 8, 64), None), ((2, 2, 64), None),
+                                      ((70, 21, 130), None), ((66, 19, 128), (1.0, 0.5, 2.0))])
+def test_vectorised_march_kernel_bit_exact_all_inputs(oracle, shape, dx, generation):
+    """The 16-byte vectorised 3-D kernels (even last axis >= 64; TMA-staged or register-marching)
+    evaluate the upwind sum in a scaled form; they must still be bit-identical to the reference
+    for ordinary values, with and without masks, on partial tiles and across plane chunks, and for
+    the values where the scaled form is not exact by itself (subnormal squares, infinities, NaNs,
+    exact zeros), which take the kernel's exact slow path."""
     import torch
     from lsml_b200.gradient import masked_gradient as mg
     rs = np.random.RandomState(11)

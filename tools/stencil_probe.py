@@ -30,6 +30,13 @@ def run(name, fn, bytes_per_voxel):
 for dx in ((1.0, 1.0, 1.0), (0.7, 1.3, 1.1)):
     dxc = _lib.double_array(dx)
     tag = "dx=1" if dx[0] == 1.0 else "dx generic"
+    _lib.lib.lsml_stencil_use_tma(0)
+    run("gmag_os f64 %s (register march)" % tag, lambda: _lib.check(_lib.lib.lsml_gmag_os_f64(3, shape, _lib.c_i64(1), _lib.ptr(A), _lib.ptr(mask), _lib.ptr(nu), _lib.ptr(out), dxc, _lib.current_stream())), 25)
+    ref_out = out.clone()
+    _lib.lib.lsml_stencil_use_tma(1)
+    out.zero_()
+    run("gmag_os f64 %s (TMA, NULL mask)" % tag, lambda: _lib.check(_lib.lib.lsml_gmag_os_f64(3, shape, _lib.c_i64(1), _lib.ptr(A), _lib.c_p(0), _lib.ptr(nu), _lib.ptr(out), dxc, _lib.current_stream())), 24)
+    print("    TMA == register march: %s" % bool(torch.equal(out, ref_out)))
     run("gmag_os f64 %s" % tag, lambda: _lib.check(_lib.lib.lsml_gmag_os_f64(3, shape, _lib.c_i64(1), _lib.ptr(A), _lib.ptr(mask), _lib.ptr(nu), _lib.ptr(out), dxc, _lib.current_stream())), 25)
     run("gradient_centered f64 %s" % tag, lambda: _lib.check(_lib.lib.lsml_gradient_centered_f64(3, shape, _lib.c_i64(1), _lib.ptr(A), _lib.ptr(mask), _lib.ptr(grads), _lib.ptr(out), dxc, 0, _lib.current_stream())), 8 + 1 + 24 + 8)
 A32, nu32, out32 = A.float(), nu.float(), out.float()
