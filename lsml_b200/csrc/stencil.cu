@@ -481,9 +481,14 @@ gmag_os_marchv_kernel(const T* __restrict__ A, const u8* __restrict__ mask,
 // ---------------------------------------------------------------------------------------------
 constexpr int TM_TJ = 8, TM_TK = 64;            // tile: 8 rows (one consumer warp each) x 64 voxels
 constexpr int TM_AW = TM_TK + 4;                // A row in smem: k0-2 .. k0+TK+1
-constexpr int TM_STAGES = 4;                    // nu / mask ring
+#ifndef TM_STAGES_N
+#define TM_STAGES_N 4
+#endif
+#ifndef TM_MIN_CTAS
+#define TM_MIN_CTAS 3
+#endif
+constexpr int TM_STAGES = TM_STAGES_N;          // nu / mask ring
 constexpr int TM_A_RING = TM_STAGES + 2;        // A planes i-1, i and the STAGES planes in flight
-constexpr int TM_CHUNK = 32;                    // planes per CTA
 constexpr int TM_A_BYTES = (TM_TJ + 2) * TM_AW * 8;      // 5440 bytes land per A tile ...
 constexpr int TM_A_SLOT = (TM_A_BYTES + 127) / 128 * 128;  // ... in 128-byte aligned ring slots
 constexpr int TM_NU_BYTES = TM_TJ * TM_TK * 8;           // 4096
@@ -528,10 +533,47 @@ struct TmaMaps {           // CUtensorMap is 128 bytes, 64-byte aligned
     alignas(64) unsigned char m[128];
 };
 
+// the two voxels of one thread (vectorised kernel's arithmetic).  BORDER: apply the i / j border
+// rule; the k border rule (only the first / last voxel of a row can need it) is always applied.
+template <bool EXACT, bool UNIT, bool BORDER>
+__device__ __forceinline__ void tma_voxels(const double2& prv, const double2& cur, const double2& nxt,
+                                           const double2& jp, const double2& jm, double left,
+                                           double right, const double2& nuv, const StencilParams& p,
+                                           bool ilo, bool ihi, bool jlo, bool jhi, bool klo, bool khi,
+                                           double (&res)[2]) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const double cc = v ? cur.y : cur.x;
+        double f0 = (v ? nxt.y : nxt.x) - cc, b0 = cc - (v ? prv.y : prv.x);
+        double f1 = (v ? jp.y : jp.x) - cc, b1 = cc - (v ? jm.y : jm.x);
+        double f2 = (v ? right : cur.y) - cc, b2 = cc - (v ? cur.x : left);
+        if (BORDER) {
+            if (ilo) b0 = f0; else if (ihi) f0 = b0;
+            if (jlo) b1 = f1; else if (jhi) f1 = b1;
+        }
+        if (v == 0 && klo) b2 = f2;
+        if (v == 1 && khi) f2 = b2;
+        if (!UNIT) {
+            f0 = scale_dx<double, EXACT>(f0, p.dx0, p.r0); b0 = scale_dx<double, EXACT>(b0, p.dx0, p.r0);
+            f1 = scale_dx<double, EXACT>(f1, p.dx1, p.r1); b1 = scale_dx<double, EXACT>(b1, p.dx1, p.r1);
+            f2 = scale_dx<double, EXACT>(f2, p.dx2, p.r2); b2 = scale_dx<double, EXACT>(b2, p.dx2, p.r2);
+        }
+        const bool neg = (v ? nuv.y : nuv.x) < 0.0;
+        const unsigned sgn = neg ? 0x80000000u : 0u;
+        // s = -1 where nu < 0: min(s*b, 0)^2 + max(s*f, 0)^2 per axis (see os_axis)
+        double s4 = neg_part_sq4(flip_sign(b0, sgn)) + pos_part_sq4(flip_sign(f0, sgn));
+        s4 = (s4 + neg_part_sq4(flip_sign(b1, sgn))) + pos_part_sq4(flip_sign(f1, sgn));
+        s4 = (s4 + neg_part_sq4(flip_sign(b2, sgn))) + pos_part_sq4(flip_sign(f2, sgn));
+        double r = 0.5 * sqrt_nonneg(s4);
+        if (!scaled_sum_ok(s4)) r = gmag_os_exact<double>(b0, f0, b1, f1, b2, f2, neg);
+        res[v] = r;
+    }
+}
+
 template <bool EXACT, bool UNIT>
 __global__ void __launch_bounds__(TM_THREADS)
 gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* __restrict__ out,
-                   StencilParams p) {
+                   StencilParams p, int chunk /* planes per CTA */) {
     extern __shared__ __align__(128) unsigned char tm_smem[];
     // TMA destinations must be 128-byte aligned
     unsigned char* sA = tm_smem + ((128u - (smem_u32(tm_smem) & 127u)) & 127u);   // A_RING A tiles
@@ -541,10 +583,12 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
     // bars[0 .. STAGES): full, bars[STAGES .. 2 STAGES): empty, bars[2 STAGES]: prologue
     const unsigned bar0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned chunks = (unsigned)((p.n0 + TM_CHUNK - 1) / TM_CHUNK);
-    const int item = (int)(blockIdx.x / chunks), ci = (int)(blockIdx.x % chunks);
-    const int i0 = ci * TM_CHUNK, i1 = min(p.n0, i0 + TM_CHUNK), L = i1 - i0;
-    const int j0 = blockIdx.y * TM_TJ, k0 = blockIdx.z * TM_TK;
+    // launch order: j tiles fastest, then k tiles, then (item, chunk): CTAs that are resident
+    // together are neighbours in j and k, so their halo rows / columns hit L2
+    const unsigned chunks = (unsigned)((p.n0 + chunk - 1) / chunk);
+    const int item = (int)(blockIdx.z / chunks), ci = (int)(blockIdx.z % chunks);
+    const int i0 = ci * chunk, i1 = min(p.n0, i0 + chunk), L = i1 - i0;
+    const int j0 = blockIdx.x * TM_TJ, k0 = blockIdx.y * TM_TK;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TM_STAGES; ++s) {
             mbar_init(bar0 + 8 * s, 1);                          // full: the producer's expect_tx
@@ -584,7 +628,6 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
     const int j = j0 + ty, k = k0 + 2 * tx;
     const bool inside = j < p.n1 && k < p.n2;                 // (n2 is even: both voxels or none)
     const bool jlo = j == 0, jhi = j == p.n1 - 1, klo = k == 0, khi = k + 2 == p.n2;
-    const bool border_jk = jlo | jhi | klo | khi;
     // byte offset of this thread's centre pair inside an A tile / a nu tile / a mask tile
     const unsigned oA = ((ty + 1) * TM_AW + 2 * tx + 2) * 8;
     const unsigned oNu = (ty * TM_TK + 2 * tx) * 8;
@@ -613,32 +656,16 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
             const int i = i0 + t;
             const bool ilo = i == 0, ihi = i == p.n0 - 1;
             double res[2];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-                const double cc = v ? cur.y : cur.x;
-                double f0 = (v ? nxt.y : nxt.x) - cc, b0 = cc - (v ? prv.y : prv.x);
-                double f1 = (v ? jp.y : jp.x) - cc, b1 = cc - (v ? jm.y : jm.x);
-                double f2 = (v ? right : cur.y) - cc, b2 = cc - (v ? cur.x : left);
-                if (ilo) b0 = f0; else if (ihi) f0 = b0;                // uniform
-                if (border_jk) {                                        // rare threads only
-                    if (jlo) b1 = f1; else if (jhi) f1 = b1;
-                    if (v == 0 && klo) b2 = f2;
-                    if (v == 1 && khi) f2 = b2;
-                }
-                if (!UNIT) {
-                    f0 = scale_dx<double, EXACT>(f0, p.dx0, p.r0); b0 = scale_dx<double, EXACT>(b0, p.dx0, p.r0);
-                    f1 = scale_dx<double, EXACT>(f1, p.dx1, p.r1); b1 = scale_dx<double, EXACT>(b1, p.dx1, p.r1);
-                    f2 = scale_dx<double, EXACT>(f2, p.dx2, p.r2); b2 = scale_dx<double, EXACT>(b2, p.dx2, p.r2);
-                }
-                const bool neg = (v ? nuv.y : nuv.x) < 0.0;
-                const unsigned sgn = neg ? 0x80000000u : 0u;
-                double s4 = neg_part_sq4(flip_sign(b0, sgn)) + pos_part_sq4(flip_sign(f0, sgn));
-                s4 = (s4 + neg_part_sq4(flip_sign(b1, sgn))) + pos_part_sq4(flip_sign(f1, sgn));
-                s4 = (s4 + neg_part_sq4(flip_sign(b2, sgn))) + pos_part_sq4(flip_sign(f2, sgn));
-                double r = 0.5 * sqrt_nonneg(s4);
-                if (!scaled_sum_ok(s4)) r = gmag_os_exact<double>(b0, f0, b1, f1, b2, f2, neg);
-                res[v] = r;
-            }
+            // Border rows (j = 0 / n1-1: one warp of a border CTA) and border planes (i = 0 /
+            // n0-1: CTA-uniform) take the general path; everything else only keeps the two
+            // k-border selects (first / last thread of the first / last k tile).  The split keeps
+            // ~30 select instructions per iteration out of the common path.
+            if (ilo | ihi | jlo | jhi)
+                tma_voxels<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, nuv, p, ilo, ihi, jlo,
+                                              jhi, klo, khi, res);
+            else
+                tma_voxels<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, nuv, p, false, false,
+                                               false, false, klo, khi, res);
             if (m == 3u) *reinterpret_cast<double2*>(po) = make_double2(res[0], res[1]);
             else if (m == 1u) po[0] = res[0];
             else po[1] = res[1];
@@ -754,9 +781,25 @@ static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const dou
         (mask && !make_map(maps.m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, g, TM_TK, TM_TJ)))
         return 0;
     const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
-    const i64 chunks = (g.n[0] + TM_CHUNK - 1) / TM_CHUNK;
-    const dim3 grid((unsigned)(g.batch * chunks), (unsigned)((g.n[1] + TM_TJ - 1) / TM_TJ),
-                    (unsigned)((g.n[2] + TM_TK - 1) / TM_TK));
+    // Planes per CTA: every CTA pays two extra A planes (its prologue), and the grid should fill
+    // whole waves of the 3 CTAs/SM that fit (72 registers x 288 threads): pick the balanced chunk
+    // length with the smallest  waves x (planes + 2).
+    const i64 tiles = (i64)((g.n[1] + TM_TJ - 1) / TM_TJ) * ((g.n[2] + TM_TK - 1) / TM_TK) * g.batch;
+    const i64 slots = (i64)LSML_SMS * TM_MIN_CTAS;
+    int chunk = g.n[0];
+    i64 best = -1;
+    for (int c = 1; c <= g.n[0]; ++c) {
+        const int len = (g.n[0] + c - 1) / c;
+        if (len < 8 && c > 1) break;
+        const i64 ctas = tiles * ((g.n[0] + len - 1) / len);
+        const i64 cost = ((ctas + slots - 1) / slots) * (len + 2);
+        if (best < 0 || cost < best) { best = cost; chunk = len; }
+    }
+    if (const char* e = getenv("LSML_TMA_CHUNK")) { const int v = atoi(e); if (v >= 1) chunk = v < g.n[0] ? v : g.n[0]; }
+    const i64 chunks = (g.n[0] + chunk - 1) / chunk;
+    if (g.batch * chunks > 65535) return 0;
+    const dim3 grid((unsigned)((g.n[1] + TM_TJ - 1) / TM_TJ), (unsigned)((g.n[2] + TM_TK - 1) / TM_TK),
+                    (unsigned)(g.batch * chunks));
     static bool configured = false;
     if (!configured) {
         LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
@@ -765,9 +808,9 @@ static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const dou
         configured = true;
     }
     const int has_mask = mask != nullptr;
-    if (unit) gmag_os_tma_kernel<true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
-    else if (exact) gmag_os_tma_kernel<true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
-    else gmag_os_tma_kernel<false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p);
+    if (unit) gmag_os_tma_kernel<true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
+    else if (exact) gmag_os_tma_kernel<true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
+    else gmag_os_tma_kernel<false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
     LSML_LAUNCH_CHECK("gmag_os_tma_kernel");
     *done = true;
     return 0;
