@@ -570,10 +570,53 @@ __device__ __forceinline__ void tma_voxels(const double2& prv, const double2& cu
     }
 }
 
-template <bool EXACT, bool UNIT>
+// centered differences of one thread's two voxels (masked_gradient.c:24-71): 0.5 (plus - minus),
+// one-sided at the borders, / dx, magnitude, optional normalisation
+template <bool EXACT, bool UNIT, bool BORDER>
+__device__ __forceinline__ void tma_centered(const double2& prv, const double2& cur, const double2& nxt,
+                                             const double2& jp, const double2& jm, double left,
+                                             double right, const StencilParams& p, bool ilo, bool ihi,
+                                             bool jlo, bool jhi, bool klo, bool khi, int normalize,
+                                             double (&d0)[2], double (&d1)[2], double (&d2)[2],
+                                             double (&g)[2]) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const double cc = v ? cur.y : cur.x;
+        const double pn = v ? nxt.y : nxt.x, pp = v ? prv.y : prv.x;
+        const double qp = v ? jp.y : jp.x, qm = v ? jm.y : jm.x;
+        const double rp = v ? right : cur.y, rm = v ? cur.x : left;
+        double a0 = 0.5 * (pn - pp), a1 = 0.5 * (qp - qm), a2 = 0.5 * (rp - rm);
+        if (BORDER) {
+            if (ilo) a0 = pn - cc; else if (ihi) a0 = cc - pp;
+            if (jlo) a1 = qp - cc; else if (jhi) a1 = cc - qm;
+        }
+        if (v == 0 && klo) a2 = rp - cc;
+        if (v == 1 && khi) a2 = cc - rm;
+        if (!UNIT) {
+            a0 = scale_dx<double, EXACT>(a0, p.dx0, p.r0);
+            a1 = scale_dx<double, EXACT>(a1, p.dx1, p.r1);
+            a2 = scale_dx<double, EXACT>(a2, p.dx2, p.r2);
+        }
+        const double gg = dev_sqrt((a0 * a0 + a1 * a1) + a2 * a2);
+        g[v] = gg;
+        if (normalize == 1 && gg > 0.0) { a0 /= gg; a1 /= gg; a2 /= gg; }
+        d0[v] = a0; d1[v] = a1; d2[v] = a2;
+    }
+}
+
+struct TmaOut {
+    double* out;         // OP 0: |Du|; OP 1: gmag
+    double* grads;       // OP 1: three arrays `plane` elements apart
+    i64 plane;
+    int normalize;
+};
+
+// OP 0: Osher-Sethian upwind |Du| (reads nu); OP 1: centered gradient + magnitude (no nu)
+template <int OP, bool EXACT, bool UNIT>
 __global__ void __launch_bounds__(TM_THREADS)
-gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* __restrict__ out,
+gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
                    StencilParams p, int chunk /* planes per CTA */) {
+    double* __restrict__ out = o.out;
     extern __shared__ __align__(128) unsigned char tm_smem[];
     // TMA destinations must be 128-byte aligned
     unsigned char* sA = tm_smem + ((128u - (smem_u32(tm_smem) & 127u)) & 127u);   // A_RING A tiles
@@ -598,7 +641,7 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const unsigned stage_bytes = TM_A_BYTES + TM_NU_BYTES + (has_mask ? TM_M_BYTES : 0);
+    const unsigned stage_bytes = TM_A_BYTES + (OP == 0 ? TM_NU_BYTES : 0) + (has_mask ? TM_M_BYTES : 0);
     if (warp == TM_TJ) {
         // ---------------------------------------------------------------- producer warp
         if (lane == 0) {
@@ -616,7 +659,8 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
                 // read in iteration u-STAGES-1); nu / mask plane i0+u -> slot s
                 tma_load_4d(smem_u32(sA + ((u + 2) % TM_A_RING) * TM_A_SLOT), &maps.a, full,
                             k0 - 2, j0 - 1, i0 + u + 1, item);
-                tma_load_4d(smem_u32(sNu + s * TM_NU_BYTES), &maps.nu, full, k0, j0, i0 + u, item);
+                if (OP == 0)
+                    tma_load_4d(smem_u32(sNu + s * TM_NU_BYTES), &maps.nu, full, k0, j0, i0 + u, item);
                 if (has_mask)
                     tma_load_4d(smem_u32(sM + s * TM_M_BYTES), &maps.m, full, k0, j0, i0 + u, item);
             }
@@ -652,23 +696,43 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, double* _
             const double2 jm = *reinterpret_cast<const double2*>(tc + oA - TM_AW * 8);
             const double left = *reinterpret_cast<const double*>(tc + oA - 8);
             const double right = *reinterpret_cast<const double*>(tc + oA + 16);
-            const double2 nuv = *reinterpret_cast<const double2*>(sNu + s * TM_NU_BYTES + oNu);
             const int i = i0 + t;
             const bool ilo = i == 0, ihi = i == p.n0 - 1;
-            double res[2];
             // Border rows (j = 0 / n1-1: one warp of a border CTA) and border planes (i = 0 /
             // n0-1: CTA-uniform) take the general path; everything else only keeps the two
             // k-border selects (first / last thread of the first / last k tile).  The split keeps
             // ~30 select instructions per iteration out of the common path.
-            if (ilo | ihi | jlo | jhi)
-                tma_voxels<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, nuv, p, ilo, ihi, jlo,
-                                              jhi, klo, khi, res);
-            else
-                tma_voxels<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, nuv, p, false, false,
-                                               false, false, klo, khi, res);
-            if (m == 3u) *reinterpret_cast<double2*>(po) = make_double2(res[0], res[1]);
-            else if (m == 1u) po[0] = res[0];
-            else po[1] = res[1];
+            if (OP == 0) {
+                const double2 nuv = *reinterpret_cast<const double2*>(sNu + s * TM_NU_BYTES + oNu);
+                double res[2];
+                if (ilo | ihi | jlo | jhi)
+                    tma_voxels<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, nuv, p, ilo, ihi,
+                                                  jlo, jhi, klo, khi, res);
+                else
+                    tma_voxels<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, nuv, p, false,
+                                                   false, false, false, klo, khi, res);
+                if (m == 3u) *reinterpret_cast<double2*>(po) = make_double2(res[0], res[1]);
+                else if (m == 1u) po[0] = res[0];
+                else po[1] = res[1];
+            } else {
+                double d0[2], d1[2], d2[2], g[2];
+                if (ilo | ihi | jlo | jhi)
+                    tma_centered<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, p, ilo, ihi, jlo,
+                                                    jhi, klo, khi, o.normalize, d0, d1, d2, g);
+                else
+                    tma_centered<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, p, false, false,
+                                                     false, false, klo, khi, o.normalize, d0, d1, d2, g);
+                double* g0 = o.grads + (po - out);
+                if (m == 3u) {
+                    *reinterpret_cast<double2*>(po) = make_double2(g[0], g[1]);
+                    *reinterpret_cast<double2*>(g0) = make_double2(d0[0], d0[1]);
+                    *reinterpret_cast<double2*>(g0 + o.plane) = make_double2(d1[0], d1[1]);
+                    *reinterpret_cast<double2*>(g0 + 2 * o.plane) = make_double2(d2[0], d2[1]);
+                } else {
+                    const int v = m == 1u ? 0 : 1;
+                    po[v] = g[v]; g0[v] = d0[v]; g0[o.plane + v] = d1[v]; g0[2 * o.plane + v] = d2[v];
+                }
+            }
         }
         // this warp is done with stage s (its nu / mask tile, and the A plane i-1 behind it)
         __syncwarp();
@@ -766,18 +830,21 @@ int stencil_use_tma(int on) {
 
 // float64 3-D grids whose rows are 16-byte multiples: the TMA plane pipeline.  *done = false when
 // the grid is not eligible (the caller falls back to the register-marching kernels).
-static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
-                       double* out, const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
+// nu == nullptr selects the centered gradient (grads / plane / normalize are then used).
+static int stencil_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
+                       double* out, double* grads, i64 plane, int normalize,
+                       const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
     *done = false;
     const bool off = !g_stencil_tma;
     auto al16 = [](const void* q) { return ((size_t)q & 15) == 0; };
-    if (off || g.ndim != 3 || g.n[2] % 2 != 0 || g.n[2] < 64 || g.n[1] < 8 || !al16(A) ||
-        !al16(nu) || !al16(out) || (mask && !al16(mask)) || (mask && g.n[2] % 16 != 0) ||
-        g.batch > 65535)
+    const bool centered = nu == nullptr;
+    if (off || g.ndim != 3 || g.n[2] % 2 != 0 || g.n[2] < 64 || g.n[1] < 8 || g.n[0] < 2 ||
+        !al16(A) || !al16(nu) || !al16(out) || (mask && !al16(mask)) || (mask && g.n[2] % 16 != 0) ||
+        (centered && (!al16(grads) || plane % 2 != 0)))
         return 0;
     TmaMaps maps;
     if (!make_map(maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, g, TM_AW, TM_TJ + 2) ||
-        !make_map(maps.nu, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, nu, g, TM_TK, TM_TJ) ||
+        (!centered && !make_map(maps.nu, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, nu, g, TM_TK, TM_TJ)) ||
         (mask && !make_map(maps.m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, g, TM_TK, TM_TJ)))
         return 0;
     const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
@@ -802,22 +869,44 @@ static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const dou
                     (unsigned)(g.batch * chunks));
     static bool configured = false;
     if (!configured) {
-        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
-        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
-        LSML_CUDA(cudaFuncSetAttribute(gmag_os_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM));
+#define LSML_TMA_ATTR(K) LSML_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM))
+        LSML_TMA_ATTR((gmag_os_tma_kernel<0, true, true>)); LSML_TMA_ATTR((gmag_os_tma_kernel<0, true, false>));
+        LSML_TMA_ATTR((gmag_os_tma_kernel<0, false, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<1, true, true>));
+        LSML_TMA_ATTR((gmag_os_tma_kernel<1, true, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<1, false, false>));
+#undef LSML_TMA_ATTR
         configured = true;
     }
     const int has_mask = mask != nullptr;
-    if (unit) gmag_os_tma_kernel<true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
-    else if (exact) gmag_os_tma_kernel<true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
-    else gmag_os_tma_kernel<false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, out, p, chunk);
+    const TmaOut o{out, grads, plane, normalize};
+#define LSML_TMA_GO(OP)                                                                                      \
+    do {                                                                                                      \
+        if (unit) gmag_os_tma_kernel<OP, true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);        \
+        else if (exact) gmag_os_tma_kernel<OP, true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk); \
+        else gmag_os_tma_kernel<OP, false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);           \
+    } while (0)
+    if (centered) LSML_TMA_GO(1); else LSML_TMA_GO(0);
+#undef LSML_TMA_GO
     LSML_LAUNCH_CHECK("gmag_os_tma_kernel");
     *done = true;
     return 0;
 }
+static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
+                       double* out, const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
+    return stencil_tma(g, A, mask, nu, out, nullptr, 0, 0, p, exact, s, done);
+}
 static int gmag_os_tma(const Geom&, const float*, const u8*, const float*, float*,
                        const StencilParams&, bool, cudaStream_t, bool* done) {
     *done = false;            // float32: the vectorised march (4 voxels per thread)
+    return 0;
+}
+static int centered_tma(const Geom& g, const double* A, const u8* mask, double* grads, double* gmag,
+                        i64 plane, int normalize, const StencilParams& p, bool exact,
+                        cudaStream_t s, bool* done) {
+    return stencil_tma(g, A, mask, nullptr, gmag, grads, plane, normalize, p, exact, s, done);
+}
+static int centered_tma(const Geom&, const float*, const u8*, float*, float*, i64, int,
+                        const StencilParams&, bool, cudaStream_t, bool* done) {
+    *done = false;
     return 0;
 }
 
@@ -874,6 +963,11 @@ int gradient_centered_dense(const Geom& g, const T* A, const u8* mask, T* grads,
     const i64 plane = g.voxels * g.batch;
     const bool exact = g.rdx[0] != 0.0 && g.rdx[1] != 0.0 && g.rdx[2] != 0.0;
     if (g.st[0] >= (i64)1 << 31) { set_error("grid plane too large for 32-bit strides"); return 1; }
+    {
+        bool done = false;
+        const int st = centered_tma(g, A, mask, grads, gmag, plane, normalize, p, exact, s, &done);
+        if (st || done) return st;
+    }
     if (march_eligible(g)) {
         const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
         dim3 mg, mb;

@@ -182,6 +182,15 @@ def test_vectorised_march_kernel_bit_exact_all_inputs(oracle, shape, dx, generat
                                                   dx=dxa).cpu().numpy()
         want = oracle.gmag_os(arr, nu, mask, dxa, use_reference=oracle.reference_lib() is not None)
         assert np.array_equal(got, want), np.abs(got - want).max()
+        # the centered gradient runs through the same plane pipeline (masked_gradient.c:13-75)
+        for normalize in (False, True):
+            grads, gm = mg.gradient_centered(t(arr), mask=None if mask is None else t(mask), dx=dxa,
+                                             normalize=normalize)
+            wg, wm = oracle.gradient_centered(arr, mask, dxa, normalize,
+                                              use_reference=oracle.reference_lib() is not None)
+            assert np.array_equal(gm.cpu().numpy(), wm)
+            for a in range(3):
+                assert np.array_equal(grads[a].cpu().numpy(), wg[a]), (a, normalize)
     # special values
     sp = arr.copy()
     flat = sp.ravel()

@@ -29,7 +29,7 @@ for rep in range(2):
     eng.set_level_sets(u0)
     for it in range(iters):
         nb = eng.n_band
-        t_step = timed(lambda: eng.step(dreg, 0.35, rebuild=False))
+        t_step = timed(lambda: eng.step(dreg, 0.35, rebuild=False)); eng._n_band_host = None
         eng._band_is_rebuilt = True
         t_fmm = timed(lambda: eng._rebuild_band(from_band=True))
         ctr = eng.fmm_counters()

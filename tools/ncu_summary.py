@@ -1,5 +1,7 @@
-"""One-page summary of an .ncu-rep (raw page): python tools/ncu_summary.py rep.ncu-rep"""
-import csv, subprocess, sys
+"""One-page summary of an .ncu-rep (raw page): python tools/ncu_summary.py rep.ncu-rep
+With `--json KEY FILE`: also merges {KEY: {dram_bytes_per_launch, duration_us, source}} into FILE
+(profiles/r2_ncu_traffic.json, which bench.py reads for `roofline.traffic`)."""
+import csv, json, os, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
@@ -25,3 +27,19 @@ for r in rows[2:]:
             i = hdr.index(k)
             print("%-82s %s %s" % (k, r[i], units[i]))
     print()
+
+if "--json" in sys.argv:
+    q = sys.argv.index("--json")
+    key, path = sys.argv[q + 1], sys.argv[q + 2]
+    r = rows[2]
+    val = lambda k: float(r[hdr.index(k)].replace(",", ""))
+    unit = lambda k: units[hdr.index(k)]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = sum(val(k) * scale[unit(k)] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    dur = val("gpu__time_duration.sum") * tscale[unit("gpu__time_duration.sum")]
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[key] = {"dram_bytes_per_launch": dram, "duration_us": dur,
+              "kernel": r[hdr.index("Kernel Name")][:120],
+              "source": "%s, ncu --set full --clock-control none" % os.path.basename(sys.argv[1])}
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
