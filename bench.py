@@ -476,9 +476,28 @@ def section_c4(ctx, total=C4_TOTAL, chunk=C4_CHUNK, log=None):
     launches = _lib.launch_count() - l0
     eng.check_converged()
     tot_units, tot_launch, failed = ctx.sum_ints([units[0], launches, int(eng._fmm_status[0].item())])
+    # per-phase device times of one engine batch on rank 0 (CUDA-event brackets; evidence pass)
+    phases, upd = None, None
+    if hi > lo:
+        eng.timers = {}
+        nb_batch = int(evolve(0, min(per_engine, hi - lo)).item())
+        ph = eng.phase_times_ms()
+        eng.timers = None
+        phases = {k: v[1] for k, v in ph.items()}
+        upd_n, upd_ms = ph.get("update", (1, 0.0))
+        if upd_ms > 0:
+            peak, peak_src = measured_peak_gbs()
+            gbs = 64.0 * nb_batch / (upd_ms * 1e-3) / 1e9        # ~64 B per band voxel
+            upd = {"bound": "hbm", "kernel": "band_update_kernel + band_apply_kernel over one engine "
+                                             "batch (%d band voxels per iteration on average)"
+                                             % (nb_batch // C4_ITERS),
+                   "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                   "algorithmic_bytes_per_launch": 64.0 * nb_batch / C4_ITERS,
+                   "ms": upd_ms / max(1, upd_n), "traffic": None, "peak_source": peak_src}
     del eng, raw
     torch.cuda.empty_cache()
     return {"value": tot_units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 1,
+            "phases_ms_per_engine_batch": phases, "roofline_update": upd,
             "n_gpus": ctx.world, "scaling": "strong",
             "config": {"workload": "C4: %d synthetic 64^3 crops in total (BASELINE configs[3]), "
                                    "contiguous index ranges per rank, engine batches of %d crops, "
@@ -872,7 +891,27 @@ def main():
     st_ms = float(np.median(st_ms))
     stencil_bytes = 25.0 * n ** 3          # 8 (A) + 1 (mask) + 8 (nu) + 8 (out) per voxel
     stencil_gbs = stencil_bytes / (st_ms * 1e-3) / 1e9
-    del A, nu, full, out, flush
+    grads = torch.zeros((3, n, n, n), dtype=torch.float64, device=device)
+
+    def centered_call():
+        _lib.check(_lib.lib.lsml_gradient_centered_f64(3, shape_c, _lib.c_i64(1), _lib.ptr(A), _lib.ptr(full),
+                                                       _lib.ptr(grads), _lib.ptr(out), dx_c, 0,
+                                                       _lib.current_stream()), "gradient_centered")
+    for _ in range(3):
+        centered_call()
+    gc_ms = []
+    for _ in range(10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        centered_call()
+        b.record()
+        torch.cuda.synchronize()
+        gc_ms.append(a.elapsed_time(b))
+    gc_ms = float(np.median(gc_ms))
+    centered_bytes = 41.0 * n ** 3         # 8 (A) + 1 (mask) + 3 x 8 (gradient) + 8 (magnitude)
+    centered_gbs = centered_bytes / (gc_ms * 1e-3) / 1e9
+    del A, nu, full, out, flush, grads
 
     # ---- aggregate over ranks ------------------------------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=device)
@@ -909,7 +948,7 @@ def main():
 
     if rank == 0:
         march_traffic, march_src = ncu_traffic("fmm_march_kernel")
-        stencil_traffic, stencil_src = ncu_traffic("gmag_os_dense")
+        stencil_traffic, stencil_src = ncu_traffic("gmag_os_tma_kernel")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -946,13 +985,20 @@ def main():
                          "note": "latency-bound (dependency depth of the fast-marching order x "
                                  "replay latency), not HBM-bound: DESIGN.md 4.6"},
             "roofline_stencil": {"bound": "hbm",
-                                 "kernel": "dense gmag_os (%d^3 float64, full mask, L2 flushed "
-                                           "between launches)" % n,
+                                 "kernel": "dense gmag_os: gmag_os_tma_kernel (TMA plane pipeline; %d^3 "
+                                           "float64, full mask, L2 flushed between launches)" % n,
                                  "achieved": stencil_gbs, "peak": peak, "unit": "GB/s",
                                  "frac": stencil_gbs / peak, "traffic": stencil_traffic,
                                  "traffic_source": stencil_src,
                                  "algorithmic_bytes_per_launch": stencil_bytes,
                                  "peak_source": peak_src, "ms": st_ms},
+            "roofline_centered": {"bound": "hbm",
+                                  "kernel": "dense gradient_centered (%d^3 float64, full mask, L2 "
+                                            "flushed between launches): the same TMA plane pipeline" % n,
+                                  "achieved": centered_gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": centered_gbs / peak, "traffic": None,
+                                  "algorithmic_bytes_per_launch": centered_bytes,
+                                  "peak_source": peak_src, "ms": gc_ms},
             "roofline_update": {"bound": "hbm",
                                 "kernel": "band_update_kernel + band_apply_kernel (banded upwind "
                                           "|Du|, u += step*v*|Du|, exact statistics)",
@@ -961,7 +1007,8 @@ def main():
                                 "algorithmic_bytes_per_launch": update_bytes,
                                 "ms": upd_ms / max(1, upd_n),
                                 "note": "two launches over ~0.27 M band voxels: launch-latency "
-                                        "bound at this band size"},
+                                        "bound at this band size; see c4.roofline_update for the "
+                                        "same kernels on a 2048-crop batch"},
             "phases_ms_per_step": {k: v[1] for k, v in phases.items()},
         }
         line.update(sections)

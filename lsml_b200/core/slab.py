@@ -40,8 +40,11 @@ from .. import _lib
 from .engine import BandEngine, gaussian_weights
 from .regressors import export_regressor
 
+import os
+
 HALO_STATE = 2          # planes of T / state exchanged per cut (replay stencil reach)
-OVERLAP = 8             # default ghost planes evaluated redundantly beyond every cut
+# default ghost planes evaluated redundantly beyond every cut (LSML_SLAB_OVERLAP overrides: probes)
+OVERLAP = int(os.environ.get("LSML_SLAB_OVERLAP", "8"))
 
 
 def plane_ranges(n0, world):
