@@ -34,10 +34,15 @@
 // advancing through the forest at its own pace (no idling on the warp's deepest lane) 568 us;
 // the current tree staged in shared memory (cp.async, double-buffered) with 2 / 4 voxels per
 // thread 560 / 599 us (kept below: forest_staged_kernel, LSML_FOREST_VARIANT=staged2|staged4).
-// Five different node paths, one time: ncu (profiles/r2_ncu_forest.txt) shows 257 M warp
-// instructions, issue slots 41 % busy, 48 % of the warp slots occupied on average (8.9 k warps
-// on 9.5 k slots: one wave whose length is its slowest warp), 22 of 32 lanes active -- the
-// walk is bound by instruction issue x occupancy, not by where the nodes live.
+// Two threads per voxel (half of the forest each, leaf references handed over through shared
+// memory so that the sum keeps sklearn's order) 704 us.  Six different walks, one time: what
+// they share is the number of L1 data-pipe WAVEFRONTS -- a divergent fetch costs one wavefront
+// per distinct sector (global) or per bank conflict (shared), ~86 per warp and tree either way.
+// ncu (profiles/r2_ncu_forest.txt): l1tex__data_pipe_lsu_wavefronts 54 % of peak over the whole
+// launch with 48 % of the warp slots occupied (one wave, ending with its slowest warps), i.e.
+// saturated while the SMs are full; issue slots 41 %, 22 of 32 lanes active.  The next step
+// would be 4-byte nodes (thresholds replaced by their rank among the forest's thresholds of that
+// feature, features by their rank) walked from shared memory: ~half the wavefronts.
 #include <cstdlib>
 #include "lsml_internal.h"
 #include "band_features.cuh"

@@ -92,10 +92,12 @@ def test_feature_program_and_api_surface():
     assert [f.name for f in feats][:2] == ["Image sample (σ = 0.000)", "Image sample (σ = 2.000)"]
     prog = FeatureProgram(fm.specs(), 2)
     assert prog.nfeat == 16 and len(prog.planes) == 4 and prog.needs_boundary
-    with pytest.raises(NotImplementedError):
-        FeatureProgram([BoundarySize(3).spec()], 3)          # Lewiner MC area not implemented
-    with pytest.raises(NotImplementedError):
-        FeatureProgram([Moments(2, orders=(3,)).spec()], 2)
+    p3 = FeatureProgram([BoundarySize(3).spec()], 3)         # 3-D: marching-cubes area (mcubes.cu)
+    assert p3.needs_boundary and p3.nfeat == 1
+    hi = FeatureProgram([Moments(2, orders=(1, 3, 4)).spec()], 2)   # orders > 2: axis histograms
+    assert hi.nfeat == 6 and hi.hi_moments == [(1, 0, 3), (2, 0, 4), (4, 1, 3), (5, 1, 4)]
+    with pytest.raises(ValueError):
+        FeatureProgram([("moments", (0,), (0,))], 2)
     ray = FeatureProgram([COMRaySample(2, n_samples=3).spec()], 2)      # 2N columns, raw image
     assert ray.nfeat == 6 and ray.planes == [("sample", 0.0)]
     assert [b & 0xffff for b in ray.b] == list(range(6)) and {b >> 16 for b in ray.b} == {3}
