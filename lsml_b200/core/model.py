@@ -56,8 +56,16 @@ def _ball_u0(eng, centres, radii):
     return u0
 
 
-def overlap_scores(eng, segs_dev):
-    """Jaccard of {u>0} vs seg per item from exact device counts (score_functions.py:4-23)."""
+def overlap_scores(eng, segs_dev, scorer=jaccard):
+    """Score of {u>0} vs seg per item (fit_job_handler.py:258-291 calls ``model.scorer(u, seg)``
+    per example).  ``jaccard`` and ``dice`` (score_functions.py:4-30) come from exact device
+    counts of the intersection and the union -- no level set leaves the GPU; any other scorer
+    is called on a host copy of each example's ``u``, as the reference does."""
+    from ..score_functions import dice
+    if scorer is not jaccard and scorer is not dice:
+        u = eng.u.cpu().numpy()
+        seg = segs_dev.cpu().numpy().astype(bool).reshape(u.shape)
+        return numpy.array([scorer(u[b], seg[b]) for b in range(eng.batch)], dtype=float)
     counts = torch.zeros((eng.batch, 2), dtype=torch.int64, device=eng.device)
     with torch.cuda.device(eng.device):
         _lib.check(_lib.lib.lsml_overlap_counts(
@@ -65,7 +73,8 @@ def overlap_scores(eng, segs_dev):
             _lib.ptr(counts), _lib.current_stream()), "overlap_counts")
     c = counts.cpu().numpy().astype(numpy.float64)
     with numpy.errstate(invalid="ignore", divide="ignore"):
-        return numpy.where(c[:, 1] == 0, 1.0, c[:, 0] / c[:, 1])
+        j = numpy.where(c[:, 1] == 0, 1.0, c[:, 0] / c[:, 1])
+    return j if scorer is jaccard else 2.0 * j / (j + 1.0)
 
 
 def balance_mask(arr, random_state=None):
@@ -248,7 +257,7 @@ class LevelSetMachineLearning:
         self._step = float(step)
 
         def record_scores():
-            s = overlap_scores(eng, segs_dev)
+            s = overlap_scores(eng, segs_dev, self.scorer)
             for key, items in self._split.items():
                 self.scores.setdefault(key, []).append(s[items])
 

@@ -40,9 +40,9 @@ ball_init_kernel(double* __restrict__ u, BallParams p, const double* __restrict_
 
 __global__ void __launch_bounds__(256)
 overlap_kernel(const double* __restrict__ u, const u8* __restrict__ seg, i64 voxels,
-               u64* __restrict__ counts /* [item][2] = {intersection, union} */) {
+               u64* __restrict__ counts /* [item][2] = {intersection, union} */, i64 item0) {
     __shared__ u64 red[32];
-    const int item = blockIdx.y;
+    const i64 item = item0 + blockIdx.y;
     const i64 base = (i64)item * voxels;
     u64 inter = 0, uni = 0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < voxels;
@@ -80,7 +80,10 @@ int overlap_counts(i64 voxels, i64 batch, const double* u, const u8* seg, u64* c
     i64 bx = (voxels + 256 * 8 - 1) / (256 * 8);
     if (bx < 1) bx = 1;
     if (bx > 1024) bx = 1024;
-    overlap_kernel<<<dim3((unsigned)bx, (unsigned)batch), 256, 0, s>>>(u, seg, voxels, counts);
+    for (i64 item0 = 0; item0 < batch; item0 += 65535) {          // gridDim.y <= 65535
+        const i64 ny = batch - item0 < 65535 ? batch - item0 : 65535;
+        overlap_kernel<<<dim3((unsigned)bx, (unsigned)ny), 256, 0, s>>>(u, seg, voxels, counts, item0);
+    }
     LSML_LAUNCH_CHECK("overlap_kernel");
     return 0;
 }

@@ -102,7 +102,8 @@ def ball_u0(eng, centres, radii):
     return torch.from_numpy(out)
 
 
-def overlap_scores(eng, segs_dev):
-    """numpy stand-in for lsml_b200.core.model.overlap_scores (score_functions.py:4-23)."""
+def overlap_scores(eng, segs_dev, scorer=None):
+    """numpy stand-in for lsml_b200.core.model.overlap_scores (score_functions.py:4-30)."""
     seg = segs_dev.numpy().astype(bool)
-    return np.array([O.jaccard(eng.u[b].numpy(), seg[b]) for b in range(eng.batch)])
+    fn = O.jaccard if scorer is None or scorer.__name__ == "jaccard" else scorer
+    return np.array([fn(eng.u[b].numpy(), seg[b]) for b in range(eng.batch)])

@@ -84,3 +84,34 @@ def test_fit_3d_reproduces_the_references_fit_on_device():
     for i in range(us.shape[0]):
         assert np.array_equal(us[i] > 0, want[i] > 0), i
         assert np.allclose(us[i], want[i], rtol=1e-5, atol=1e-8), np.abs(us[i] - want[i]).max()
+
+
+def test_fit_uses_the_models_scorer():
+    """fit_job_handler.py:258-291 records ``model.scorer(u, seg)``: dice comes from the same exact
+    device counts as jaccard, any other callable is evaluated on host copies."""
+    import numpy as np
+    from sklearn.linear_model import LinearRegression
+    from lsml_b200 import LevelSetMachineLearning
+    from lsml_b200.feature import get_basic_image_features
+    from lsml_b200.initializer import BallInitializer
+    from lsml_b200.score_functions import dice, jaccard
+    rs = np.random.RandomState(0)
+    g = np.indices((33, 33)).astype(float) - 16
+    imgs = [((g ** 2).sum(0) < r * r).astype(float) + 0.1 * rs.randn(33, 33) for r in (8, 9, 10, 11, 7, 12)]
+    segs = [((g ** 2).sum(0) < r * r) for r in (8, 9, 10, 11, 7, 12)]
+
+    def custom(u, seg, threshold=0.0):
+        return float(((u > threshold) == seg).mean())
+
+    got = {}
+    for name, scorer in (("jaccard", jaccard), ("dice", dice), ("custom", custom)):
+        m = LevelSetMachineLearning(get_basic_image_features(ndim=2, sigmas=[0, 2]),
+                                    BallInitializer(radius=5), scorer=scorer)
+        m.fit(imgs=imgs, segs=segs, regression_model_class=LinearRegression, max_iters=3,
+              datasets_split=([0, 1, 2, 3], [4], [5]), step=0.5, validation_history_len=10,
+              random_state=np.random.RandomState(1))
+        got[name] = np.asarray(m.training_scores)
+    j = got["jaccard"]
+    assert np.allclose(got["dice"], 2 * j / (j + 1), rtol=0, atol=1e-15)
+    assert got["custom"].shape == j.shape and not np.allclose(got["custom"], j)
+    assert (got["custom"] > 0.5).all()
