@@ -458,17 +458,17 @@ gmag_os_marchv_kernel(const T* __restrict__ A, const u8* __restrict__ mask,
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA plane pipeline (the 256^3 / 1024^3 float64 case; north_star: "shared-memory or TMA tile
-// staging, halos").
+// TMA plane pipeline (the 256^3 / 1024^3 case, float64 and float32; north_star: "shared-memory or
+// TMA tile staging, halos").
 //
 // ncu on the vectorised march above: 311 instructions per two-voxel iteration, issue slots 49 %
 // busy at 24 warps/SM, DRAM 39 % -- more than half of the instructions are 64-bit address
 // arithmetic, pointer bumps and the seven global loads per iteration.  Here NO consumer thread
 // computes a global load address: a CTA owns a (TJ x TK) column tile of a chunk of planes and
 // marches along axis 0 while one producer warp streams, per plane,
-//     the A tile WITH its one-voxel halo   (TJ+2) x (TK+4) doubles   cp.async.bulk.tensor.4d
-//     the nu tile                           TJ x TK doubles
-//     the mask tile                         TJ x TK bytes
+//     the A tile WITH its halo   (TJ+2) rows x (512 + 32) bytes   cp.async.bulk.tensor.4d
+//     the nu tile                 TJ rows x 512 bytes
+//     the mask tile               TJ rows x TK bytes
 // into a ring of shared-memory stages through three tensor maps over (k, j, i, item); an
 // mbarrier per stage carries the byte count (full) and the consumers' release (empty), so the
 // eight consumer warps never meet at a block barrier.  Out-of-range halo cells are zero-filled
@@ -479,8 +479,11 @@ gmag_os_marchv_kernel(const T* __restrict__ A, const u8* __restrict__ mask,
 // aligned).  A[i-1] and A[i] of the column stay in registers.  The arithmetic is the vectorised
 // kernel's (bit-exact, same range test and fallback).
 // ---------------------------------------------------------------------------------------------
-constexpr int TM_TJ = 8, TM_TK = 64;            // tile: 8 rows (one consumer warp each) x 64 voxels
-constexpr int TM_AW = TM_TK + 4;                // A row in smem: k0-2 .. k0+TK+1
+// Tile geometry in BYTES is the same for both element types: a thread owns 16 bytes along k (two
+// float64 or four float32 voxels), a warp one row of 512 bytes, a CTA eight rows.
+constexpr int TM_TJ = 8;                        // rows per tile (one consumer warp each)
+constexpr int TM_ROW_BYTES = 512;               // 64 float64 / 128 float32 voxels
+constexpr int TM_AROW_BYTES = TM_ROW_BYTES + 32;  // A row in smem: 16 bytes of halo on either side
 #ifndef TM_STAGES_N
 #define TM_STAGES_N 4
 #endif
@@ -489,13 +492,13 @@ constexpr int TM_AW = TM_TK + 4;                // A row in smem: k0-2 .. k0+TK+
 #endif
 constexpr int TM_STAGES = TM_STAGES_N;          // nu / mask ring
 constexpr int TM_A_RING = TM_STAGES + 2;        // A planes i-1, i and the STAGES planes in flight
-constexpr int TM_A_BYTES = (TM_TJ + 2) * TM_AW * 8;      // 5440 bytes land per A tile ...
+constexpr int TM_A_BYTES = (TM_TJ + 2) * TM_AROW_BYTES;    // 5440 bytes land per A tile ...
 constexpr int TM_A_SLOT = (TM_A_BYTES + 127) / 128 * 128;  // ... in 128-byte aligned ring slots
-constexpr int TM_NU_BYTES = TM_TJ * TM_TK * 8;           // 4096
-constexpr int TM_M_BYTES = TM_TJ * TM_TK;                // 512
-constexpr int TM_CONSUMERS = TM_TJ * 32;                 // 256 threads
-constexpr int TM_THREADS = TM_CONSUMERS + 32;            // + the producer warp
-constexpr size_t TM_SMEM = (size_t)TM_A_RING * TM_A_SLOT + (size_t)TM_STAGES * (TM_NU_BYTES + TM_M_BYTES) +
+constexpr int TM_NU_BYTES = TM_TJ * TM_ROW_BYTES;          // 4096
+constexpr int TM_M_MAX = TM_TJ * (TM_ROW_BYTES / 4);       // mask tile: 512 (f64) / 1024 (f32) bytes
+constexpr int TM_CONSUMERS = TM_TJ * 32;                   // 256 threads
+constexpr int TM_THREADS = TM_CONSUMERS + 32;              // + the producer warp
+constexpr size_t TM_SMEM = (size_t)TM_A_RING * TM_A_SLOT + (size_t)TM_STAGES * (TM_NU_BYTES + TM_M_MAX) +
                            2 * (TM_STAGES + 1) * 8 + 128;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -533,96 +536,107 @@ struct TmaMaps {           // CUtensorMap is 128 bytes, 64-byte aligned
     alignas(64) unsigned char m[128];
 };
 
-// the two voxels of one thread (vectorised kernel's arithmetic).  BORDER: apply the i / j border
-// rule; the k border rule (only the first / last voxel of a row can need it) is always applied.
-template <bool EXACT, bool UNIT, bool BORDER>
-__device__ __forceinline__ void tma_voxels(const double2& prv, const double2& cur, const double2& nxt,
-                                           const double2& jp, const double2& jm, double left,
-                                           double right, const double2& nuv, const StencilParams& p,
-                                           bool ilo, bool ihi, bool jlo, bool jhi, bool klo, bool khi,
-                                           double (&res)[2]) {
+// one thread's N voxels: centre vector `cur` with its six neighbour sets
+template <typename T>
+struct TmaStencil {
+    static constexpr int N = VecOf<T>::N;
+    T prv[N], cur[N], nxt[N], jp[N], jm[N];
+    T left, right;
+};
+
+// Osher-Sethian |Du| of the N voxels (vectorised kernel's arithmetic).  BORDER: apply the i / j
+// border rule; the k border rule (only the first / last voxel of a row can need it) always is.
+template <typename T, bool EXACT, bool UNIT, bool BORDER>
+__device__ __forceinline__ void tma_upwind(const TmaStencil<T>& q, const T (&nuv)[VecOf<T>::N],
+                                           const StencilParams& p, bool ilo, bool ihi, bool jlo,
+                                           bool jhi, bool klo, bool khi, T (&res)[VecOf<T>::N]) {
+    constexpr int N = VecOf<T>::N;
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const double cc = v ? cur.y : cur.x;
-        double f0 = (v ? nxt.y : nxt.x) - cc, b0 = cc - (v ? prv.y : prv.x);
-        double f1 = (v ? jp.y : jp.x) - cc, b1 = cc - (v ? jm.y : jm.x);
-        double f2 = (v ? right : cur.y) - cc, b2 = cc - (v ? cur.x : left);
+    for (int v = 0; v < N; ++v) {
+        const T cc = q.cur[v];
+        T f0 = q.nxt[v] - cc, b0 = cc - q.prv[v];
+        T f1 = q.jp[v] - cc, b1 = cc - q.jm[v];
+        T f2 = (v + 1 < N ? q.cur[v + 1 < N ? v + 1 : v] : q.right) - cc;
+        T b2 = cc - (v > 0 ? q.cur[v > 0 ? v - 1 : 0] : q.left);
         if (BORDER) {
             if (ilo) b0 = f0; else if (ihi) f0 = b0;
             if (jlo) b1 = f1; else if (jhi) f1 = b1;
         }
         if (v == 0 && klo) b2 = f2;
-        if (v == 1 && khi) f2 = b2;
+        if (v == N - 1 && khi) f2 = b2;
         if (!UNIT) {
-            f0 = scale_dx<double, EXACT>(f0, p.dx0, p.r0); b0 = scale_dx<double, EXACT>(b0, p.dx0, p.r0);
-            f1 = scale_dx<double, EXACT>(f1, p.dx1, p.r1); b1 = scale_dx<double, EXACT>(b1, p.dx1, p.r1);
-            f2 = scale_dx<double, EXACT>(f2, p.dx2, p.r2); b2 = scale_dx<double, EXACT>(b2, p.dx2, p.r2);
+            f0 = scale_dx<T, EXACT>(f0, (T)p.dx0, (T)p.r0); b0 = scale_dx<T, EXACT>(b0, (T)p.dx0, (T)p.r0);
+            f1 = scale_dx<T, EXACT>(f1, (T)p.dx1, (T)p.r1); b1 = scale_dx<T, EXACT>(b1, (T)p.dx1, (T)p.r1);
+            f2 = scale_dx<T, EXACT>(f2, (T)p.dx2, (T)p.r2); b2 = scale_dx<T, EXACT>(b2, (T)p.dx2, (T)p.r2);
         }
-        const bool neg = (v ? nuv.y : nuv.x) < 0.0;
+        const bool neg = nuv[v] < T(0);
         const unsigned sgn = neg ? 0x80000000u : 0u;
         // s = -1 where nu < 0: min(s*b, 0)^2 + max(s*f, 0)^2 per axis (see os_axis)
-        double s4 = neg_part_sq4(flip_sign(b0, sgn)) + pos_part_sq4(flip_sign(f0, sgn));
+        T s4 = neg_part_sq4(flip_sign(b0, sgn)) + pos_part_sq4(flip_sign(f0, sgn));
         s4 = (s4 + neg_part_sq4(flip_sign(b1, sgn))) + pos_part_sq4(flip_sign(f1, sgn));
         s4 = (s4 + neg_part_sq4(flip_sign(b2, sgn))) + pos_part_sq4(flip_sign(f2, sgn));
-        double r = 0.5 * sqrt_nonneg(s4);
-        if (!scaled_sum_ok(s4)) r = gmag_os_exact<double>(b0, f0, b1, f1, b2, f2, neg);
+        T r = T(0.5) * sqrt_nonneg(s4);
+        if (!scaled_sum_ok(s4)) r = gmag_os_exact<T>(b0, f0, b1, f1, b2, f2, neg);
         res[v] = r;
     }
 }
 
-// centered differences of one thread's two voxels (masked_gradient.c:24-71): 0.5 (plus - minus),
-// one-sided at the borders, / dx, magnitude, optional normalisation
-template <bool EXACT, bool UNIT, bool BORDER>
-__device__ __forceinline__ void tma_centered(const double2& prv, const double2& cur, const double2& nxt,
-                                             const double2& jp, const double2& jm, double left,
-                                             double right, const StencilParams& p, bool ilo, bool ihi,
-                                             bool jlo, bool jhi, bool klo, bool khi, int normalize,
-                                             double (&d0)[2], double (&d1)[2], double (&d2)[2],
-                                             double (&g)[2]) {
+// centered differences of the N voxels (masked_gradient.c:24-71): 0.5 (plus - minus), one-sided
+// at the borders, / dx, magnitude, optional normalisation
+template <typename T, bool EXACT, bool UNIT, bool BORDER>
+__device__ __forceinline__ void tma_centered(const TmaStencil<T>& q, const StencilParams& p, bool ilo,
+                                             bool ihi, bool jlo, bool jhi, bool klo, bool khi,
+                                             int normalize, T (&d0)[VecOf<T>::N], T (&d1)[VecOf<T>::N],
+                                             T (&d2)[VecOf<T>::N], T (&g)[VecOf<T>::N]) {
+    constexpr int N = VecOf<T>::N;
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const double cc = v ? cur.y : cur.x;
-        const double pn = v ? nxt.y : nxt.x, pp = v ? prv.y : prv.x;
-        const double qp = v ? jp.y : jp.x, qm = v ? jm.y : jm.x;
-        const double rp = v ? right : cur.y, rm = v ? cur.x : left;
-        double a0 = 0.5 * (pn - pp), a1 = 0.5 * (qp - qm), a2 = 0.5 * (rp - rm);
+    for (int v = 0; v < N; ++v) {
+        const T cc = q.cur[v];
+        const T rp = v + 1 < N ? q.cur[v + 1 < N ? v + 1 : v] : q.right;
+        const T rm = v > 0 ? q.cur[v > 0 ? v - 1 : 0] : q.left;
+        T a0 = T(0.5) * (q.nxt[v] - q.prv[v]), a1 = T(0.5) * (q.jp[v] - q.jm[v]), a2 = T(0.5) * (rp - rm);
         if (BORDER) {
-            if (ilo) a0 = pn - cc; else if (ihi) a0 = cc - pp;
-            if (jlo) a1 = qp - cc; else if (jhi) a1 = cc - qm;
+            if (ilo) a0 = q.nxt[v] - cc; else if (ihi) a0 = cc - q.prv[v];
+            if (jlo) a1 = q.jp[v] - cc; else if (jhi) a1 = cc - q.jm[v];
         }
         if (v == 0 && klo) a2 = rp - cc;
-        if (v == 1 && khi) a2 = cc - rm;
+        if (v == N - 1 && khi) a2 = cc - rm;
         if (!UNIT) {
-            a0 = scale_dx<double, EXACT>(a0, p.dx0, p.r0);
-            a1 = scale_dx<double, EXACT>(a1, p.dx1, p.r1);
-            a2 = scale_dx<double, EXACT>(a2, p.dx2, p.r2);
+            a0 = scale_dx<T, EXACT>(a0, (T)p.dx0, (T)p.r0);
+            a1 = scale_dx<T, EXACT>(a1, (T)p.dx1, (T)p.r1);
+            a2 = scale_dx<T, EXACT>(a2, (T)p.dx2, (T)p.r2);
         }
-        const double gg = dev_sqrt((a0 * a0 + a1 * a1) + a2 * a2);
+        const T gg = dev_sqrt((a0 * a0 + a1 * a1) + a2 * a2);
         g[v] = gg;
-        if (normalize == 1 && gg > 0.0) { a0 /= gg; a1 /= gg; a2 /= gg; }
+        if (normalize == 1 && gg > T(0)) { a0 /= gg; a1 /= gg; a2 /= gg; }
         d0[v] = a0; d1[v] = a1; d2[v] = a2;
     }
 }
 
+template <typename T>
 struct TmaOut {
-    double* out;         // OP 0: |Du|; OP 1: gmag
-    double* grads;       // OP 1: three arrays `plane` elements apart
+    T* out;              // OP 0: |Du|; OP 1: gmag
+    T* grads;            // OP 1: three arrays `plane` elements apart
     i64 plane;
     int normalize;
 };
 
 // OP 0: Osher-Sethian upwind |Du| (reads nu); OP 1: centered gradient + magnitude (no nu)
-template <int OP, bool EXACT, bool UNIT>
+template <typename T, int OP, bool EXACT, bool UNIT>
 __global__ void __launch_bounds__(TM_THREADS)
-gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
+gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut<T> o,
                    StencilParams p, int chunk /* planes per CTA */) {
-    double* __restrict__ out = o.out;
+    typedef typename VecOf<T>::type V;
+    constexpr int N = VecOf<T>::N;                       // voxels per thread
+    constexpr int TK = TM_ROW_BYTES / (int)sizeof(T);    // voxels per tile row
+    constexpr int M_BYTES = TM_TJ * TK;                  // mask tile
+    T* __restrict__ out = o.out;
     extern __shared__ __align__(128) unsigned char tm_smem[];
     // TMA destinations must be 128-byte aligned
     unsigned char* sA = tm_smem + ((128u - (smem_u32(tm_smem) & 127u)) & 127u);   // A_RING A tiles
-    unsigned char* sNu = sA + TM_A_RING * TM_A_SLOT;               // STAGES nu tiles
+    unsigned char* sNu = sA + TM_A_RING * TM_A_SLOT;                     // STAGES nu tiles
     unsigned char* sM = sNu + TM_STAGES * TM_NU_BYTES;                   // STAGES mask tiles
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sM + TM_STAGES * TM_M_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sM + TM_STAGES * TM_M_MAX);
     // bars[0 .. STAGES): full, bars[STAGES .. 2 STAGES): empty, bars[2 STAGES]: prologue
     const unsigned bar0 = smem_u32(bars);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -631,7 +645,7 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
     const unsigned chunks = (unsigned)((p.n0 + chunk - 1) / chunk);
     const int item = (int)(blockIdx.z / chunks), ci = (int)(blockIdx.z % chunks);
     const int i0 = ci * chunk, i1 = min(p.n0, i0 + chunk), L = i1 - i0;
-    const int j0 = blockIdx.x * TM_TJ, k0 = blockIdx.y * TM_TK;
+    const int j0 = blockIdx.x * TM_TJ, k0 = blockIdx.y * TK;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TM_STAGES; ++s) {
             mbar_init(bar0 + 8 * s, 1);                          // full: the producer's expect_tx
@@ -641,15 +655,16 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const unsigned stage_bytes = TM_A_BYTES + (OP == 0 ? TM_NU_BYTES : 0) + (has_mask ? TM_M_BYTES : 0);
+    const unsigned stage_bytes = TM_A_BYTES + (OP == 0 ? TM_NU_BYTES : 0) + (has_mask ? M_BYTES : 0);
     if (warp == TM_TJ) {
         // ---------------------------------------------------------------- producer warp
         if (lane == 0) {
-            // prologue: A planes i0-1 and i0 (ring slots 0 and 1)
+            // prologue: A planes i0-1 and i0 (ring slots 0 and 1); the A box starts N voxels (16
+            // bytes) left of the tile and one row above it
             const unsigned pro = bar0 + 8 * 2 * TM_STAGES;
             mbar_expect_tx(pro, 2 * TM_A_BYTES);
-            tma_load_4d(smem_u32(sA), &maps.a, pro, k0 - 2, j0 - 1, i0 - 1, item);
-            tma_load_4d(smem_u32(sA + TM_A_SLOT), &maps.a, pro, k0 - 2, j0 - 1, i0, item);
+            tma_load_4d(smem_u32(sA), &maps.a, pro, k0 - N, j0 - 1, i0 - 1, item);
+            tma_load_4d(smem_u32(sA + TM_A_SLOT), &maps.a, pro, k0 - N, j0 - 1, i0, item);
             for (int u = 0; u < L; ++u) {
                 const int s = u % TM_STAGES;
                 if (u >= TM_STAGES) mbar_wait(bar0 + 8 * (TM_STAGES + s), ((u / TM_STAGES) - 1) & 1);
@@ -658,44 +673,49 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
                 // A plane i0+u+1 -> ring slot (u+2) % A_RING (the slot of plane i0+u-STAGES-1, last
                 // read in iteration u-STAGES-1); nu / mask plane i0+u -> slot s
                 tma_load_4d(smem_u32(sA + ((u + 2) % TM_A_RING) * TM_A_SLOT), &maps.a, full,
-                            k0 - 2, j0 - 1, i0 + u + 1, item);
+                            k0 - N, j0 - 1, i0 + u + 1, item);
                 if (OP == 0)
                     tma_load_4d(smem_u32(sNu + s * TM_NU_BYTES), &maps.nu, full, k0, j0, i0 + u, item);
                 if (has_mask)
-                    tma_load_4d(smem_u32(sM + s * TM_M_BYTES), &maps.m, full, k0, j0, i0 + u, item);
+                    tma_load_4d(smem_u32(sM + s * TM_M_MAX), &maps.m, full, k0, j0, i0 + u, item);
             }
         }
         return;
     }
     // -------------------------------------------------------------------- consumer warps
     const int ty = warp, tx = lane;
-    const int j = j0 + ty, k = k0 + 2 * tx;
-    const bool inside = j < p.n1 && k < p.n2;                 // (n2 is even: both voxels or none)
-    const bool jlo = j == 0, jhi = j == p.n1 - 1, klo = k == 0, khi = k + 2 == p.n2;
-    // byte offset of this thread's centre pair inside an A tile / a nu tile / a mask tile
-    const unsigned oA = ((ty + 1) * TM_AW + 2 * tx + 2) * 8;
-    const unsigned oNu = (ty * TM_TK + 2 * tx) * 8;
-    const unsigned oM = ty * TM_TK + 2 * tx;
-    double* po = out + (((i64)item * p.n0 + i0) * p.n1 + j) * (i64)p.n2 + k;
+    const int j = j0 + ty, k = k0 + N * tx;
+    const bool inside = j < p.n1 && k < p.n2;                 // (n2 % N == 0: all N voxels or none)
+    const bool jlo = j == 0, jhi = j == p.n1 - 1, klo = k == 0, khi = k + N == p.n2;
+    // byte offset of this thread's centre vector inside an A tile / a nu tile / a mask tile
+    const unsigned oA = (ty + 1) * TM_AROW_BYTES + 16 * tx + 16;
+    const unsigned oNu = ty * TM_ROW_BYTES + 16 * tx;
+    const unsigned oM = ty * TK + N * tx;
+    T* po = out + (((i64)item * p.n0 + i0) * p.n1 + j) * (i64)p.n2 + k;
     mbar_wait(bar0 + 8 * 2 * TM_STAGES, 0);
-    double2 prv = *reinterpret_cast<const double2*>(sA + oA);
-    double2 cur = *reinterpret_cast<const double2*>(sA + TM_A_SLOT + oA);
+    TmaStencil<T> q;
+    unpack(*reinterpret_cast<const V*>(sA + oA), q.prv);
+    unpack(*reinterpret_cast<const V*>(sA + TM_A_SLOT + oA), q.cur);
     for (int t = 0; t < L; ++t) {
         const int s = t % TM_STAGES;
         mbar_wait(bar0 + 8 * s, (t / TM_STAGES) & 1);
         const unsigned char* tc = sA + ((t + 1) % TM_A_RING) * TM_A_SLOT;      // plane i
         const unsigned char* tn = sA + ((t + 2) % TM_A_RING) * TM_A_SLOT;      // plane i+1
-        const double2 nxt = *reinterpret_cast<const double2*>(tn + oA);
-        unsigned m = 3u;
+        unpack(*reinterpret_cast<const V*>(tn + oA), q.nxt);
+        unsigned m = (1u << N) - 1u;
         if (has_mask) {
-            const unsigned raw = *reinterpret_cast<const unsigned short*>(sM + s * TM_M_BYTES + oM);
-            m = ((raw & 0xffu) ? 1u : 0u) | ((raw & 0xff00u) ? 2u : 0u);
+            unsigned raw;
+            if (N == 2) raw = *reinterpret_cast<const unsigned short*>(sM + s * TM_M_MAX + oM);
+            else raw = *reinterpret_cast<const unsigned*>(sM + s * TM_M_MAX + oM);
+            m = 0u;
+#pragma unroll
+            for (int v = 0; v < N; ++v) m |= ((raw >> (8 * v)) & 0xffu) ? (1u << v) : 0u;
         }
         if (m && inside) {
-            const double2 jp = *reinterpret_cast<const double2*>(tc + oA + TM_AW * 8);
-            const double2 jm = *reinterpret_cast<const double2*>(tc + oA - TM_AW * 8);
-            const double left = *reinterpret_cast<const double*>(tc + oA - 8);
-            const double right = *reinterpret_cast<const double*>(tc + oA + 16);
+            unpack(*reinterpret_cast<const V*>(tc + oA + TM_AROW_BYTES), q.jp);
+            unpack(*reinterpret_cast<const V*>(tc + oA - TM_AROW_BYTES), q.jm);
+            q.left = *reinterpret_cast<const T*>(tc + oA - sizeof(T));
+            q.right = *reinterpret_cast<const T*>(tc + oA + 16);
             const int i = i0 + t;
             const bool ilo = i == 0, ihi = i == p.n0 - 1;
             // Border rows (j = 0 / n1-1: one warp of a border CTA) and border planes (i = 0 /
@@ -703,41 +723,47 @@ gmag_os_tma_kernel(const __grid_constant__ TmaMaps maps, int has_mask, TmaOut o,
             // k-border selects (first / last thread of the first / last k tile).  The split keeps
             // ~30 select instructions per iteration out of the common path.
             if (OP == 0) {
-                const double2 nuv = *reinterpret_cast<const double2*>(sNu + s * TM_NU_BYTES + oNu);
-                double res[2];
+                T nuv[N], res[N];
+                unpack(*reinterpret_cast<const V*>(sNu + s * TM_NU_BYTES + oNu), nuv);
                 if (ilo | ihi | jlo | jhi)
-                    tma_voxels<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, nuv, p, ilo, ihi,
-                                                  jlo, jhi, klo, khi, res);
+                    tma_upwind<T, EXACT, UNIT, true>(q, nuv, p, ilo, ihi, jlo, jhi, klo, khi, res);
                 else
-                    tma_voxels<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, nuv, p, false,
-                                                   false, false, false, klo, khi, res);
-                if (m == 3u) *reinterpret_cast<double2*>(po) = make_double2(res[0], res[1]);
-                else if (m == 1u) po[0] = res[0];
-                else po[1] = res[1];
-            } else {
-                double d0[2], d1[2], d2[2], g[2];
-                if (ilo | ihi | jlo | jhi)
-                    tma_centered<EXACT, UNIT, true>(prv, cur, nxt, jp, jm, left, right, p, ilo, ihi, jlo,
-                                                    jhi, klo, khi, o.normalize, d0, d1, d2, g);
-                else
-                    tma_centered<EXACT, UNIT, false>(prv, cur, nxt, jp, jm, left, right, p, false, false,
-                                                     false, false, klo, khi, o.normalize, d0, d1, d2, g);
-                double* g0 = o.grads + (po - out);
-                if (m == 3u) {
-                    *reinterpret_cast<double2*>(po) = make_double2(g[0], g[1]);
-                    *reinterpret_cast<double2*>(g0) = make_double2(d0[0], d0[1]);
-                    *reinterpret_cast<double2*>(g0 + o.plane) = make_double2(d1[0], d1[1]);
-                    *reinterpret_cast<double2*>(g0 + 2 * o.plane) = make_double2(d2[0], d2[1]);
+                    tma_upwind<T, EXACT, UNIT, false>(q, nuv, p, false, false, false, false, klo, khi, res);
+                if (m == (1u << N) - 1u) {
+                    *reinterpret_cast<V*>(po) = pack(res);
                 } else {
-                    const int v = m == 1u ? 0 : 1;
-                    po[v] = g[v]; g0[v] = d0[v]; g0[o.plane + v] = d1[v]; g0[2 * o.plane + v] = d2[v];
+#pragma unroll
+                    for (int v = 0; v < N; ++v)
+                        if ((m >> v) & 1u) po[v] = res[v];
+                }
+            } else {
+                T d0[N], d1[N], d2[N], g[N];
+                if (ilo | ihi | jlo | jhi)
+                    tma_centered<T, EXACT, UNIT, true>(q, p, ilo, ihi, jlo, jhi, klo, khi, o.normalize,
+                                                       d0, d1, d2, g);
+                else
+                    tma_centered<T, EXACT, UNIT, false>(q, p, false, false, false, false, klo, khi,
+                                                        o.normalize, d0, d1, d2, g);
+                T* g0 = o.grads + (po - out);
+                if (m == (1u << N) - 1u) {
+                    *reinterpret_cast<V*>(po) = pack(g);
+                    *reinterpret_cast<V*>(g0) = pack(d0);
+                    *reinterpret_cast<V*>(g0 + o.plane) = pack(d1);
+                    *reinterpret_cast<V*>(g0 + 2 * o.plane) = pack(d2);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < N; ++v)
+                        if ((m >> v) & 1u) {
+                            po[v] = g[v]; g0[v] = d0[v]; g0[o.plane + v] = d1[v]; g0[2 * o.plane + v] = d2[v];
+                        }
                 }
             }
         }
         // this warp is done with stage s (its nu / mask tile, and the A plane i-1 behind it)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (TM_STAGES + s));
-        prv = cur; cur = nxt;
+#pragma unroll
+        for (int v = 0; v < N; ++v) { q.prv[v] = q.cur[v]; q.cur[v] = q.nxt[v]; }
         po += p.st0;
     }
 }
@@ -828,30 +854,35 @@ int stencil_use_tma(int on) {
     return prev;
 }
 
-// float64 3-D grids whose rows are 16-byte multiples: the TMA plane pipeline.  *done = false when
-// the grid is not eligible (the caller falls back to the register-marching kernels).
+// 3-D grids whose rows are 16-byte multiples: the TMA plane pipeline.  *done = false when the
+// grid is not eligible (the caller falls back to the register-marching kernels).
 // nu == nullptr selects the centered gradient (grads / plane / normalize are then used).
-static int stencil_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
-                       double* out, double* grads, i64 plane, int normalize,
-                       const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
+template <typename T>
+static int stencil_tma(const Geom& g, const T* A, const u8* mask, const T* nu, T* out, T* grads,
+                       i64 plane, int normalize, const StencilParams& p, bool exact,
+                       cudaStream_t s, bool* done) {
+    constexpr int N = VecOf<T>::N;
+    constexpr int TK = TM_ROW_BYTES / (int)sizeof(T);
+    const CUtensorMapDataType dtype = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+                                                     : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     *done = false;
     const bool off = !g_stencil_tma;
     auto al16 = [](const void* q) { return ((size_t)q & 15) == 0; };
     const bool centered = nu == nullptr;
-    if (off || g.ndim != 3 || g.n[2] % 2 != 0 || g.n[2] < 64 || g.n[1] < 8 || g.n[0] < 2 ||
+    if (off || g.ndim != 3 || g.n[2] % N != 0 || g.n[2] < TK || g.n[1] < 8 || g.n[0] < 2 ||
         !al16(A) || !al16(nu) || !al16(out) || (mask && !al16(mask)) || (mask && g.n[2] % 16 != 0) ||
-        (centered && (!al16(grads) || plane % 2 != 0)))
+        (centered && (!al16(grads) || plane % N != 0)))
         return 0;
     TmaMaps maps;
-    if (!make_map(maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, A, g, TM_AW, TM_TJ + 2) ||
-        (!centered && !make_map(maps.nu, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, nu, g, TM_TK, TM_TJ)) ||
-        (mask && !make_map(maps.m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, g, TM_TK, TM_TJ)))
+    if (!make_map(maps.a, dtype, sizeof(T), A, g, TK + 2 * N, TM_TJ + 2) ||
+        (!centered && !make_map(maps.nu, dtype, sizeof(T), nu, g, TK, TM_TJ)) ||
+        (mask && !make_map(maps.m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, mask, g, TK, TM_TJ)))
         return 0;
     const bool unit = g.dx[0] == 1.0 && g.dx[1] == 1.0 && g.dx[2] == 1.0;
     // Planes per CTA: every CTA pays two extra A planes (its prologue), and the grid should fill
     // whole waves of the 3 CTAs/SM that fit (72 registers x 288 threads): pick the balanced chunk
     // length with the smallest  waves x (planes + 2).
-    const i64 tiles = (i64)((g.n[1] + TM_TJ - 1) / TM_TJ) * ((g.n[2] + TM_TK - 1) / TM_TK) * g.batch;
+    const i64 tiles = (i64)((g.n[1] + TM_TJ - 1) / TM_TJ) * ((g.n[2] + TK - 1) / TK) * g.batch;
     const i64 slots = (i64)LSML_SMS * TM_MIN_CTAS;
     int chunk = g.n[0];
     i64 best = -1;
@@ -865,24 +896,24 @@ static int stencil_tma(const Geom& g, const double* A, const u8* mask, const dou
     if (const char* e = getenv("LSML_TMA_CHUNK")) { const int v = atoi(e); if (v >= 1) chunk = v < g.n[0] ? v : g.n[0]; }
     const i64 chunks = (g.n[0] + chunk - 1) / chunk;
     if (g.batch * chunks > 65535) return 0;
-    const dim3 grid((unsigned)((g.n[1] + TM_TJ - 1) / TM_TJ), (unsigned)((g.n[2] + TM_TK - 1) / TM_TK),
+    const dim3 grid((unsigned)((g.n[1] + TM_TJ - 1) / TM_TJ), (unsigned)((g.n[2] + TK - 1) / TK),
                     (unsigned)(g.batch * chunks));
-    static bool configured = false;
+    static bool configured = false;      // (one flag per element type: function-local static of a template)
     if (!configured) {
 #define LSML_TMA_ATTR(K) LSML_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM))
-        LSML_TMA_ATTR((gmag_os_tma_kernel<0, true, true>)); LSML_TMA_ATTR((gmag_os_tma_kernel<0, true, false>));
-        LSML_TMA_ATTR((gmag_os_tma_kernel<0, false, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<1, true, true>));
-        LSML_TMA_ATTR((gmag_os_tma_kernel<1, true, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<1, false, false>));
+        LSML_TMA_ATTR((gmag_os_tma_kernel<T, 0, true, true>)); LSML_TMA_ATTR((gmag_os_tma_kernel<T, 0, true, false>));
+        LSML_TMA_ATTR((gmag_os_tma_kernel<T, 0, false, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<T, 1, true, true>));
+        LSML_TMA_ATTR((gmag_os_tma_kernel<T, 1, true, false>)); LSML_TMA_ATTR((gmag_os_tma_kernel<T, 1, false, false>));
 #undef LSML_TMA_ATTR
         configured = true;
     }
     const int has_mask = mask != nullptr;
-    const TmaOut o{out, grads, plane, normalize};
-#define LSML_TMA_GO(OP)                                                                                      \
-    do {                                                                                                      \
-        if (unit) gmag_os_tma_kernel<OP, true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);        \
-        else if (exact) gmag_os_tma_kernel<OP, true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk); \
-        else gmag_os_tma_kernel<OP, false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);           \
+    const TmaOut<T> o{out, grads, plane, normalize};
+#define LSML_TMA_GO(OP)                                                                                         \
+    do {                                                                                                         \
+        if (unit) gmag_os_tma_kernel<T, OP, true, true><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);        \
+        else if (exact) gmag_os_tma_kernel<T, OP, true, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk); \
+        else gmag_os_tma_kernel<T, OP, false, false><<<grid, TM_THREADS, TM_SMEM, s>>>(maps, has_mask, o, p, chunk);           \
     } while (0)
     if (centered) LSML_TMA_GO(1); else LSML_TMA_GO(0);
 #undef LSML_TMA_GO
@@ -890,24 +921,16 @@ static int stencil_tma(const Geom& g, const double* A, const u8* mask, const dou
     *done = true;
     return 0;
 }
-static int gmag_os_tma(const Geom& g, const double* A, const u8* mask, const double* nu,
-                       double* out, const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
-    return stencil_tma(g, A, mask, nu, out, nullptr, 0, 0, p, exact, s, done);
+template <typename T>
+static int gmag_os_tma(const Geom& g, const T* A, const u8* mask, const T* nu, T* out,
+                       const StencilParams& p, bool exact, cudaStream_t s, bool* done) {
+    return stencil_tma<T>(g, A, mask, nu, out, nullptr, 0, 0, p, exact, s, done);
 }
-static int gmag_os_tma(const Geom&, const float*, const u8*, const float*, float*,
-                       const StencilParams&, bool, cudaStream_t, bool* done) {
-    *done = false;            // float32: the vectorised march (4 voxels per thread)
-    return 0;
-}
-static int centered_tma(const Geom& g, const double* A, const u8* mask, double* grads, double* gmag,
-                        i64 plane, int normalize, const StencilParams& p, bool exact,
-                        cudaStream_t s, bool* done) {
-    return stencil_tma(g, A, mask, nullptr, gmag, grads, plane, normalize, p, exact, s, done);
-}
-static int centered_tma(const Geom&, const float*, const u8*, float*, float*, i64, int,
-                        const StencilParams&, bool, cudaStream_t, bool* done) {
-    *done = false;
-    return 0;
+template <typename T>
+static int centered_tma(const Geom& g, const T* A, const u8* mask, T* grads, T* gmag, i64 plane,
+                        int normalize, const StencilParams& p, bool exact, cudaStream_t s,
+                        bool* done) {
+    return stencil_tma<T>(g, A, mask, nullptr, gmag, grads, plane, normalize, p, exact, s, done);
 }
 
 template <typename T>

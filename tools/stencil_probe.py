@@ -41,6 +41,12 @@ for dx in ((1.0, 1.0, 1.0), (0.7, 1.3, 1.1)):
     run("gradient_centered f64 %s" % tag, lambda: _lib.check(_lib.lib.lsml_gradient_centered_f64(3, shape, _lib.c_i64(1), _lib.ptr(A), _lib.ptr(mask), _lib.ptr(grads), _lib.ptr(out), dxc, 0, _lib.current_stream())), 8 + 1 + 24 + 8)
 A32, nu32, out32 = A.float(), nu.float(), out.float()
 dxc = _lib.double_array((1.0, 1.0, 1.0))
+_lib.lib.lsml_stencil_use_tma(0)
+run("gmag_os f32 dx=1 (register march)", lambda: _lib.check(_lib.lib.lsml_gmag_os_f32(3, shape, _lib.c_i64(1), _lib.ptr(A32), _lib.ptr(mask), _lib.ptr(nu32), _lib.ptr(out32), dxc, _lib.current_stream())), 13)
+ref32 = out32.clone()
+_lib.lib.lsml_stencil_use_tma(1)
+out32.zero_()
 run("gmag_os f32 dx=1", lambda: _lib.check(_lib.lib.lsml_gmag_os_f32(3, shape, _lib.c_i64(1), _lib.ptr(A32), _lib.ptr(mask), _lib.ptr(nu32), _lib.ptr(out32), dxc, _lib.current_stream())), 13)
+print("    f32 TMA == register march: %s" % bool(torch.equal(out32, ref32)))
 b2 = torch.empty_like(A)
 run("torch copy (reference)", lambda: b2.copy_(A), 16)
