@@ -35,7 +35,36 @@ struct BandGeom {
     int ndim, n0, n1, n2;
     i64 voxels;
     double dx0, dx1, dx2, r0, r1, r2;
+    double inv_voxels;     // 1 / voxels (item of a flat index without a 64-bit division)
+    int small;             // voxels < 2^32: the in-item index fits 32 bits
+    int single;            // batch == 1
 };
+
+// flat index -> (item, i, j, k).  64-bit integer divisions cost ~100 instructions each on this
+// path (four per voxel before); the item comes from one multiplication by 1/voxels with a +-1
+// fix-up (exact: l < 2^53), the coordinates from 32-bit divisions when the item fits 32 bits.
+__device__ __forceinline__ i64 decode_voxel(i64 l, const BandGeom& g, int& i, int& j, int& k) {
+    i64 item = 0, loc = l;
+    if (!g.single) {
+        item = __double2ll_rz((double)l * g.inv_voxels);
+        loc = l - item * g.voxels;
+        if (loc < 0) { loc += g.voxels; --item; }
+        else if (loc >= g.voxels) { loc -= g.voxels; ++item; }
+    }
+    if (g.small) {
+        const unsigned lo = (unsigned)loc;
+        const unsigned r = lo / (unsigned)g.n2;
+        k = (int)(lo - r * (unsigned)g.n2);
+        const unsigned ii = r / (unsigned)g.n1;
+        j = (int)(r - ii * (unsigned)g.n1);
+        i = (int)ii;
+    } else {
+        k = (int)(loc % g.n2);
+        const i64 r = loc / g.n2;
+        j = (int)(r % g.n1); i = (int)(r / g.n1);
+    }
+    return item;
+}
 
 __global__ void __launch_bounds__(256)
 band_update_kernel(const double* __restrict__ u, const double* __restrict__ vel,
@@ -45,10 +74,8 @@ band_update_kernel(const double* __restrict__ u, const double* __restrict__ vel,
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < nb;
          b += (i64)gridDim.x * blockDim.x) {
         const i64 l = __ldg(band_idx + b);
-        const i64 loc = l % g.voxels;
-        const int k = (int)(loc % g.n2);
-        const i64 r = loc / g.n2;
-        const int j = (int)(r % g.n1), i = (int)(r / g.n1);
+        int i, j, k;
+        decode_voxel(l, g, i, j, k);
         const double c = __ldg(u + l), v = __ldg(vel + b);
         const bool neg = v < 0.0;
         double acc = 0.0, f, bk;
@@ -120,9 +147,9 @@ band_apply_kernel(double* __restrict__ u, const double* __restrict__ new_u,
             const double nv = __ldg(new_u + b), ov = u[l];
             const int pos = (nv > 0.0) - (ov > 0.0), zer = (nv == 0.0) - (ov == 0.0);
             if (pos) {
-                const u64 k = (u64)(loc % g.n2);
-                const i64 r = loc / g.n2;
-                const u64 j = (u64)(r % g.n1), i = (u64)(r / g.n1);
+                int ci, cj, ck;
+                decode_voxel(l, g, ci, cj, ck);
+                const u64 i = (u64)ci, j = (u64)cj, k = (u64)ck;
                 const u64 sgn = pos > 0 ? (u64)1 : ~(u64)0;        // +1 / -1 (mod 2^64)
                 d[0] += sgn;
                 d[1] += sgn * i; d[2] += sgn * j; d[3] += sgn * k;
@@ -142,6 +169,9 @@ int band_update(const Geom& g, double* u, const double* vel, const i64* band_idx
     bg.ndim = g.ndim; bg.n0 = g.n[0]; bg.n1 = g.n[1]; bg.n2 = g.n[2]; bg.voxels = g.voxels;
     bg.dx0 = g.dx[0]; bg.dx1 = g.dx[1]; bg.dx2 = g.dx[2];
     bg.r0 = g.rdx[0]; bg.r1 = g.rdx[1]; bg.r2 = g.rdx[2];
+    bg.inv_voxels = 1.0 / (double)g.voxels;
+    bg.small = g.voxels < ((i64)1 << 32) ? 1 : 0;
+    bg.single = g.batch == 1 ? 1 : 0;
     band_update_kernel<<<LSML_SMS * 8, 256, 0, s>>>(u, vel, band_idx, n_band, bg, step, new_u, gmag_out);
     LSML_LAUNCH_CHECK("band_update_kernel");
     if (apply) {

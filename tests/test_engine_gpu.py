@@ -261,3 +261,34 @@ def test_incremental_statistics_and_sparse_rebuild_match_dense(shape, dx):
         ref.set_level_sets(u_now)
         assert np.array_equal(ref.mask.cpu().numpy(), mask_inc), it
         assert np.array_equal(ref.band_idx[:ref.n_band].cpu().numpy(), idx_inc), it
+
+
+def test_vanishing_level_set_makes_later_steps_noops(oracle):
+    """`if mask.any()` (model.py:381) without the host: when an update pushes the whole level set
+    below zero the rebuilt band is empty (distance_transform.py:42-47) and every later step is a
+    no-op -- the kernels read the band size from the device and find nothing to do."""
+    from sklearn.linear_model import LinearRegression
+    from lsml_b200.core.engine import BandEngine
+    shape = (24, 26)
+    g = np.indices(shape).astype(float)
+    u0 = 3.0 - np.sqrt((g[0] - 12) ** 2 + (g[1] - 13) ** 2)          # a small disc
+    img = np.random.RandomState(0).randn(*shape)
+    specs = [("image_sample", 0.0), ("size",)]
+    reg = LinearRegression().fit(np.random.RandomState(1).randn(8, 2), np.full(8, -30.0))   # v = -30
+    eng = BandEngine(shape, 1, dx=np.ones(2), band=3.0, specs=specs)
+    eng.load_images(img[None], normalize=False)
+    eng.set_level_sets(u0[None])
+    assert eng.n_band > 0
+    eng.step(reg, 1.0)
+    u1 = eng.u[0].cpu().numpy()
+    assert (u1 <= 0).all() or (u1 > 0).sum() == 0
+    assert eng.n_band == 0 and int(eng.mask.sum()) == 0
+    dist, mask = oracle.distance_transform(u1, 3.0, np.ones(2))
+    assert not mask.any()
+    for _ in range(3):                      # no-ops: u unchanged, band stays empty, units unchanged
+        units = eng.band_voxel_iterations
+        eng.step(reg, 1.0)
+        assert eng.n_band == 0
+        assert eng.band_voxel_iterations == units
+        assert np.array_equal(eng.u[0].cpu().numpy(), u1)
+    eng.check_converged()
