@@ -655,8 +655,12 @@ def section_c2(ctx, total=1024, features="basic", log=None):
     launches = _lib.launch_count() - l0
     eng.check_converged()
     tot_units, tot_launch = ctx.sum_ints([sum(units), launches])
+    eng.timers = {}
+    one_pass()
+    phases = {k: v[1] for k, v in eng.phase_times_ms().items()}
+    eng.timers = None
     return {"value": tot_units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / reps, "steps": reps,
-            "n_gpus": ctx.world, "scaling": "strong",
+            "n_gpus": ctx.world, "scaling": "strong", "phases_ms_per_step": phases,
             "config": {"workload": "C2: %d synthetic 101x101 images in total (BASELINE configs[1]), "
                                    "%d on rank 0 in one engine, RF-100 velocity, F=%d (%s), band=3, "
                                    "%d iterations per step; no data-path collective"

@@ -91,6 +91,13 @@ int lsml_compact_mask(long long total, long long voxels_per_item, const uint8_t 
 int lsml_gauss1d_f64(int ndim, const int *shape, long long batch, const double *in, double *out,
                      const double *weights, int radius, int antisym, int axis, int mode,
                      void *stream);
+/* scipy.ndimage.gaussian_filter(in, (sigma0, sigma1)) on a batch of 2-D items small enough to
+ * live in shared memory twice (both passes in one kernel, bit-identical to two lsml_gauss1d_f64
+ * calls).  w0 / w1: DEVICE weights with the centre at w[r]; r < 0 skips that axis.  *done = 0
+ * when the items are too large: chain lsml_gauss1d_f64 instead.  (examples/gestalt2d/
+ * prev_iter_feature.py:21-22 calls gaussian_filter(u, sigma) every iteration.) */
+int lsml_gauss2d_f64(const int *shape, long long batch, const double *in, double *out,
+                     const double *w0, int r0, const double *w1, int r1, int *done, void *stream);
 /* |numpy.gradient(img, *dx)| (ImageEdgeSample with sigma == 0, image.py:48-49) */
 int lsml_np_gradient_mag_f64(int ndim, const int *shape, long long batch, const double *in,
                              double *out, const double *dx, void *stream);

@@ -338,6 +338,25 @@ class BandEngine:
         if not axes:
             dst.copy_(src)
             return
+        if self.ndim == 2 and src.data_ptr() != dst.data_ptr():
+            # both passes in one kernel when an item fits in shared memory twice
+            wr = []
+            for i in range(2):
+                if i in axes:
+                    key = (float(sigmas[i]), 0)
+                    if key not in self._weights:
+                        w, radius = gaussian_weights(sigmas[i], 0)
+                        self._weights[key] = (torch.from_numpy(w).to(self.device), radius)
+                    wr.append(self._weights[key])
+                else:
+                    wr.append((None, -1))
+            done = ctypes.c_int(0)
+            _lib.check(_lib.lib.lsml_gauss2d_f64(
+                self._shape_c, _lib.c_i64(self.batch), _lib.ptr(src), _lib.ptr(dst),
+                _lib.ptr(wr[0][0]), ctypes.c_int(wr[0][1]), _lib.ptr(wr[1][0]), ctypes.c_int(wr[1][1]),
+                ctypes.byref(done), self._stream()), "gauss2d")
+            if done.value:
+                return
         if len(axes) > 1 and self._tmp_plane is None:
             self._tmp_plane = torch.empty_like(self.u)
         tmp = self._tmp_plane

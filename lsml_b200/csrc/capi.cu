@@ -215,6 +215,16 @@ int lsml_gauss1d_f64(int ndim, const int* shape, long long batch, const double* 
     if (axis < 0 || axis >= ndim) { set_error("gauss1d: axis %d out of range", axis); return 1; }
     return gauss1d(g, in, out, weights, radius, antisym, 3 - ndim + axis, mode, (cudaStream_t)stream);
 }
+int lsml_gauss2d_f64(const int* shape, long long batch, const double* in, double* out,
+                     const double* w0, int r0, const double* w1, int r1, int* done, void* stream) {
+    const int ndim = 2;
+    const double* dx = nullptr;
+    GEOM(g);
+    bool d = false;
+    const int st = gauss2d_small(g, in, out, w0, r0, w1, r1, &d, (cudaStream_t)stream);
+    if (done) *done = d ? 1 : 0;
+    return st;
+}
 int lsml_np_gradient_mag_f64(int ndim, const int* shape, long long batch, const double* in,
                              double* out, const double* dx, void* stream) {
     GEOM(g);

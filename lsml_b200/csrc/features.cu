@@ -63,6 +63,123 @@ gauss1d_kernel(const double* __restrict__ in, double* __restrict__ out,
     else out[l] = sqrt(tmp * tmp);
 }
 
+// Both passes of scipy.ndimage.gaussian_filter on a batch of SMALL 2-D items in one kernel: one
+// CTA per item, the item lives in shared memory (the axis-0 pass row by row), so a plane
+// costs one global read and one global write per pixel instead of two of each, and every tap is
+// a conflict-free shared-memory load.  Same expressions in the same order as gauss1d_kernel
+// (axis 0 first, then axis 1; symmetric pairing), hence bit-identical.  Used for the level-set
+// dependent planes of examples/gestalt2d (PrevIterFeature: gaussian_filter(u, sigma) EVERY
+// iteration), where eight gauss1d launches were half of the C2 step.
+constexpr int G2_THREADS = 512;
+constexpr int G2_WARPS = G2_THREADS / 32;
+
+__device__ __forceinline__ double gauss_line(const double* __restrict__ line, int stride, int c,
+                                             int n, const double* __restrict__ w, int r) {
+    double tmp = line[c * stride] * w[r];
+    if (c - r >= 0 && c + r < n) {
+        for (int jj = -r; jj < 0; ++jj)
+            tmp = tmp + (line[(c + jj) * stride] + line[(c - jj) * stride]) * w[r + jj];
+    } else if (r <= n) {
+        // one reflection at most (d c b a | a b c d | d c b a): no integer modulo on this path,
+        // which every warp of the axis-1 pass takes (its lanes span interior and edge columns)
+        for (int jj = -r; jj < 0; ++jj) {
+            int ia = c + jj, ib = c - jj;
+            ia = ia < 0 ? -ia - 1 : ia;
+            ib = ib >= n ? 2 * n - 1 - ib : ib;
+            tmp = tmp + (line[ia * stride] + line[ib * stride]) * w[r + jj];
+        }
+    } else {
+        for (int jj = -r; jj < 0; ++jj)
+            tmp = tmp + (line[reflect_index(c + jj, n) * stride] +
+                         line[reflect_index(c - jj, n) * stride]) * w[r + jj];
+    }
+    return tmp;
+}
+
+// The item sits in shared memory once; every warp takes whole output rows: it first forms the
+// row of the axis-0 pass (column taps: consecutive lanes read consecutive words) in a private
+// row buffer, then runs the axis-1 pass along that buffer and stores the row -- no block
+// barrier after the load, two CTAs per SM.
+__global__ void __launch_bounds__(G2_THREADS)
+gauss2d_smem_kernel(const double* __restrict__ in, double* __restrict__ out,
+                    const double* __restrict__ w0, int r0, const double* __restrict__ w1, int r1,
+                    int n1, int n2) {
+    extern __shared__ double g2[];
+    const int voxels = n1 * n2;
+    double* a = g2;                                   // the item
+    double* rows = g2 + voxels;                       // G2_WARPS row buffers of n2 doubles
+    double* sw0 = rows + G2_WARPS * n2;               // weights, centre at [r]
+    double* sw1 = sw0 + (r0 < 0 ? 0 : 2 * r0 + 1);
+    const double* src = in + (i64)blockIdx.x * voxels;
+    double* dst = out + (i64)blockIdx.x * voxels;
+    for (int t = threadIdx.x; t < voxels; t += G2_THREADS) a[t] = __ldg(src + t);
+    for (int t = threadIdx.x; t < 2 * r0 + 1; t += G2_THREADS) sw0[t] = __ldg(w0 + t);
+    for (int t = threadIdx.x; t < 2 * r1 + 1; t += G2_THREADS) sw1[t] = __ldg(w1 + t);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* row = rows + warp * n2;
+    // Four outputs per lane and step (columns lane, lane+32, lane+64, lane+96 of the warp's
+    // row): four independent accumulation chains hide the float64 add latency of each.
+    for (int i = warp; i < n1; i += G2_WARPS) {
+        for (int j0 = lane; j0 < n2; j0 += 128) {
+            int jq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jq[q] = min(j0 + 32 * q, n2 - 1);
+            double t[4];
+            if (r0 < 0) {                 // scipy skips sigma <= 1e-15
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = a[i * n2 + jq[q]];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = a[i * n2 + jq[q]] * sw0[r0];
+                const bool interior = i - r0 >= 0 && i + r0 < n1;
+                for (int jj = -r0; jj < 0; ++jj) {
+                    int ia = i + jj, ib = i - jj;
+                    if (!interior) {
+                        if (r0 <= n1) { ia = ia < 0 ? -ia - 1 : ia; ib = ib >= n1 ? 2 * n1 - 1 - ib : ib; }
+                        else { ia = reflect_index(ia, n1); ib = reflect_index(ib, n1); }
+                    }
+                    const double wv = sw0[r0 + jj];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        t[q] = t[q] + (a[ia * n2 + jq[q]] + a[ib * n2 + jq[q]]) * wv;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j0 + 32 * q < n2) row[j0 + 32 * q] = t[q];
+        }
+        __syncwarp();
+        for (int j0 = lane; j0 < n2; j0 += 128) {
+            int jq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) jq[q] = min(j0 + 32 * q, n2 - 1);
+            double t[4];
+            if (r1 < 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = row[jq[q]];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = row[jq[q]] * sw1[r1];
+                for (int jj = -r1; jj < 0; ++jj) {
+                    const double wv = sw1[r1 + jj];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int ia = jq[q] + jj, ib = jq[q] - jj;
+                        if (r1 <= n2) { ia = ia < 0 ? -ia - 1 : ia; ib = ib >= n2 ? 2 * n2 - 1 - ib : ib; }
+                        else { ia = reflect_index(ia, n2); ib = reflect_index(ib, n2); }
+                        t[q] = t[q] + (row[ia] + row[ib]) * wv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j0 + 32 * q < n2) dst[i * n2 + j0 + 32 * q] = t[q];
+        }
+        __syncwarp();
+    }
+}
+
 // numpy.gradient along one axis (edge_order=1): interior (f[+1]-f[-1])/(2 dx), ends (f1-f0)/dx
 __device__ __forceinline__ double np_grad_axis(const double* __restrict__ A, i64 l, i64 st, int c,
                                                int n, double dx) {
@@ -429,6 +546,26 @@ int gauss1d(const Geom& g, const double* in, double* out, const double* w, int r
     gauss1d_kernel<<<grid, block, 0, s>>>(in, out, w, radius, antisym, g.n[0], g.n[1], g.n[2],
                                           axis_padded, rows, mode);
     LSML_LAUNCH_CHECK("gauss1d_kernel");
+    return 0;
+}
+
+// gaussian_filter(in, (sigma0, sigma1)) for 2-D items that fit in shared memory twice; radius < 0
+// skips an axis.  *done = false when the items are too large (the caller chains gauss1d).
+int gauss2d_small(const Geom& g, const double* in, double* out, const double* w0, int r0,
+                  const double* w1, int r1, bool* done, cudaStream_t s) {
+    *done = false;
+    if (g.ndim != 2) return 0;
+    const int q0 = r0 < 0 ? 0 : 2 * r0 + 1, q1 = r1 < 0 ? 0 : 2 * r1 + 1;
+    const size_t smem = ((size_t)g.voxels + (size_t)G2_WARPS * g.n[2] + q0 + q1 + 2) * sizeof(double);
+    if (smem > 220 * 1024 || g.batch > 0x7fffffff) return 0;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        LSML_CUDA(cudaFuncSetAttribute(gauss2d_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    gauss2d_smem_kernel<<<(unsigned)g.batch, G2_THREADS, smem, s>>>(in, out, w0, r0, w1, r1, g.n[1], g.n[2]);
+    LSML_LAUNCH_CHECK("gauss2d_smem_kernel");
+    *done = true;
     return 0;
 }
 

@@ -28,6 +28,8 @@ namespace lsml {
 struct FeatProgram;
 int gauss1d(const Geom& g, const double* in, double* out, const double* w, int radius,
             int antisym, int axis_padded, int mode, cudaStream_t s);
+int gauss2d_small(const Geom& g, const double* in, double* out, const double* w0, int r0,
+                  const double* w1, int r1, bool* done, cudaStream_t s);
 int np_gradient_mag(const Geom& g, const double* in, double* out, cudaStream_t s);
 i64 normalize_workspace_bytes(i64 voxels, i64 batch);
 int normalize_images(i64 voxels, i64 batch, const double* img, double* out, void* workspace,

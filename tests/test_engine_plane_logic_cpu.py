@@ -47,6 +47,20 @@ class FakeLib:
         self.calls.append(("gauss1d", axis, mode, radius, antisym.value))
         return 0
 
+    def lsml_gauss2d_f64(self, shape, batch, src, dst, w0, r0, w1, r1, done, stream):
+        """Both passes of a small 2-D item in one call (axis 0 first, then axis 1); r < 0 skips."""
+        batch, r0, r1 = batch.value, r0.value, r1.value
+        full = (batch, shape[0], shape[1])
+        t = _view(src, full).copy()
+        if r0 >= 0:
+            t = correlate1d(t, _view(w0, (2 * r0 + 1,)).copy(), axis=1, mode="reflect")
+        if r1 >= 0:
+            t = correlate1d(t, _view(w1, (2 * r1 + 1,)).copy(), axis=2, mode="reflect")
+        _view(dst, full)[...] = t
+        done._obj.value = 1
+        self.calls.append(("gauss2d", r0, r1))
+        return 0
+
     def lsml_np_gradient_mag_f64(self, ndim, shape, batch, src, dst, dx, stream):
         ndim, batch = ndim.value, batch.value
         full = (batch,) + tuple(shape[i] for i in range(ndim))
