@@ -21,6 +21,10 @@
  *                          flat index) and non-causal quadratic roots (the farthest neighbour
  *                          is dropped and the quadratic re-solved, as the published method
  *                          prescribes; see fmm_solve).
+ *   orc_marching_cubes_area
+ *                          surface area of {u = 0} in 3-D (skimage marching_cubes_lewiner +
+ *                          mesh_surface_area, lsml/feature/provided/shape.py:88-89); see the
+ *                          comment at the function: PARITY UNPINNED beyond test_shape.py:59-107.
  *   orc_marching_squares_length
  *                          skimage.measure.find_contours(u, 0) total poly-line length with
  *                          lsml's closing chord and dx[::-1] scaling, lsml/feature/provided/shape.py:70-85.

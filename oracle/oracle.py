@@ -11,12 +11,16 @@ so that timing it is an honest stand-in for the reference's CPU path on a box wh
 ``/root/reference`` is absent.  Where the reference's own C file could be compiled
 (``oracle/_ref/masked_gradient_ref.so``) it is used for the gradient kernels.
 
-Pinned against the reference itself by ``tests/test_oracle_vs_reference.py`` (runs only where
-``/root/reference`` exists) and by the committed fixtures under ``tests/golden/`` produced by
-``oracle/gen_golden.py`` from the imported reference.
+Pinned against the reference itself by ``tests/test_oracle_golden.py`` (the committed fixtures
+under ``tests/golden/``, produced by ``oracle/gen_golden.py`` from the imported reference, and the
+reference's own C file compiled into ``oracle/_ref``), ``tests/test_host_mirror_vs_reference.py``
+and the ``reference`` leg of ``tests/test_reference_suite.py`` (both run only where
+``/root/reference`` exists).
 
 PARITY UNPINNED pieces (third-party code absent from ``/root/reference``): the fast-marching
-distance (scikit-fmm) and the contour length (scikit-image); see ``lsml_oracle.c`` header.
+distance (scikit-fmm; ``skfmm_literal.c`` is an upstream-literal restatement used as a measuring
+stick), the contour length and the marching-cubes area (scikit-image); see
+the ``lsml_oracle.c`` header.
 """
 import ctypes
 import itertools
