@@ -217,3 +217,24 @@ def test_vectorised_march_kernel_bit_exact_all_inputs(oracle, shape, dx, generat
         got = mg.gradient_magnitude_osher_sethian(t(a32), t(n32), dx=dxa).cpu().numpy()
         want = oracle.gmag_os(a32.astype(np.float64), n32.astype(np.float64), None, dxa)
         assert np.allclose(got, want, rtol=2e-6, atol=1e-6)
+
+
+def test_host_pointer_dropin_at_volume_size(oracle):
+    """The six reference symbols on HOST buffers at a size where the
+    staging copies matter: 160 x 144 x 192 float64 (35 MB per array), banded and full masks."""
+    from lsml_b200.gradient import masked_gradient as mg
+    rs = np.random.RandomState(21)
+    shape = (160, 144, 192)
+    arr = rs.randn(*shape)
+    nu = rs.randn(*shape)
+    dx = np.array([1.0, 0.5, 2.0])
+    for mask in (None, np.abs(arr) < 0.1):
+        got = mg.gradient_magnitude_osher_sethian(arr, nu, mask=mask, dx=dx)
+        want = oracle.gmag_os(arr, nu, mask, dx, use_reference=oracle.reference_lib() is not None)
+        assert np.array_equal(got, want)
+    grads, gmag = mg.gradient_centered(arr, mask=np.abs(arr) < 0.5, dx=dx, normalize=True)
+    wg, wm = oracle.gradient_centered(arr, np.abs(arr) < 0.5, dx, True,
+                                      use_reference=oracle.reference_lib() is not None)
+    assert np.array_equal(gmag, wm)
+    for a in range(3):
+        assert np.array_equal(grads[a], wg[a])
