@@ -1025,11 +1025,26 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             // entry k of the work set goes to warp k % nwarps, lane k / nwarps: a small set is
             // spread one entry per warp (a lone lane runs its own path, not the union of 32
             // divergent ones), a large one fills the warps evenly
-            for (i64 k = (i64)lane * nwarps + gwarp; k < work; k += nthreads) {
-                const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
-                                                : park[pbase + k - (end - begin)];
-                process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
-                ++nreplay;
+#ifndef FMM_DENSE_FACTOR
+#define FMM_DENSE_FACTOR 4
+#endif
+            if (work >= (i64)FMM_DENSE_FACTOR * nwarps) {
+                // a large set: consecutive entries (pushed together by neighbouring threads, i.e.
+                // voxels that are neighbours in space) go to the lanes of ONE warp -- similar
+                // stencils, similar replay paths, overlapping cache lines
+                for (i64 k = tid; k < work; k += nthreads) {
+                    const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
+                                                    : park[pbase + k - (end - begin)];
+                    process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
+                    ++nreplay;
+                }
+            } else {
+                for (i64 k = (i64)lane * nwarps + gwarp; k < work; k += nthreads) {
+                    const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
+                                                    : park[pbase + k - (end - begin)];
+                    process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
+                    ++nreplay;
+                }
             }
         } else {
             // ---- fallback: scan the candidate list; a warp collects its queued entries in

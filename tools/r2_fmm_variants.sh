@@ -1,9 +1,9 @@
 #!/bin/bash
-# A/B of the march kernel's occupancy target (rebuilds fmm.o on the box)
+# A/B of march-kernel build variants (rebuilds fmm.o on the box): tools/r2_fmm_variants.sh "-DX=.." ...
 cd lsml_b200/csrc
-for v in "-DFMM_MIN_BLOCKS=4" "-DFMM_MIN_BLOCKS=3" "-DFMM_MIN_BLOCKS=5" "-DFMM_MIN_BLOCKS=6" "-DFMM_MIN_BLOCKS=2"; do
+for v in "$@"; do
     rm -f build/fmm.o
-    make EXTRA="$v -Xptxas -v" 2>&1 | grep -A2 "fmm_march_kernelILi3" | grep -E "registers|spill" | head -2
+    make EXTRA="$v" 2>&1 | grep -E "error" | head -3
     echo "== $v"
-    (cd ../..; timeout 200 python tools/fmm_probe.py 256 12 2>&1 | grep -E "^it  (5|8|11)")
+    (cd ../..; timeout 200 python tools/fmm_probe.py 256 12 2>&1 | grep -E "^it  (5|8|11)" | cut -c1-140; timeout 200 python bench.py --workload c4 --items 2048 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c4-2048', d['ms_per_step'], d['phases_ms_per_engine_batch']['rebuild'])")
 done
