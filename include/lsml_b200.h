@@ -219,6 +219,31 @@ int lsml_mlp_predict_band(const lsml_band_source *src, const long long *n_band, 
                           const double *const *W, const double *const *b, int act, double *out,
                           void *stream);
 
+/* A forest in the RANK-QUANTISED layout (lsml_b200/core/regressors.py: pack_ranked; regress.cu:
+ * forest_ranked_kernel): per feature f the sorted distinct float32 thresholds S_f of the forest
+ * (thr_tab = S_0 | S_1 | ..., thr_off = int[nfeat + 1]); trees in preorder, an internal node one
+ * 32-bit word  bit 0 / 1: left / right child is a leaf | feature << 2 | j << (2 + fbits) |
+ * (offset of the right child in words) << (2 + fbits + rbits)  with threshold S_f[j], the left
+ * child in the next word, a leaf as its float64 value in two words; tree_start = int[n_trees + 1]
+ * word offsets (multiples of 4; words 16-byte aligned); max_tree_words = the largest tree.  Same
+ * decisions, same leaves, same float64 sum in tree order as lsml_forest_predict -- i.e. as
+ * scikit-learn's predict (model.py:388) -- walked from shared memory.  All pointers DEVICE. */
+typedef struct lsml_ranked_forest {
+    const unsigned *words;
+    const int *tree_start;
+    const uint8_t *root_is_leaf;
+    const float *thr_tab;
+    const int *thr_off;
+    int n_trees, nfeat, fbits, rbits, max_tree_words;
+    double divisor;
+} lsml_ranked_forest;
+int lsml_forest_ranked_predict(const double *X, const long long *n_band, int nfeat,
+                               const double *mean, const double *scale,
+                               const lsml_ranked_forest *forest, double *out, void *stream);
+int lsml_forest_ranked_predict_band(const lsml_band_source *src, const long long *n_band,
+                                    const double *mean, const double *scale,
+                                    const lsml_ranked_forest *forest, double *out, void *stream);
+
 /* ---- banded update u[mask] += step*v*|Du|_upwind (model.py:390-394) ------------------------- */
 /* new_u[b] receives the updated value of band voxel b; with apply != 0 it is also scattered
  * into u.  gmag_out (may be NULL) receives the upwind gradient magnitude per band voxel. */

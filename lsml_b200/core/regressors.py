@@ -9,6 +9,7 @@ Training stays on the host; only ``predict`` runs on the GPU, with scikit-learn'
 host-callback fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -190,10 +191,112 @@ def pack_supernodes(nodes, bases, root_is_leaf):
     return out, leaves, root_ref, root_is_leaf.copy()
 
 
+RANKED_MAX_TREE_WORDS = 8192      # a tree must fit the kernel's shared-memory tree buffer
+RANKED_TREE_ALIGN = 4             # trees start on 16-byte boundaries (vector copies)
+
+
+def pack_ranked(nodes, bases, root_is_leaf, n_features):
+    """The single-node packing of :func:`pack_trees` -> the RANK-QUANTISED layout walked from
+    shared memory (regress.cu: forest_ranked_kernel), or ``None`` when the forest does not fit it.
+
+    A tree only ever asks ``x[f] <= thr``; with ``S_f`` the sorted distinct (float32) thresholds
+    the forest uses on feature ``f`` and ``rank_f(x) = #{s in S_f : s < x}``, that is
+    ``rank_f(x) <= j`` for the node whose threshold is ``S_f[j]`` -- exactly, for every float32
+    ``x`` (NaN ranks above everything: ``!(x <= thr)`` sends it right, as the other kernels do).
+    A voxel's features are therefore reduced ONCE to 16-bit ranks, and an internal node shrinks
+    to one 32-bit word::
+
+        bit 0 / 1: the left / right child is a leaf | feature << 2 | j << (2 + fbits) |
+        (offset of the right child in words) << (2 + fbits + rbits)
+
+    Trees are laid out in preorder: the left child is the next word, a leaf is its float64
+    value in two words.  Returns a dict: ``words`` uint32, ``tree_start`` int32[T+1] (word
+    offsets, multiples of 4), ``thr_tab`` float32 (the S_f back to back), ``thr_off``
+    int32[F+1], ``fbits``, ``rbits``, ``max_tree_words``.
+    """
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+    bases = np.asarray(bases, dtype=np.int64)
+    root_is_leaf = np.asarray(root_is_leaf, dtype=np.uint8)
+    n, T = nodes.shape[0], len(root_is_leaf)
+    if T == 0 or n_features < 1:
+        return None
+    meta = nodes[:, 1].astype(np.int64)
+    tree_of = np.repeat(np.arange(T), np.diff(bases))
+    left = bases[tree_of] + (meta & 0x3fffff)           # valid for internal nodes only
+    lleaf, rleaf = (meta >> 23) & 1, (meta >> 22) & 1
+    # leaf flags and depth of every node, level by level over all trees at once
+    is_leaf = np.zeros(n, dtype=bool)
+    roots = bases[:-1]
+    is_leaf[roots] = root_is_leaf != 0
+    levels = []
+    frontier = roots[root_is_leaf == 0]
+    while frontier.size:
+        levels.append(frontier)
+        L = left[frontier]
+        is_leaf[L], is_leaf[L + 1] = lleaf[frontier] != 0, rleaf[frontier] != 0
+        kids = np.concatenate([L, L + 1])
+        frontier = kids[~is_leaf[kids]]
+    internal = ~is_leaf
+    feat = np.where(internal, (meta >> 24) & 0xff, 0)
+    if internal.any() and feat[internal].max() >= n_features:
+        raise ValueError("tree uses a feature index outside the feature map")
+    # per-feature threshold tables and the rank of every node's threshold
+    thr = nodes[:, 0].view(np.float32)
+    tabs, thr_off, rank = [], [0], np.zeros(n, dtype=np.int64)
+    for f in range(n_features):
+        sel = internal & (feat == f)
+        s = np.unique(thr[sel])
+        if s.size > 65535:
+            return None
+        rank[sel] = np.searchsorted(s, thr[sel])
+        tabs.append(s)
+        thr_off.append(thr_off[-1] + s.size)
+    # subtree sizes in words (bottom-up), then positions (top-down)
+    size = np.where(is_leaf, 2, 0).astype(np.int64)
+    for lv in reversed(levels):
+        size[lv] = 1 + size[left[lv]] + size[left[lv] + 1]
+    tree_words = (size[roots] + RANKED_TREE_ALIGN - 1) // RANKED_TREE_ALIGN * RANKED_TREE_ALIGN
+    tree_start = np.concatenate([[0], np.cumsum(tree_words)])
+    if tree_words.max() > RANKED_MAX_TREE_WORDS or tree_start[-1] >= 2 ** 31:
+        return None
+    pos = np.zeros(n, dtype=np.int64)
+    pos[roots] = tree_start[:-1]
+    for lv in levels:
+        pos[left[lv]] = pos[lv] + 1
+        pos[left[lv] + 1] = pos[lv] + 1 + size[left[lv]]
+    off = np.where(internal, 1 + size[np.where(internal, left, 0)], 0)
+    bits = lambda v: max(1, int(v).bit_length())
+    fbits = bits(n_features - 1)
+    rbits = bits(max(1, max(s.size for s in tabs) - 1))
+    if fbits + rbits + bits(off.max()) > 30:
+        return None
+    words = np.zeros(int(tree_start[-1]), dtype=np.uint32)
+    ii = np.flatnonzero(internal)
+    words[pos[ii]] = (lleaf[ii] | (rleaf[ii] << 1) | (feat[ii] << 2) | (rank[ii] << (2 + fbits)) |
+                      (off[ii] << (2 + fbits + rbits))).astype(np.uint32)
+    li = np.flatnonzero(is_leaf)
+    words[pos[li]] = nodes[li, 0]
+    words[pos[li] + 1] = nodes[li, 1]
+    return {"words": words, "tree_start": tree_start.astype(np.int32),
+            "thr_tab": (np.concatenate(tabs) if tabs else np.zeros(0)).astype(np.float32),
+            "thr_off": np.asarray(thr_off, dtype=np.int32), "fbits": fbits, "rbits": rbits,
+            "max_tree_words": int(tree_words.max())}
+
+
+class RankedForest(ctypes.Structure):
+    """``lsml_ranked_forest`` of include/lsml_b200.h."""
+    _fields_ = [("words", ctypes.c_void_p), ("tree_start", ctypes.c_void_p),
+                ("root_is_leaf", ctypes.c_void_p), ("thr_tab", ctypes.c_void_p),
+                ("thr_off", ctypes.c_void_p), ("n_trees", ctypes.c_int), ("nfeat", ctypes.c_int),
+                ("fbits", ctypes.c_int), ("rbits", ctypes.c_int),
+                ("max_tree_words", ctypes.c_int), ("divisor", ctypes.c_double)]
+
+
 class ForestDeviceRegressor(DeviceRegressor):
     """``nodes`` / ``tree_base`` / ``root_is_leaf`` are the canonical single-node export
-    (:func:`pack_trees`, also what the golden fixtures store); the kernels walk the super-node
-    layout derived from it on first use."""
+    (:func:`pack_trees`, also what the golden fixtures store); the kernels walk layouts derived
+    from it on first use: rank-quantised 4-byte nodes from shared memory (:func:`pack_ranked`)
+    when the forest fits that format, else 32-byte super nodes (:func:`pack_supernodes`)."""
 
     def __init__(self, trees, n_features, divisor, scaler, device):
         super().__init__(n_features, scaler, device)
@@ -205,7 +308,8 @@ class ForestDeviceRegressor(DeviceRegressor):
         self.root_is_leaf = _dev(root_leaf, device)
         self.divisor = float(divisor)
         self.max_nodes = int(np.diff(bases).max()) if len(bases) > 1 else 0
-        self._super = self._pack_super(nodes, bases, root_leaf)
+        self._super = None                  # derived layouts are built on first use
+        self._ranked = None
 
     def _pack_super(self, nodes, bases, root_leaf):
         sn, leaves, root_ref, _ = pack_supernodes(nodes, bases, root_leaf)
@@ -222,7 +326,36 @@ class ForestDeviceRegressor(DeviceRegressor):
                                            self.root_is_leaf.cpu().numpy())
         return self._super
 
+    def _ranked_layout(self):
+        """The rank-quantised layout (``RankedForest`` struct + the tensors it points into), or
+        None when the forest does not fit it / LSML_FOREST_VARIANT asks for another kernel."""
+        if getattr(self, "_ranked", None) is None:
+            self._ranked = False
+            variant = os.environ.get("LSML_FOREST_VARIANT", "")
+            pk = None
+            if variant in ("", "ranked") and self.n_features <= 64:
+                pk = pack_ranked(self.nodes.cpu().numpy(), self.tree_base.cpu().numpy(),
+                                 self.root_is_leaf.cpu().numpy(), self.n_features)
+            if pk is not None:
+                keep = [_dev(pk[k], self.device) for k in ("words", "tree_start", "thr_tab",
+                                                           "thr_off")]
+                if keep[2].numel() == 0:               # (no internal node anywhere)
+                    keep[2] = torch.zeros(1, dtype=torch.float32, device=self.device)
+                rf = RankedForest(keep[0].data_ptr(), keep[1].data_ptr(),
+                                  self.root_is_leaf.data_ptr(), keep[2].data_ptr(),
+                                  keep[3].data_ptr(), self.n_trees, self.n_features, pk["fbits"],
+                                  pk["rbits"], pk["max_tree_words"], self.divisor)
+                self._ranked = (rf, keep)
+        return self._ranked or None
+
     def predict_into(self, X, n_band, out):
+        rk = self._ranked_layout()
+        if rk is not None:
+            _lib.check(_lib.lib.lsml_forest_ranked_predict(
+                _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
+                _lib.ptr(self.scale), ctypes.byref(rk[0]), _lib.ptr(out), _lib.current_stream()),
+                "forest_ranked_predict")
+            return
         sn, leaves, root_ref = self._layout()
         _lib.check(_lib.lib.lsml_forest_predict(
             _lib.ptr(X), _lib.ptr(n_band), ctypes.c_int(self.n_features), _lib.ptr(self.mean),
@@ -233,6 +366,13 @@ class ForestDeviceRegressor(DeviceRegressor):
             "forest_predict")
 
     def predict_band(self, src, n_band, out):
+        rk = self._ranked_layout()
+        if rk is not None:
+            _lib.check(_lib.lib.lsml_forest_ranked_predict_band(
+                ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean), _lib.ptr(self.scale),
+                ctypes.byref(rk[0]), _lib.ptr(out), _lib.current_stream()),
+                "forest_ranked_predict_band")
+            return
         sn, leaves, root_ref = self._layout()
         _lib.check(_lib.lib.lsml_forest_predict_band(
             ctypes.byref(src), _lib.ptr(n_band), _lib.ptr(self.mean),

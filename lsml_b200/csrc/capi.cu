@@ -390,6 +390,27 @@ int lsml_mlp_predict_band(const lsml_band_source* src, const long long* n_band, 
     return mlp_predict_band(bf, n_band, mean, scale, n_layers, sizes, W, b, act, out,
                             (cudaStream_t)stream);
 }
+static int ranked_args(const lsml_ranked_forest* f, RankedArgs& a) {
+    if (f == nullptr) { set_error("ranked forest is NULL"); return 1; }
+    a = RankedArgs{f->words, f->tree_start, f->root_is_leaf, f->thr_tab, f->thr_off, f->n_trees,
+                   f->nfeat, f->fbits, f->rbits, f->max_tree_words, f->divisor};
+    return 0;
+}
+int lsml_forest_ranked_predict(const double* X, const long long* n_band, int nfeat,
+                               const double* mean, const double* scale,
+                               const lsml_ranked_forest* forest, double* out, void* stream) {
+    RankedArgs a;
+    if (ranked_args(forest, a)) return 1;
+    return forest_ranked_predict(X, n_band, nfeat, mean, scale, a, out, (cudaStream_t)stream);
+}
+int lsml_forest_ranked_predict_band(const lsml_band_source* src, const long long* n_band,
+                                    const double* mean, const double* scale,
+                                    const lsml_ranked_forest* forest, double* out, void* stream) {
+    BandFeatures bf;
+    RankedArgs a;
+    if (band_source(src, bf) || ranked_args(forest, a)) return 1;
+    return forest_ranked_predict_band(bf, n_band, mean, scale, a, out, (cudaStream_t)stream);
+}
 int lsml_band_update(int ndim, const int* shape, long long batch, const double* dx, double* u,
                      const double* vel, const long long* band_idx, const long long* n_band,
                      double step, double* new_u, double* gmag_out, int apply, void* stream) {

@@ -840,17 +840,32 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
     const int nring = __popc(ringp), nwon = __popc(won);
     i64 pos, cpos;
     {
-        cg::coalesced_group cgp = cg::coalesced_threads();
-        const int last = (int)cgp.size() - 1;
-        const int ir = cg::inclusive_scan(cgp, nring), iw = cg::inclusive_scan(cgp, nwon);
-        const int tr = cgp.shfl(ir, last), tw = cgp.shfl(iw, last);
+        // exclusive prefix sums of nring (<= 12: 4 bits) and nwon (<= 6: 3 bits) over the lanes
+        // publishing together, one ballot per bit (cg::inclusive_scan on a coalesced group
+        // loops over __fns: ~7 % of the kernel's instructions in round 2's profile)
+        const unsigned active = __activemask();
+        const unsigned lower = active & ((1u << (threadIdx.x & 31u)) - 1u);
+        int er = 0, tr = 0, ew = 0, tw = 0;
+#pragma unroll
+        for (int bit = 0; bit < 4; ++bit) {
+            const unsigned bal = __ballot_sync(active, (nring >> bit) & 1);
+            er += __popc(bal & lower) << bit;
+            tr += __popc(bal) << bit;
+        }
+#pragma unroll
+        for (int bit = 0; bit < 3; ++bit) {
+            const unsigned bal = __ballot_sync(active, (nwon >> bit) & 1);
+            ew += __popc(bal & lower) << bit;
+            tw += __popc(bal) << bit;
+        }
+        const int leader = __ffs(active) - 1;
         i64 br = 0, bw = 0;
-        if (cgp.thread_rank() == 0) {
+        if ((int)(threadIdx.x & 31u) == leader) {
             if (tr) br = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->tail3[sc.tslot]), (u64)tr);
             if (tw) bw = (i64)atomicAdd(reinterpret_cast<u64*>(&sc.ctr->n_cand), (u64)tw);
         }
-        pos = sc.base + cgp.shfl(br, 0) + ir - nring;
-        cpos = cgp.shfl(bw, 0) + iw - nwon;
+        pos = sc.base + __shfl_sync(active, br, leader) + er;
+        cpos = __shfl_sync(active, bw, leader) + ew;
     }
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -1022,29 +1037,27 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                            hint_tag, slot};
             const i64 work = end - begin + nbk;
             const i64 pbase = nbk ? ctr->offs[sweep] : 0;
-            // entry k of the work set goes to warp k % nwarps, lane k / nwarps: a small set is
-            // spread one entry per warp (a lone lane runs its own path, not the union of 32
-            // divergent ones), a large one fills the warps evenly
-#ifndef FMM_DENSE_FACTOR
-#define FMM_DENSE_FACTOR 4
+            // The work set is dealt to the warps in CHUNKS of G consecutive entries (entries
+            // pushed together belong to neighbouring voxels: similar stencils, similar replay
+            // paths, overlapping cache lines), chunk c to warp c % nwarps; G is the largest power
+            // of two that still gives every warp work (G = 1: a small set is spread one entry
+            // per warp -- a lone lane runs its own path, not the union of 32 divergent ones;
+            // G = 32: a large one fills whole warps with consecutive entries).
+            // -DFMM_CHUNK=n fixes G (probes, tools/r2_fmm_variants.sh).
+            int G = 1;
+#ifdef FMM_CHUNK
+            G = FMM_CHUNK;
+#else
+            while (G < 32 && (i64)(2 * G) * nwarps <= work) G <<= 1;
 #endif
-            if (work >= (i64)FMM_DENSE_FACTOR * nwarps) {
-                // a large set: consecutive entries (pushed together by neighbouring threads, i.e.
-                // voxels that are neighbours in space) go to the lanes of ONE warp -- similar
-                // stencils, similar replay paths, overlapping cache lines
-                for (i64 k = tid; k < work; k += nthreads) {
-                    const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
-                                                    : park[pbase + k - (end - begin)];
-                    process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
-                    ++nreplay;
-                }
-            } else {
-                for (i64 k = (i64)lane * nwarps + gwarp; k < work; k += nthreads) {
-                    const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
-                                                    : park[pbase + k - (end - begin)];
-                    process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
-                    ++nreplay;
-                }
+            const int per_warp = 32 / G;             // chunks a warp holds per pass
+            for (i64 round = lane / G;; round += per_warp) {
+                const i64 k = (round * nwarps + gwarp) * G + (lane & (G - 1));
+                if (k >= work) break;
+                const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
+                                                : park[pbase + k - (end - begin)];
+                process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
+                ++nreplay;
             }
         } else {
             // ---- fallback: scan the candidate list; a warp collects its queued entries in

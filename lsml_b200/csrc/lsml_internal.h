@@ -76,6 +76,21 @@ int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double*
                         const unsigned* root_ref, const u8* root_is_leaf, int n_trees,
                         double divisor, const void* nodes8, const int* tree_base, int max_nodes,
                         double* out, cudaStream_t s);
+// rank-quantised forest (regress.cu: forest_ranked_kernel; lsml_b200.h: lsml_ranked_forest)
+struct RankedArgs {
+    const unsigned* words;
+    const int* tree_start;
+    const u8* root_is_leaf;
+    const float* thr_tab;
+    const int* thr_off;
+    int n_trees, nfeat, fbits, rbits, max_tree_words;
+    double divisor;
+};
+int forest_ranked_predict(const double* X, const i64* n_band, int F, const double* mean,
+                          const double* scale, const RankedArgs& a, double* out, cudaStream_t s);
+int forest_ranked_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                               const double* scale, const RankedArgs& a, double* out,
+                               cudaStream_t s);
 int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,
                 int n_layers, const int* sizes, const double* const* W, const double* const* b,
                 int act, double* out, cudaStream_t s);

@@ -273,6 +273,154 @@ forest_staged_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Sta
     }
 }
 
+// --------------------------------------------------------------------------- ranked forest
+// Rank-quantised forest walked from shared memory (lsml_b200/core/regressors.py: pack_ranked).
+// A tree only asks `x[f] <= thr`; with S_f the sorted distinct float32 thresholds of feature f
+// and rank_f(x) = #{s in S_f : s < x}, that is `rank_f(x) <= j` for the node holding S_f[j].  A
+// voxel's features are reduced ONCE to ranks (one binary search per feature), an internal node
+// is ONE 32-bit word
+//     bit 0 / 1: the left / right child is a leaf | feature << 2 | rank << (2 + fbits) |
+//     (offset of the right child in words) << (2 + fbits + rbits)
+// trees are stored in preorder (left child = next word, a leaf = its float64 value in two
+// words), and the whole forest is ~3.7 KB per 300-leaf tree: a CTA stages GROUPS of ~20 trees in
+// shared memory and walks them for its 512 (x V) voxels, the float64 sum keeping sklearn's tree
+// order.  A node visit is two shared-memory loads -- the node (divergent: ~3-4 bank-conflict
+// wavefronts per warp instead of up to 32 L1 tag lookups of a 32-byte global node) and the
+// voxel's rank of that feature ([feature][voxel] layout: conflict-free) -- and ~13 instructions;
+// the ranks are stored pre-shifted so that the comparison needs no field extraction.
+struct RankedView {
+    const unsigned* words;
+    const int* tree_start;     // [n_trees + 1], word offsets (multiples of 4)
+    const u8* root_is_leaf;    // [n_trees]
+    const float* thr_tab;      // S_0 | S_1 | ...
+    const int* thr_off;        // [F + 1]
+    int n_trees, fbits, rbits;
+    double divisor;
+};
+
+constexpr int RK_THREADS = 512;
+constexpr int RK_CTAS_PER_SM = 2;
+constexpr int RK_MAX_GROUP = 128;          // trees per staged group
+constexpr int RK_SMEM_PER_CTA = 112 * 1024;
+
+// #{s in S_f : s < x}, NaN -> |S_f| (ranks above every threshold: `!(x <= thr)` goes right)
+__device__ __forceinline__ unsigned rank_of(const float* __restrict__ tab, int lo, int hi, float x) {
+    if (x != x) return (unsigned)(hi - lo);
+    const int first = lo;
+    int len = hi - lo;
+    while (len > 0) {
+        const int half = len >> 1;
+        if (__ldg(tab + lo + half) < x) { lo += half + 1; len -= half + 1; }
+        else len = half;
+    }
+    return (unsigned)(lo - first);
+}
+
+__device__ __forceinline__ unsigned lds32(unsigned saddr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+__device__ __forceinline__ unsigned mad32(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <int V>
+__global__ void __launch_bounds__(RK_THREADS, RK_CTAS_PER_SM)
+forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, RankedView rv,
+                     double* __restrict__ out, int cap_words) {
+    extern __shared__ __align__(16) unsigned rk_smem[];
+    __shared__ int s_base[RK_MAX_GROUP];
+    __shared__ u8 s_rootleaf[RK_MAX_GROUP];
+    constexpr int N = V * RK_THREADS;
+    const int F = src.F;
+    unsigned* const ranks = rk_smem;                 // [F][N], rank << (2 + fbits)
+    unsigned* const trees = rk_smem + (size_t)F * N; // [cap_words]
+    const int rshift = 2 + rv.fbits;
+    const unsigned fmask4 = ((1u << rv.fbits) - 1u) << 2;
+    const unsigned rmask = ((1u << rv.rbits) - 1u) << rshift;
+    const int oshift = rshift + rv.rbits;
+    const i64 nb = *n_band;
+    const i64 nchunks = (nb + N - 1) / N;
+    for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        __syncthreads();                             // the previous chunk's walks are done
+        unsigned valid = 0u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int slot = v * RK_THREADS + threadIdx.x;
+            const i64 b = chunk * N + slot;
+            if (b < nb) {
+                valid |= 1u << v;
+                const VoxelRef vr = row_ref(src, b);
+                for (int f = 0; f < F; ++f) {
+                    const float x = __double2float_rn(scaled(src, b, vr, f, sc));
+                    const unsigned r = rank_of(rv.thr_tab, __ldg(rv.thr_off + f),
+                                               __ldg(rv.thr_off + f + 1), x);
+                    ranks[f * N + slot] = r << rshift;
+                }
+            }
+        }
+        double acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = 0.0;
+        // 32-bit shared addresses: this thread's column of the rank table, the tree buffer
+        const unsigned my_sa = (unsigned)__cvta_generic_to_shared(ranks + threadIdx.x);
+        const unsigned trees_sa = (unsigned)__cvta_generic_to_shared(trees);
+        int t0 = 0;
+        while (t0 < rv.n_trees) {
+            // group [t0, t1): as many whole trees as the buffer holds
+            const int gbase = __ldg(rv.tree_start + t0);
+            int t1 = t0 + 1;
+            while (t1 < rv.n_trees && t1 - t0 < RK_MAX_GROUP &&
+                   __ldg(rv.tree_start + t1 + 1) - gbase <= cap_words) ++t1;
+            const int gwords = __ldg(rv.tree_start + t1) - gbase;
+            __syncthreads();                         // the previous group's walks are done
+            {
+                const uint4* gsrc = reinterpret_cast<const uint4*>(rv.words + gbase);
+                uint4* gdst = reinterpret_cast<uint4*>(trees);
+                for (int i = threadIdx.x; i < (gwords >> 2); i += RK_THREADS) gdst[i] = __ldg(gsrc + i);
+                for (int t = t0 + threadIdx.x; t < t1; t += RK_THREADS) {
+                    s_base[t - t0] = (__ldg(rv.tree_start + t) - gbase) * 4;      // bytes
+                    s_rootleaf[t - t0] = __ldg(rv.root_is_leaf + t);
+                }
+            }
+            __syncthreads();
+            for (int t = 0; t < t1 - t0; ++t) {
+                unsigned ia[V];                      // shared address of the chain's node
+                unsigned live = s_rootleaf[t] ? 0u : valid;
+#pragma unroll
+                for (int v = 0; v < V; ++v) ia[v] = trees_sa + (unsigned)s_base[t];
+                while (live) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if (V > 1 && !((live >> v) & 1u)) continue;
+                        const unsigned n = lds32(ia[v]);
+                        // row `feature` of the rank table: (feature * 4) * N bytes
+                        const unsigned w = lds32(mad32(n & fmask4, N, my_sa + v * RK_THREADS * 4));
+                        const bool right = w > (n & rmask);
+                        unsigned nx = ia[v] + 4u;                      // left child: next word
+                        if (right) nx = ia[v] + ((n >> oshift) << 2);
+                        ia[v] = nx;
+                        if (n & (right ? 2u : 1u)) live &= ~(1u << v);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v)          // (a dead slot reads two node words: harmless)
+                    acc[v] += __hiloint2double((int)lds32(ia[v] + 4u), (int)lds32(ia[v]));
+            }
+            t0 = t1;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const i64 b = chunk * N + v * RK_THREADS + threadIdx.x;
+            if (b < nb) out[b] = acc[v] / rv.divisor;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------- MLP
 // One thread per band voxel; weights are read through the read-only path (L1-resident: a
 // (F x H) float64 layer with F=16, H=100 is 12.8 KB).  Activations ping-pong in shared memory
@@ -415,6 +563,63 @@ static int forest_launch(const FeatSrc& src, const i64* n_band, const double* me
     return 0;
 }
 
+template <int V>
+static int ranked_launch_v(const FeatSrc& src, const i64* n_band, const Scaler& sc,
+                           const RankedView& rv, double* out, size_t smem, int ctas_per_sm,
+                           cudaStream_t s) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        LSML_CUDA(cudaFuncSetAttribute(forest_ranked_kernel<V>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const size_t rank_bytes = (size_t)src.F * V * RK_THREADS * sizeof(unsigned);
+    const int cap_words = (int)((smem - rank_bytes) / sizeof(unsigned)) & ~3;
+    forest_ranked_kernel<V><<<LSML_SMS * ctas_per_sm, RK_THREADS, smem, s>>>(src, n_band, sc, rv,
+                                                                              out, cap_words);
+    LSML_LAUNCH_CHECK("forest_ranked_kernel");
+    return 0;
+}
+
+// voxels per thread (LSML_FOREST_RK_V = 1 | 2 overrides the default of 1: probes)
+static int ranked_v_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LSML_FOREST_RK_V");
+        v = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }
+    return v;
+}
+
+static int ranked_launch(const FeatSrc& src, const i64* n_band, const double* mean,
+                         const double* scale, const RankedArgs& a, double* out, cudaStream_t s) {
+    if (a.nfeat != src.F) { set_error("ranked forest: exported for %d features, source has %d", a.nfeat, src.F); return 1; }
+    if (a.n_trees < 1 || a.fbits < 1 || a.rbits < 1 || 2 + a.fbits + a.rbits > 31 ||
+        src.F > (1 << a.fbits) || a.max_tree_words < 2) {
+        set_error("ranked forest: bad layout parameters");
+        return 1;
+    }
+    if ((reinterpret_cast<uintptr_t>(a.words) & 15u) != 0) {
+        set_error("ranked forest: words must be 16-byte aligned");
+        return 1;
+    }
+    const Scaler sc{mean, scale};
+    const RankedView rv{a.words, a.tree_start, a.root_is_leaf, a.thr_tab, a.thr_off,
+                        a.n_trees, a.fbits, a.rbits, a.divisor};
+    const size_t tree_bytes = (size_t)a.max_tree_words * sizeof(unsigned);
+    const size_t want_trees = tree_bytes > 32 * 1024 ? tree_bytes : 32 * 1024;
+    const size_t two = RK_SMEM_PER_CTA - 1024, one = 224 * 1024;      // per CTA: 2 / 1 per SM
+    const size_t rank1 = (size_t)src.F * RK_THREADS * sizeof(unsigned);
+    const int vo = ranked_v_override();
+    if (vo == 2 && 2 * rank1 + want_trees <= two)
+        return ranked_launch_v<2>(src, n_band, sc, rv, out, two, 2, s);
+    if (rank1 + want_trees <= two) return ranked_launch_v<1>(src, n_band, sc, rv, out, two, 2, s);
+    if (rank1 + tree_bytes <= one) return ranked_launch_v<1>(src, n_band, sc, rv, out, one, 1, s);
+    set_error("ranked forest: %d features and trees of %d words do not fit shared memory",
+              src.F, a.max_tree_words);
+    return 1;
+}
+
 static int mlp_launch(const FeatSrc& src, const i64* n_band, const double* mean,
                       const double* scale, int n_layers, const int* sizes, const double* const* W,
                       const double* const* b, int act, double* out, cudaStream_t s) {
@@ -464,6 +669,16 @@ int forest_predict_band(const BandFeatures& bf, const i64* n_band, const double*
                         double* out, cudaStream_t s) {
     return forest_launch(program_source(bf), n_band, mean, scale, nodes, leaves, root_ref,
                          root_is_leaf, n_trees, divisor, nodes8, tree_base, max_nodes, out, s);
+}
+
+int forest_ranked_predict(const double* X, const i64* n_band, int F, const double* mean,
+                          const double* scale, const RankedArgs& a, double* out, cudaStream_t s) {
+    return ranked_launch(matrix_source(X, F), n_band, mean, scale, a, out, s);
+}
+int forest_ranked_predict_band(const BandFeatures& bf, const i64* n_band, const double* mean,
+                               const double* scale, const RankedArgs& a, double* out,
+                               cudaStream_t s) {
+    return ranked_launch(program_source(bf), n_band, mean, scale, a, out, s);
 }
 
 int mlp_predict(const double* X, const i64* n_band, const double* mean, const double* scale,

@@ -39,6 +39,7 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if 
 static inline u64 atomicMax(u64* p, u64 v) { u64 o = *p; if (v > o) *p = v; return o; }
 static inline unsigned __activemask() { return 1u; }
 static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -184,6 +184,86 @@ def test_pack_supernodes_round_trip():
         assert np.array_equal(got, m.predict(Xt)), type(m).__name__
 
 
+def _walk_ranked(pk, root_leaf, X32):
+    """numpy restatement of regress.cu: forest_ranked_kernel (ranks once, 4-byte nodes)."""
+    words, start = pk["words"], pk["tree_start"]
+    tab, off, fb, rb = pk["thr_tab"], pk["thr_off"], pk["fbits"], pk["rbits"]
+    F = len(off) - 1
+    ranks = np.empty((len(X32), F), dtype=np.int64)
+    for f in range(F):
+        s = tab[off[f]:off[f + 1]]
+        ranks[:, f] = np.where(np.isnan(X32[:, f]), len(s), np.searchsorted(s, X32[:, f], "left"))
+    out = np.zeros(len(X32))
+    for t in range(len(root_leaf)):
+        for i in range(len(X32)):
+            idx, leaf = int(start[t]), bool(root_leaf[t])
+            while not leaf:
+                n = int(words[idx])
+                f, j = (n >> 2) & ((1 << fb) - 1), (n >> (2 + fb)) & ((1 << rb) - 1)
+                right = ranks[i, f] > j
+                leaf = bool(n & (2 if right else 1))
+                idx += (n >> (2 + fb + rb)) if right else 1
+            out[i] += words[idx:idx + 2].view(np.float64)[0]
+    return out
+
+
+def test_pack_ranked_round_trip():
+    """The rank-quantised 4-byte-node layout (shared-memory forest kernel) reaches the same leaves
+    as scikit-learn: thresholds replaced by their rank among the forest's thresholds of that
+    feature, features by their rank -- including values EQUAL to a threshold, NaN, depth-1 /
+    single-leaf trees and the bench's forest recipe (max_samples=300)."""
+    from sklearn.ensemble import ExtraTreesRegressor, RandomForestRegressor
+    from sklearn.tree import DecisionTreeRegressor
+    from lsml_b200.core.regressors import pack_ranked, pack_trees
+    rs = np.random.RandomState(3)
+    X = rs.randn(600, 6)
+    X[:, 5] = np.round(X[:, 5])                        # few distinct values: shared thresholds
+    y = X[:, 0] * 2 + np.sin(X[:, 1]) + X[:, 5] + 0.1 * rs.randn(600)
+    models = [RandomForestRegressor(n_estimators=6, max_depth=7, random_state=0).fit(X, y),
+              RandomForestRegressor(n_estimators=9, max_samples=300, random_state=1).fit(X, y),
+              ExtraTreesRegressor(n_estimators=3, max_depth=9, random_state=2).fit(X, y),
+              DecisionTreeRegressor(max_depth=1).fit(X, y),
+              DecisionTreeRegressor(max_depth=2).fit(X, y),
+              DecisionTreeRegressor().fit(X, np.ones(600))]          # a single leaf
+    Xt = rs.randn(150, 6)
+    Xt[:40] = X[:40]
+    Xt[:, 5] = np.round(Xt[:, 5])
+    for m in models:
+        trees = [e.tree_ for e in m.estimators_] if hasattr(m, "estimators_") else [m.tree_]
+        nodes, bases, root = pack_trees(trees, 6)
+        pk = pack_ranked(nodes, bases, root, 6)
+        assert pk is not None and pk["words"].dtype == np.uint32
+        assert (pk["tree_start"] % 4 == 0).all() and pk["tree_start"][-1] == len(pk["words"])
+        assert 2 + pk["fbits"] + pk["rbits"] <= 30
+        X32 = Xt.astype(np.float32)
+        # values exactly ON thresholds (x <= thr goes left) and just above them
+        tab = pk["thr_tab"]
+        if len(tab):
+            f0 = int(np.argmax(np.diff(pk["thr_off"])))
+            s = tab[pk["thr_off"][f0]:pk["thr_off"][f0 + 1]]
+            k = min(len(s), 20)
+            X32[40:40 + k, f0] = s[:k]
+            X32[60:60 + k, f0] = np.nextafter(s[:k], np.float32(np.inf))
+        got = _walk_ranked(pk, root, X32) / len(trees)
+        assert np.array_equal(got, m.predict(X32.astype(np.float64))), type(m).__name__
+    # NaN features go right everywhere, as `!(x <= thr)` does in the other kernels
+    m = models[1]
+    nodes, bases, root = pack_trees([e.tree_ for e in m.estimators_], 6)
+    pk = pack_ranked(nodes, bases, root, 6)
+    Xn = np.full((1, 6), np.nan, dtype=np.float32)
+    want = 0.0
+    for e in m.estimators_:
+        t, i = e.tree_, 0
+        while t.children_left[i] != -1:
+            i = t.children_right[i]
+        want += t.value[i, 0, 0]
+    assert _walk_ranked(pk, root, Xn)[0] == want
+    # a forest that does not fit the format is refused, not mangled
+    big = DecisionTreeRegressor().fit(rs.randn(9000, 6), rs.randn(9000))
+    nodes, bases, root = pack_trees([big.tree_], 6)
+    assert pack_ranked(nodes, bases, root, 6) is None
+
+
 def test_fit_host_logic_matches_reference_statements():
     """The host-side pieces of `fit` that decide WHICH data is used, against literal
     transcriptions of the reference's statements (datasets_handler.py:312-362; the reference's

@@ -171,9 +171,15 @@ def _train_models(X, y, seed=0):
     return models
 
 
-def test_regressors_against_sklearn():
+@pytest.mark.parametrize("variant", ["ranked", "global"])
+def test_regressors_against_sklearn(variant, monkeypatch):
+    """``variant``: which forest kernel the exported model walks -- rank-quantised 4-byte nodes
+    from shared memory (the default whenever the forest fits that format) or 32-byte super
+    nodes from global memory; ExtraTrees with full-depth trees of 4000 samples do not fit the
+    ranked format and take the super-node path in both runs."""
     import torch
     from lsml_b200.core.regressors import export_regressor
+    monkeypatch.setenv("LSML_FOREST_VARIANT", variant)
     rs = np.random.RandomState(5)
     X = rs.randn(4000, 12) * rs.rand(12) * 5 + rs.randn(12)
     y = np.sin(X[:, 0]) + 0.5 * X[:, 3] - (X[:, 5] > 0.3) + 0.1 * rs.randn(4000)
@@ -185,12 +191,43 @@ def test_regressors_against_sklearn():
     Xd = torch.from_numpy(Xt).cuda()
     for name, m in models.items():
         want = m.predict(Xt)
-        got = export_regressor(m).predict(Xd).cpu().numpy()
+        reg = export_regressor(m)
+        got = reg.predict(Xd).cpu().numpy()
         if name in ("forest", "forest_noscale", "extra", "tree"):
             assert np.array_equal(got, want), (name, np.abs(got - want).max())
+            if name in ("forest", "forest_noscale", "tree"):
+                assert (reg._ranked_layout() is not None) == (variant == "ranked"), name
         else:
             assert np.allclose(got, want, rtol=1e-11, atol=1e-12), \
                 (name, np.abs(got - want).max())
+
+
+def test_ranked_forest_shapes():
+    """The shared-memory forest kernel at its corners: more trees than one staged group holds,
+    64 features (one CTA per SM), a batch that is not a multiple of the chunk, NaN features."""
+    import torch
+    from sklearn.ensemble import RandomForestRegressor
+    from lsml_b200.core.regressors import export_regressor
+    rs = np.random.RandomState(11)
+    for F, n_trees, n in ((5, 150, 2051), (64, 30, 1500), (33, 40, 513)):
+        X = rs.randn(1500, F)
+        y = X[:, 0] - 2 * X[:, F - 1] + np.cos(X[:, F // 2]) + 0.1 * rs.randn(1500)
+        m = RandomForestRegressor(n_estimators=n_trees, max_samples=400, random_state=0).fit(X, y)
+        reg = export_regressor(m)
+        assert reg._ranked_layout() is not None
+        Xt = rs.randn(n, F)
+        Xt[:200] = X[:200]
+        got = reg.predict(torch.from_numpy(Xt).cuda()).cpu().numpy()
+        assert np.array_equal(got, m.predict(Xt)), (F, n_trees)
+    Xn = np.full((3, 33), np.nan)
+    got = reg.predict(torch.from_numpy(Xn).cuda()).cpu().numpy()
+    want = 0.0
+    for e in m.estimators_:
+        t, i = e.tree_, 0
+        while t.children_left[i] != -1:
+            i = t.children_right[i]
+        want += t.value[i, 0, 0]
+    assert np.array_equal(got, np.full(3, want / len(m.estimators_)))
 
 
 @pytest.mark.parametrize("shape,dx", [((51, 51), (1.0, 1.0)), ((30, 33, 29), (1.0, 0.75, 1.5))])
