@@ -865,6 +865,13 @@ def main():
     rebuild_bytes = 17.0 * avg_cand
     rebuild_gbs = rebuild_bytes / (rebuild_avg_ms * 1e-3) / 1e9 if rebuild_avg_ms > 0 else 0.0
     upd_n, upd_ms = phases.get("update", (1, 0.0))
+    # the velocity kernel (features gathered in-kernel -> forest): dominant kernel of region (A),
+    # i.e. of BASELINE.json's metric.  Algorithmic bytes per band voxel: band index
+    # (8) + one float64 per image plane (8 P) + velocity out (8).
+    vel_n, vel_ms = phases.get("predict", (1, 0.0))
+    n_planes = int(eng.planes.shape[0]) if getattr(eng, "planes", None) is not None else 0
+    velocity_bytes = (16.0 + 8.0 * n_planes) * (bvi / max(1, args.steps)) / N_ITERS
+    velocity_gbs = velocity_bytes / (vel_ms / max(1, vel_n) * 1e-3) / 1e9 if vel_ms > 0 else 0.0
     update_bytes = 64.0 * (bvi / max(1, args.steps)) / N_ITERS      # ~64 B/band voxel
     update_gbs = update_bytes / (upd_ms / max(1, upd_n) * 1e-3) / 1e9 if upd_ms > 0 else 0.0
 
@@ -1003,6 +1010,20 @@ def main():
                                   "frac": centered_gbs / peak, "traffic": None,
                                   "algorithmic_bytes_per_launch": centered_bytes,
                                   "peak_source": peak_src, "ms": gc_ms},
+            "roofline_velocity": {"bound": "hbm",
+                                  "kernel": "forest_ranked_kernel: feature gather + RF-100 walked from "
+                                            "shared memory (rank-quantised 4-byte nodes), the dominant "
+                                            "kernel of region (A)",
+                                  "achieved": velocity_gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": velocity_gbs / peak,
+                                  "traffic": ncu_traffic("forest_ranked_kernel")[0],
+                                  "traffic_source": ncu_traffic("forest_ranked_kernel")[1],
+                                  "algorithmic_bytes_per_launch": velocity_bytes,
+                                  "peak_source": peak_src, "ms": vel_ms / max(1, vel_n),
+                                  "note": "not HBM-bound: ~1100 dependent shared-memory node visits "
+                                          "per voxel; the limiter is the L1/shared data pipe "
+                                          "(bank-conflict wavefronts of divergent node fetches) and "
+                                          "instruction issue, DESIGN.md 4.4"},
             "roofline_update": {"bound": "hbm",
                                 "kernel": "band_update_kernel + band_apply_kernel (banded upwind "
                                           "|Du|, u += step*v*|Du|, exact statistics)",

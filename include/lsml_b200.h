@@ -331,6 +331,9 @@ int lsml_fmm_sweep_sizes(long long total, void *workspace, long long *out, void 
  * runs)}. */
 long long lsml_fmm_counters_offset(long long total);
 long long lsml_fmm_status_offset(void);
+/* diagnostics (builds with -DFMM_PHASE_CLOCKS): byte offset, inside the counters, of int64[8] SM
+ * cycles one lane spent per phase of the small grid-wide sweeps (see FmmCounters::phase) */
+long long lsml_fmm_phase_offset(void);
 
 /* ---- either side of the path -------------------------------------------------- */
 /* u0 = 2*ball - 1 with ball = (radius - |idx*dx - location*dx|) > 0

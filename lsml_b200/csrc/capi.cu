@@ -497,6 +497,7 @@ int lsml_fmm_sweep_sizes(long long total, void* workspace, long long* out, void*
 
 long long lsml_fmm_counters_offset(long long total) { return fmm_counters_offset(total); }
 long long lsml_fmm_status_offset(void) { return fmm_counters_failed_offset(); }
+long long lsml_fmm_phase_offset(void) { return fmm_counters_phase_offset(); }
 
 int lsml_ball_init(int ndim, const int* shape, long long batch, const double* dx, double* u,
                    const double* location, double radius, const double* centres,

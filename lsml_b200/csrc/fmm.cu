@@ -113,6 +113,9 @@ struct FmmCounters {      // device-resident
     i64 live[4];          // {sweep, rix, begin, end} published by thread 0 before every grid-wide
                           // step: readable from another stream while a march is running (hang
                           // diagnosis, tools/c4_probe.py)
+    i64 phase[8];         // -DFMM_PHASE_CLOCKS: SM cycles one lane spent per phase of the small
+                          // grid-wide sweeps {loop top -> entry, replay, record, publish, fence,
+                          // barrier, -, number of sweeps sampled} (diagnostic, tools/fmm_probe.py)
 };
 // [host-sched:end]
 
@@ -621,8 +624,14 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
     unsigned F = 0u;                  // frozen now
     unsigned E = 0u;                  // pending event (marched voxel with a value inside the band)
     const double inf = pos_inf();
-#pragma unroll
-    for (int r = 0; r < 13; ++r) { tv[r] = inf; qr[r] = 0.f; lv[r] = 0; }
+    tv[6] = inf; qr[6] = 0.f; lv[6] = 0;
+    // ALL stencil loads are issued before any of them is used: 24 independent L2 reads, one round
+    // trip.  (Written as "if in range { load; use }" per slot, the loads sit in 12 separate
+    // conditional blocks and each block waits for its own round trip: 12 in a row, a quarter of
+    // the replay's latency in round 2's profile.)  An out-of-range slot reads x itself.
+    double tl[13];
+    u8 sl[13];
+    unsigned okm = 0u;
 #pragma unroll
     for (int ax = 3 - NDIM; ax < 3; ++ax) {
 #pragma unroll
@@ -631,17 +640,28 @@ __device__ double replay(i64 l, const int (&coord)[3], const double* __restrict_
 #pragma unroll
             for (int which = 1; which <= 2; ++which) {
                 const int cc = coord[ax] + which * j;
-                if (cc >= 0 && cc < ext[ax]) {
-                    const i64 n = l + which * j * st[ax];
-                    const double t = __ldcg(T + n);   // L2: other CTAs update T concurrently
-                    const u8 s = __ldcg(mask + n);
-                    const int r = slot_rank(ax, d, which);
-                    tv[r] = t; qr[r] = qmag(t); lv[r] = s >> 2;
-                    if (s == ST_INIT) F |= 1u << r;
-                    else if ((s & ST_CAND) && (fabs(t) <= band)) E |= 1u << r;
-                }
+                const bool ok = cc >= 0 && cc < ext[ax];
+                const i64 n = ok ? l + which * j * st[ax] : l;
+                const int r = slot_rank(ax, d, which);
+                tl[r] = __ldcg(T + n);            // L2: other CTAs update T concurrently
+                sl[r] = __ldcg(mask + n);
+                okm |= ok ? 1u << r : 0u;
             }
         }
+    }
+#pragma unroll
+    for (int r = 0; r < 13; ++r) {
+        if (r == 6) continue;
+        if (NDIM < 3 && (r < 2 || r > 10)) { tv[r] = inf; qr[r] = 0.f; lv[r] = 0; continue; }
+        if (NDIM < 2 && (r < 4 || r > 8)) { tv[r] = inf; qr[r] = 0.f; lv[r] = 0; continue; }
+        const bool ok = (okm >> r) & 1u;
+        const double t = tl[r];
+        const u8 s = sl[r];
+        tv[r] = ok ? t : inf;
+        qr[r] = ok ? qmag(t) : 0.f;
+        lv[r] = ok ? (unsigned char)(s >> 2) : (unsigned char)0;
+        F |= (ok && s == ST_INIT) ? 1u << r : 0u;
+        E |= (ok && s != ST_INIT && (s & ST_CAND) && fabs(t) <= band) ? 1u << r : 0u;
     }
     float ql[13];                     // dynamically indexed copy
 #pragma unroll
@@ -792,30 +812,45 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
     const unsigned cur = sc.next - 1u;
     constexpr int NS = 4 * NDIM;
     const int offs[4] = {-2, -1, 1, 2};
-    // phase 1: state bytes of the stencil
+    // phase 1: state bytes of the stencil.  Every phase issues ALL its loads / atomics before it
+    // looks at any result (an out-of-range slot reads x itself), so that a phase costs one L2
+    // round trip and not one per neighbour.
     unsigned valid = 0u;
     u8 s[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const int cc = coord[ax] + j;
-        s[k] = 0xff;
-        if (cc >= 0 && cc < ext[ax] && (ax != 0 || (cc >= g.own_lo && cc < g.own_hi))) {
-            valid |= 1u << k;                     // (halo copies are neither queued nor claimed)
-            s[k] = __ldcg(mask + l + j * st[ax]);
-        }
+        const bool okk = cc >= 0 && cc < ext[ax] && (ax != 0 || (cc >= g.own_lo && cc < g.own_hi));
+        valid |= okk ? 1u << k : 0u;              // (halo copies are neither queued nor claimed)
+        s[k] = __ldcg(mask + (okk ? l + j * st[ax] : l));
     }
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if (!((valid >> k) & 1u)) s[k] = 0xff;
     // phase 2: scheduling records of the candidates; claims of far direct neighbours
     uint2 a[NS];
-    unsigned won = 0u;
+    unsigned oldw[NS];
+    unsigned claims = 0u, won = 0u;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        const i64 n = ((valid >> k) & 1u) ? l + j * st[ax] : l;
+        a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
+        oldw[k] = 0xffffffffu;
+        if (expose && (j == 1 || j == -1) && s[k] == 0) {        // claim(): state 0 -> candidate
+            claims |= 1u << k;
+            oldw[k] = atomicOr(reinterpret_cast<unsigned*>(mask + (n & ~(i64)3)),
+                               (unsigned)ST_CAND << (8u * (unsigned)(n & 3)));
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const i64 n = l + j * st[ax];
-        a[k] = make_uint2(0xffffffffu, 0u);
-        if ((s[k] & 3) == ST_CAND || (expose && (j == 1 || j == -1) && s[k] == 0))
-            a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
-        if (expose && (j == 1 || j == -1) && s[k] == 0 && claim(mask, n, ST_CAND)) won |= 1u << k;
+        const bool claimed = (claims >> k) & 1u;
+        if (claimed && ((oldw[k] >> (8u * (unsigned)(n & 3))) & 0xffu) == 0u) won |= 1u << k;
+        if (!((s[k] & 3) == ST_CAND || claimed)) a[k] = make_uint2(0xffffffffu, 0u);
     }
     // phase 3: queue (atomicMax on the epoch; the thread that raises it owns the push)
     unsigned prev[NS], target[NS];
@@ -889,7 +924,7 @@ template <int NDIM>
 __device__ __forceinline__ void process_candidate(i64 e, const double* __restrict__ u, double* T,
                                                   u8* mask, i64* list, i64 cap, const FmmGeom& g,
                                                   double band, const Sched& sc, unsigned gen_tag,
-                                                  i64* hist) {
+                                                  i64* hist, long long* clk = nullptr) {
     int coord[3];
     const i64 l = decode(e, g, coord);
     const double old = __ldcg(T + l);
@@ -898,16 +933,30 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     unsigned level;
     const double nw = replay<NDIM>(l, coord, u, T, mask, g, band, reach, level);
     const bool changed = __double_as_longlong(old) != __double_as_longlong(nw);
+#ifdef FMM_PHASE_CLOCKS
+    if (clk) clk[0] = clock64() + (changed ? 0 : 0);
+#endif
     // depth: visible to the neighbours' replays through the state byte, and kept (tagged with
     // this rebuild) as the hint for the next rebuild
     mask[l] = (u8)((level << 2) | ST_CAND);
-    if (lvl != (gen_tag | level)) {
+    // the hint is the SWEEP the voxel should be evaluated at next time: its depth, plus
+    // (-DFMM_HINT_SLACK_SHIFT=n) depth >> n sweeps of slack that absorb small shifts of the
+    // dependency structure upstream instead of cascading them into re-evaluations downstream
+#ifdef FMM_HINT_SLACK_SHIFT
+    const unsigned hint = level + (level >> FMM_HINT_SLACK_SHIFT);
+#else
+    const unsigned hint = level;
+#endif
+    if (lvl != (gen_tag | hint)) {
         if ((lvl & 0xff00u) == gen_tag) warp_agg_add(hist, lvl & 0xffu, -1);
-        warp_agg_add(hist, level, 1);
-        lvl = gen_tag | level;
+        warp_agg_add(hist, hint, 1);
+        lvl = gen_tag | hint;
     }
     // reach and hint share a 32-bit word that only this voxel's evaluator writes
     reinterpret_cast<unsigned*>(sc.aux + l)[1] = (unsigned)reach_up16(reach) | (lvl << 16);
+#ifdef FMM_PHASE_CLOCKS
+    if (clk) clk[1] = clock64();
+#endif
     if (!changed) return;
     __stcg(T + l, nw);
     // a voxel whose value enters the band exposes its direct neighbours
@@ -953,6 +1002,8 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     i64 begin = ctr->resume_begin, end = begin + vtail[rix % 3u];   // queued by seed / requeue
     bool scan = vovf[2] != 0;          // ... which report overflow into slot 2
     i64 nreplay = 0;
+    i64 nbk_pre = 0;
+    bool pre = false;
     // Every CTA must have taken its snapshot of the start state before any CTA mutates it: a
     // small first work set sends CTA 0 straight into its single-CTA sweeps, which zero
     // tail3[rix % 3] from their second sweep on -- a CTA scheduled a few microseconds late
@@ -962,7 +1013,12 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     // last_bucket only grows and is compared while nothing is being processed).
     grid.sync();
     while (barriers < FMM_MAX_SWEEPS && sweep < FMM_SWEEP_LIMIT) {
-        i64 nbk = (hints && sweep < 256u) ? vfill[sweep] : 0;       // bucket of this sweep
+#ifdef FMM_PHASE_CLOCKS
+        const long long loop_top = clock64();
+#endif
+        // bucket of this sweep (already fetched with the ring window after the last barrier)
+        i64 nbk = pre ? nbk_pre : ((hints && sweep < 256u) ? vfill[sweep] : 0);
+        pre = false;
         if (end == begin && nbk == 0 && !scan) {
             if (!hints || (i64)sweep >= *vlast) { converged = true; break; }
             ++sweep;                    // nothing queued for this sweep, something parked later
@@ -1039,26 +1095,61 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             const i64 pbase = nbk ? ctr->offs[sweep] : 0;
             // The work set is dealt to the warps in CHUNKS of G consecutive entries (entries
             // pushed together belong to neighbouring voxels: similar stencils, similar replay
-            // paths, overlapping cache lines), chunk c to warp c % nwarps; G is the largest power
-            // of two that still gives every warp work (G = 1: a small set is spread one entry
-            // per warp -- a lone lane runs its own path, not the union of 32 divergent ones;
-            // G = 32: a large one fills whole warps with consecutive entries).
+            // paths, overlapping cache lines), chunk c to warp c % nwarps; G is the smallest power
+            // of two with which no warp gets a second, unrelated chunk (G = 1: a small set is
+            // spread one entry per warp -- a lone lane runs its own path, not the union of 32
+            // divergent ones; G = 32: a large one fills whole warps with consecutive entries).
+            // Measured against "largest G that still gives every warp work" (-DFMM_CHUNK_FLOOR):
+            // 1191 vs 1234 us per 256^3 rebuild, equal on 2048-crop batches.
             // -DFMM_CHUNK=n fixes G (probes, tools/r2_fmm_variants.sh).
             int G = 1;
 #ifdef FMM_CHUNK
             G = FMM_CHUNK;
+#elif defined(FMM_CHUNK_FLOOR)
+            while (G < 32 && (i64)(2 * G) * nwarps <= work) G <<= 1;   // every warp gets work
 #else
-            while (G < 32 && (i64)(2 * G) * nwarps <= work) G <<= 1;
+            while (G < 32 && (i64)G * nwarps < work) G <<= 1;          // at most one chunk per warp
 #endif
             const int per_warp = 32 / G;             // chunks a warp holds per pass
+#ifdef FMM_PHASE_CLOCKS
+            const bool sampled = tid == 32 && work > 32 && work <= nwarps;
+            long long ck[6] = {0, 0, 0, 0, 0, 0};
+#endif
             for (i64 round = lane / G;; round += per_warp) {
                 const i64 k = (round * nwarps + gwarp) * G + (lane & (G - 1));
                 if (k >= work) break;
                 const i64 ent = k < end - begin ? ring.slots[(begin + k) & (ring.cap - 1)]
                                                 : park[pbase + k - (end - begin)];
+#ifdef FMM_PHASE_CLOCKS
+                if (sampled) {
+                    ck[0] = clock64() + (ent & 0);   // (after the entry has arrived)
+                    process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur, ck + 1);
+                    ck[3] = clock64();
+                } else
+#endif
                 process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
                 ++nreplay;
             }
+#ifdef FMM_PHASE_CLOCKS
+            if (sampled) {
+                __threadfence();
+                ck[4] = clock64();
+                grid.sync();
+                ck[5] = clock64();
+                ctr->phase[0] += ck[0] - loop_top;
+                ctr->phase[1] += ck[1] - ck[0];
+                ctr->phase[2] += ck[2] - ck[1];
+                ctr->phase[3] += ck[3] - ck[2];
+                ctr->phase[4] += ck[4] - ck[3];
+                ctr->phase[5] += ck[5] - ck[4];
+                ctr->phase[7] += 1;
+                begin = end;
+                end = begin + vtail[(rix + 1u) % 3u];
+                scan = vovf[slot] != 0;
+                ++sweep; ++rix; ++barriers;
+                continue;
+            }
+#endif
         } else {
             // ---- fallback: scan the candidate list; a warp collects its queued entries in
             // shared memory and evaluates them 32 at a time
@@ -1093,13 +1184,26 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             }
             __syncwarp();
         }
+        // (grid.sync() alone -- CTA barrier + atom.add.release.gpu by one thread per CTA + acquire
+        // polling, cooperative_groups/details/sync.h -- orders the sweep's writes as well and the
+        // suite passes without the explicit fence; measured, dropping it saves nothing:
+        // -DFMM_NO_EXTRA_FENCE 1100 / 1253 us vs 1096 / 1252 us per rebuild.  It stays.)
+#ifndef FMM_NO_EXTRA_FENCE
         __threadfence();
+#endif
         grid.sync();
         // ring entries behind `end` are complete unless this sweep overflowed, in which case the
-        // next sweep scans instead
-        begin = end;
-        end = begin + vtail[(rix + 1u) % 3u];
-        scan = vovf[slot] != 0;
+        // next sweep scans instead.  The three words the next sweep's header needs are fetched
+        // together: one L2 round trip.
+        {
+            const i64 queued = vtail[(rix + 1u) % 3u];
+            const i64 dropped = vovf[slot];
+            nbk_pre = (hints && sweep + 1u < 256u) ? vfill[sweep + 1u] : 0;   // final since the barrier
+            pre = true;
+            begin = end;
+            end = begin + queued;
+            scan = dropped != 0;
+        }
         ++sweep;
         ++rix;
         ++barriers;
@@ -1478,5 +1582,6 @@ i64 fmm_counters_offset(i64 total) {
            2 * ring_capacity(total) * (i64)sizeof(i64);
 }
 i64 fmm_counters_stamps_offset() { return (i64)offsetof(FmmCounters, stamps); }
+i64 fmm_counters_phase_offset() { return (i64)offsetof(FmmCounters, phase); }
 
 }  // namespace lsml

@@ -121,6 +121,7 @@ int fmm_slab_finish(const Geom& g, int own_lo, int own_hi, double band, u8* mask
 int fmm_counters_ptr(i64 total, void* workspace, const i64** out);
 i64 fmm_counters_sizes_offset();
 i64 fmm_counters_stamps_offset();
+i64 fmm_counters_phase_offset();
 i64 fmm_counters_failed_offset();
 i64 fmm_counters_offset(i64 total);
 

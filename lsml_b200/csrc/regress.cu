@@ -299,7 +299,6 @@ struct RankedView {
 };
 
 constexpr int RK_THREADS = 512;
-constexpr int RK_CTAS_PER_SM = 2;
 constexpr int RK_MAX_GROUP = 128;          // trees per staged group
 constexpr int RK_SMEM_PER_CTA = 112 * 1024;
 
@@ -328,8 +327,8 @@ __device__ __forceinline__ unsigned mad32(unsigned a, unsigned b, unsigned c) {
     return d;
 }
 
-template <int V>
-__global__ void __launch_bounds__(RK_THREADS, RK_CTAS_PER_SM)
+template <int V, int CTAS>
+__global__ void __launch_bounds__(RK_THREADS, CTAS)
 forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, RankedView rv,
                      double* __restrict__ out, int cap_words) {
     extern __shared__ __align__(16) unsigned rk_smem[];
@@ -343,9 +342,15 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
     const unsigned fmask4 = ((1u << rv.fbits) - 1u) << 2;
     const unsigned rmask = ((1u << rv.rbits) - 1u) << rshift;
     const int oshift = rshift + rv.rbits;
+    // 32-bit shared addresses: this thread's column of the rank table, the tree buffer
+    const unsigned my_sa = (unsigned)__cvta_generic_to_shared(ranks + threadIdx.x);
+    const unsigned trees_sa = (unsigned)__cvta_generic_to_shared(trees);
     const i64 nb = *n_band;
     const i64 nchunks = (nb + N - 1) / N;
     for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        // ---- features -> ranks: one binary search per feature in the threshold tables (global
+        // memory, L2-resident; staging them through the tree buffer first was measured and is
+        // no faster: the searches of one CTA overlap with the other CTA's walks)
         __syncthreads();                             // the previous chunk's walks are done
         unsigned valid = 0u;
 #pragma unroll
@@ -366,9 +371,6 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
         double acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0.0;
-        // 32-bit shared addresses: this thread's column of the rank table, the tree buffer
-        const unsigned my_sa = (unsigned)__cvta_generic_to_shared(ranks + threadIdx.x);
-        const unsigned trees_sa = (unsigned)__cvta_generic_to_shared(trees);
         int t0 = 0;
         while (t0 < rv.n_trees) {
             // group [t0, t1): as many whole trees as the buffer holds
@@ -377,7 +379,7 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
             while (t1 < rv.n_trees && t1 - t0 < RK_MAX_GROUP &&
                    __ldg(rv.tree_start + t1 + 1) - gbase <= cap_words) ++t1;
             const int gwords = __ldg(rv.tree_start + t1) - gbase;
-            __syncthreads();                         // the previous group's walks are done
+            __syncthreads();                         // the previous group's walks / the ranks are done
             {
                 const uint4* gsrc = reinterpret_cast<const uint4*>(rv.words + gbase);
                 uint4* gdst = reinterpret_cast<uint4*>(trees);
@@ -389,27 +391,51 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
             }
             __syncthreads();
             for (int t = 0; t < t1 - t0; ++t) {
-                unsigned ia[V];                      // shared address of the chain's node
-                unsigned live = s_rootleaf[t] ? 0u : valid;
-#pragma unroll
-                for (int v = 0; v < V; ++v) ia[v] = trees_sa + (unsigned)s_base[t];
-                while (live) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        if (V > 1 && !((live >> v) & 1u)) continue;
-                        const unsigned n = lds32(ia[v]);
+                const unsigned root = trees_sa + (unsigned)s_base[t];
+                if (V == 1) {
+                    unsigned ia = root;              // shared address of the chain's node
+                    bool live = (valid & 1u) && !s_rootleaf[t];
+                    while (live) {
+                        const unsigned n = lds32(ia);
                         // row `feature` of the rank table: (feature * 4) * N bytes
-                        const unsigned w = lds32(mad32(n & fmask4, N, my_sa + v * RK_THREADS * 4));
+                        const unsigned w = lds32(mad32(n & fmask4, N, my_sa));
                         const bool right = w > (n & rmask);
-                        unsigned nx = ia[v] + 4u;                      // left child: next word
-                        if (right) nx = ia[v] + ((n >> oshift) << 2);
-                        ia[v] = nx;
-                        if (n & (right ? 2u : 1u)) live &= ~(1u << v);
+                        unsigned nx = ia + 4u;                         // left child: next word
+                        if (right) nx = ia + ((n >> oshift) << 2);
+                        ia = nx;
+                        live = !(n & (right ? 2u : 1u));
                     }
-                }
+                    // (a dead slot reads two node words as a value that is never stored)
+                    acc[0] += __hiloint2double((int)lds32(ia + 4u), (int)lds32(ia));
+                } else {
+                    // V independent chains per thread, walked in lockstep without branches so
+                    // that their shared-memory round trips overlap; a finished chain stays on
+                    // its last internal node (re-reading it is harmless) and remembers its leaf
+                    unsigned ia[V], leaf[V];
+                    unsigned live = s_rootleaf[t] ? 0u : valid;
 #pragma unroll
-                for (int v = 0; v < V; ++v)          // (a dead slot reads two node words: harmless)
-                    acc[v] += __hiloint2double((int)lds32(ia[v] + 4u), (int)lds32(ia[v]));
+                    for (int v = 0; v < V; ++v) { ia[v] = root; leaf[v] = root; }
+                    while (live) {
+                        unsigned n[V], w[V];
+#pragma unroll
+                        for (int v = 0; v < V; ++v) n[v] = lds32(ia[v]);
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            w[v] = lds32(mad32(n[v] & fmask4, N, my_sa + v * RK_THREADS * 4));
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            const bool right = w[v] > (n[v] & rmask);
+                            const unsigned nx = right ? ia[v] + ((n[v] >> oshift) << 2) : ia[v] + 4u;
+                            const bool on = (live >> v) & 1u;
+                            const bool ends = (n[v] & (right ? 2u : 1u)) != 0u;
+                            if (on && ends) { leaf[v] = nx; live &= ~(1u << v); }
+                            if (on && !ends) ia[v] = nx;
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        acc[v] += __hiloint2double((int)lds32(leaf[v] + 4u), (int)lds32(leaf[v]));
+                }
             }
             t0 = t1;
         }
@@ -563,30 +589,29 @@ static int forest_launch(const FeatSrc& src, const i64* n_band, const double* me
     return 0;
 }
 
-template <int V>
+template <int V, int CTAS>
 static int ranked_launch_v(const FeatSrc& src, const i64* n_band, const Scaler& sc,
-                           const RankedView& rv, double* out, size_t smem, int ctas_per_sm,
-                           cudaStream_t s) {
+                           const RankedView& rv, double* out, size_t smem, cudaStream_t s) {
     static size_t configured = 0;
     if (smem > configured) {
-        LSML_CUDA(cudaFuncSetAttribute(forest_ranked_kernel<V>,
+        LSML_CUDA(cudaFuncSetAttribute(forest_ranked_kernel<V, CTAS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const size_t rank_bytes = (size_t)src.F * V * RK_THREADS * sizeof(unsigned);
     const int cap_words = (int)((smem - rank_bytes) / sizeof(unsigned)) & ~3;
-    forest_ranked_kernel<V><<<LSML_SMS * ctas_per_sm, RK_THREADS, smem, s>>>(src, n_band, sc, rv,
-                                                                              out, cap_words);
+    forest_ranked_kernel<V, CTAS><<<LSML_SMS * CTAS, RK_THREADS, smem, s>>>(src, n_band, sc, rv, out,
+                                                                           cap_words);
     LSML_LAUNCH_CHECK("forest_ranked_kernel");
     return 0;
 }
 
-// voxels per thread (LSML_FOREST_RK_V = 1 | 2 overrides the default of 1: probes)
-static int ranked_v_override() {
+// probes: LSML_FOREST_RK = "<voxels per thread><CTAs per SM>", e.g. 12 (the default), 22, 13
+static int ranked_override() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("LSML_FOREST_RK_V");
-        v = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+        const char* e = getenv("LSML_FOREST_RK");
+        v = (e && e[0] >= '1' && e[0] <= '2' && e[1] >= '1' && e[1] <= '3') ? (e[0] - '0') * 10 + (e[1] - '0') : 0;
     }
     return v;
 }
@@ -608,13 +633,16 @@ static int ranked_launch(const FeatSrc& src, const i64* n_band, const double* me
                         a.n_trees, a.fbits, a.rbits, a.divisor};
     const size_t tree_bytes = (size_t)a.max_tree_words * sizeof(unsigned);
     const size_t want_trees = tree_bytes > 32 * 1024 ? tree_bytes : 32 * 1024;
-    const size_t two = RK_SMEM_PER_CTA - 1024, one = 224 * 1024;      // per CTA: 2 / 1 per SM
+    // shared memory per CTA with 3 / 2 / 1 CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
+    const size_t three = 74 * 1024, two = RK_SMEM_PER_CTA - 1024, one = 224 * 1024;
     const size_t rank1 = (size_t)src.F * RK_THREADS * sizeof(unsigned);
-    const int vo = ranked_v_override();
-    if (vo == 2 && 2 * rank1 + want_trees <= two)
-        return ranked_launch_v<2>(src, n_band, sc, rv, out, two, 2, s);
-    if (rank1 + want_trees <= two) return ranked_launch_v<1>(src, n_band, sc, rv, out, two, 2, s);
-    if (rank1 + tree_bytes <= one) return ranked_launch_v<1>(src, n_band, sc, rv, out, one, 1, s);
+    const int ov = ranked_override();
+    if (ov == 13 && rank1 + want_trees <= three) return ranked_launch_v<1, 3>(src, n_band, sc, rv, out, three, s);
+    if (ov == 23 && 2 * rank1 + want_trees <= three) return ranked_launch_v<2, 3>(src, n_band, sc, rv, out, three, s);
+    if (ov == 22 && 2 * rank1 + want_trees <= two) return ranked_launch_v<2, 2>(src, n_band, sc, rv, out, two, s);
+    if (ov == 21 && 2 * rank1 + tree_bytes <= one) return ranked_launch_v<2, 1>(src, n_band, sc, rv, out, one, s);
+    if (rank1 + want_trees <= two) return ranked_launch_v<1, 2>(src, n_band, sc, rv, out, two, s);
+    if (rank1 + tree_bytes <= one) return ranked_launch_v<1, 1>(src, n_band, sc, rv, out, one, s);
     set_error("ranked forest: %d features and trees of %d words do not fit shared memory",
               src.F, a.max_tree_words);
     return 1;

@@ -35,7 +35,9 @@ def sched_lib(tmp_path_factory):
     cpp, so = str(out / "fmm_sched_host.cpp"), str(out / "fmm_sched_host.so")
     with open(cpp, "w") as f:
         f.write(text)
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused",
+    # LSML_HOST_SCHED_DEFS: extra -D switches of fmm.cu's build variants (tools/r2_fmm_variants.sh)
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-unused"] +
+                          os.environ.get("LSML_HOST_SCHED_DEFS", "").split() + [
                            "-shared", "-fPIC", "-I", os.path.join(HERE, "native"), cpp, "-o", so])
     lib = ctypes.CDLL(so)
     lib.hs_create.restype = ctypes.c_void_p

@@ -39,3 +39,12 @@ for rep in range(2):
 ss = eng.fmm_sweep_sizes()
 print("sweep sizes:", ss[:32])
 print("sweep us   :", [round((ss[32+i+1]-ss[32+i])/1e3,1) for i in range(31) if ss[32+i+1] > 0])
+from lsml_b200 import _lib
+_lib.lib.lsml_fmm_phase_offset.restype = _lib.c_i64
+_lib.lib.lsml_fmm_counters_offset.restype = _lib.c_i64
+off = int(_lib.lib.lsml_fmm_counters_offset(_lib.c_i64(eng.total))) + int(_lib.lib.lsml_fmm_phase_offset())
+ph = eng._ws_fmm.view(torch.uint8)[off:off + 64].view(torch.int64).cpu().numpy()
+if ph[7] > 0:   # -DFMM_PHASE_CLOCKS build: cycles per phase of a single-lane grid-wide sweep
+    names = ["top->entry", "replay", "record", "publish", "fence", "barrier"]
+    print("phase cycles per sampled sweep (%d sweeps):" % ph[7],
+          {n: round(float(ph[i]) / ph[7]) for i, n in enumerate(names)})

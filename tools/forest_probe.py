@@ -36,6 +36,22 @@ for _ in range(10):
     ts.append(a.elapsed_time(b) * 1e3)
 got = eng.vel[:nb].cpu().numpy()
 want = host.predict(X)
+if os.environ.get("LSML_FOREST_DEPTHS"):
+    # how deep the walks are: mean leaf depth, and the mean over warps (32 consecutive band
+    # voxels) of the deepest lane -- what a lock-step warp pays per tree
+    forest = host.steps[-1][1]
+    Xs = host.steps[0][1].transform(X).astype(np.float32)
+    tot = mx = 0.0
+    for est in forest.estimators_[:20]:
+        t = est.tree_
+        depth = np.zeros(t.node_count, dtype=np.int64)
+        for i in range(t.node_count):
+            if t.children_left[i] != -1:
+                depth[t.children_left[i]] = depth[t.children_right[i]] = depth[i] + 1
+        d = depth[t.apply(Xs)]
+        tot += d.mean()
+        mx += d[:len(d) // 32 * 32].reshape(-1, 32).max(axis=1).mean()
+    print("leaf depth: mean %.2f, mean of the per-warp maximum %.2f (20 trees)" % (tot / 20, mx / 20))
 print("variant %-8s band %d trees %d max_nodes %d: %.1f us (median of 10), equal to sklearn: %s"
-      % (os.environ.get("LSML_FOREST_VARIANT", "default"), nb, reg.n_trees, reg.max_nodes,
+      % (os.environ.get("LSML_FOREST_VARIANT", "default") + os.environ.get("LSML_FOREST_RK", ""), nb, reg.n_trees, reg.max_nodes,
          float(np.median(ts)), bool(np.array_equal(got, want))))
