@@ -222,8 +222,8 @@ int lsml_mlp_predict_band(const lsml_band_source *src, const long long *n_band, 
 /* A forest in the RANK-QUANTISED layout (lsml_b200/core/regressors.py: pack_ranked; regress.cu:
  * forest_ranked_kernel): per feature f the sorted distinct float32 thresholds S_f of the forest
  * (thr_tab = S_0 | S_1 | ..., thr_off = int[nfeat + 1]); trees in preorder, an internal node one
- * 32-bit word  bit 0 / 1: left / right child is a leaf | feature << 2 | j << (2 + fbits) |
- * (offset of the right child in words) << (2 + fbits + rbits)  with threshold S_f[j], the left
+ * 32-bit word, fields from the top  feature (fbits) | j (rbits) | offset of the right child in
+ * words | bit 1 / bit 0: the right / left child is a leaf  with threshold S_f[j], the left
  * child in the next word, a leaf as its float64 value in two words; tree_start = int[n_trees + 1]
  * word offsets (multiples of 4; words 16-byte aligned); max_tree_words = the largest tree.  Same
  * decisions, same leaves, same float64 sum in tree order as lsml_forest_predict -- i.e. as

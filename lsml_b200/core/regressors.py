@@ -203,11 +203,15 @@ def pack_ranked(nodes, bases, root_is_leaf, n_features):
     the forest uses on feature ``f`` and ``rank_f(x) = #{s in S_f : s < x}``, that is
     ``rank_f(x) <= j`` for the node whose threshold is ``S_f[j]`` -- exactly, for every float32
     ``x`` (NaN ranks above everything: ``!(x <= thr)`` sends it right, as the other kernels do).
-    A voxel's features are therefore reduced ONCE to 16-bit ranks, and an internal node shrinks
-    to one 32-bit word::
+    A voxel's features are therefore reduced ONCE to ranks, and an internal node shrinks to one
+    32-bit word, fields from the top::
 
-        bit 0 / 1: the left / right child is a leaf | feature << 2 | j << (2 + fbits) |
-        (offset of the right child in words) << (2 + fbits + rbits)
+        feature (fbits) | rank j (rbits) | offset of the right child in words | bit 1: the right
+        child is a leaf | bit 0: the left child is a leaf
+
+    so that, with the voxel's rank stored as ``feature << (32 - fbits) | rank << (32 - fbits -
+    rbits)``, "go right" is ONE unsigned comparison of two words (the fields below the rank
+    cannot flip it), and ``word & offset mask`` IS the byte offset of the right child.
 
     Trees are laid out in preorder: the left child is the next word, a leaf is its float64
     value in two words.  Returns a dict: ``words`` uint32, ``tree_start`` int32[T+1] (word
@@ -267,13 +271,13 @@ def pack_ranked(nodes, bases, root_is_leaf, n_features):
     off = np.where(internal, 1 + size[np.where(internal, left, 0)], 0)
     bits = lambda v: max(1, int(v).bit_length())
     fbits = bits(n_features - 1)
-    rbits = bits(max(1, max(s.size for s in tabs) - 1))
+    rbits = bits(max(s.size for s in tabs))       # a voxel's rank goes up to |S_f| inclusive
     if fbits + rbits + bits(off.max()) > 30:
         return None
     words = np.zeros(int(tree_start[-1]), dtype=np.uint32)
     ii = np.flatnonzero(internal)
-    words[pos[ii]] = (lleaf[ii] | (rleaf[ii] << 1) | (feat[ii] << 2) | (rank[ii] << (2 + fbits)) |
-                      (off[ii] << (2 + fbits + rbits))).astype(np.uint32)
+    words[pos[ii]] = (lleaf[ii] | (rleaf[ii] << 1) | (off[ii] << 2) |
+                      (rank[ii] << (32 - fbits - rbits)) | (feat[ii] << (32 - fbits))).astype(np.uint32)
     li = np.flatnonzero(is_leaf)
     words[pos[li]] = nodes[li, 0]
     words[pos[li] + 1] = nodes[li, 1]

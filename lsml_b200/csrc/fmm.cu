@@ -942,8 +942,13 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     // the hint is the SWEEP the voxel should be evaluated at next time: its depth, plus
     // (-DFMM_HINT_SLACK_SHIFT=n) depth >> n sweeps of slack that absorb small shifts of the
     // dependency structure upstream instead of cascading them into re-evaluations downstream
-#ifdef FMM_HINT_SLACK_SHIFT
+#if defined(FMM_HINT_SLACK_SHIFT)
     const unsigned hint = level + (level >> FMM_HINT_SLACK_SHIFT);
+#elif defined(FMM_HINT_EARLY)
+    // ... or FMM_HINT_EARLY sweeps BEFORE its depth: a voxel whose depth shrank since the last
+    // rebuild is then still on time (a late evaluation delays everything downstream of it and
+    // adds sweeps; an early one only costs a replay)
+    const unsigned hint = level > FMM_HINT_EARLY ? level - FMM_HINT_EARLY : 1u;
 #else
     const unsigned hint = level;
 #endif

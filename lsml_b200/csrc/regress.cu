@@ -278,16 +278,23 @@ forest_staged_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Sta
 // A tree only asks `x[f] <= thr`; with S_f the sorted distinct float32 thresholds of feature f
 // and rank_f(x) = #{s in S_f : s < x}, that is `rank_f(x) <= j` for the node holding S_f[j].  A
 // voxel's features are reduced ONCE to ranks (one binary search per feature), an internal node
-// is ONE 32-bit word
-//     bit 0 / 1: the left / right child is a leaf | feature << 2 | rank << (2 + fbits) |
-//     (offset of the right child in words) << (2 + fbits + rbits)
+// is ONE 32-bit word, fields from the top
+//     feature (fbits) | rank j (rbits) | offset of the right child in words | bit 1 / bit 0: the
+//     right / left child is a leaf
 // trees are stored in preorder (left child = next word, a leaf = its float64 value in two
 // words), and the whole forest is ~3.7 KB per 300-leaf tree: a CTA stages GROUPS of ~20 trees in
 // shared memory and walks them for its 512 (x V) voxels, the float64 sum keeping sklearn's tree
 // order.  A node visit is two shared-memory loads -- the node (divergent: ~3-4 bank-conflict
 // wavefronts per warp instead of up to 32 L1 tag lookups of a 32-byte global node) and the
-// voxel's rank of that feature ([feature][voxel] layout: conflict-free) -- and ~13 instructions;
-// the ranks are stored pre-shifted so that the comparison needs no field extraction.
+// voxel's rank of that feature ([feature][voxel] layout: conflict-free).  The voxel's rank is
+// stored as `feature << (32 - fbits) | rank << (32 - fbits - rbits)`: "go right" is then ONE
+// unsigned comparison of that word with the node word (same top field, the fields below the rank
+// cannot flip the result), and `node & offset mask` is the byte offset of the right child.
+// ncu of the first version (profiles/r2b_ncu_forest_ranked.txt): neither shared-memory
+// wavefronts (42 %) nor issue slots (64 %) bound the walk but the INTEGER ALU pipe (half rate:
+// LOP3 / SHF / SEL / ISETP cost two cycles per warp; 8 of the 13 instructions per level), which is
+// why doubling the resident warps changed nothing.  The walk below spends 4-5 ALU-pipe and 3-4
+// FMA-pipe (IMAD / IMAD.HI) instructions per level instead.
 struct RankedView {
     const unsigned* words;
     const int* tree_start;     // [n_trees + 1], word offsets (multiples of 4)
@@ -327,24 +334,56 @@ __device__ __forceinline__ unsigned mad32(unsigned a, unsigned b, unsigned c) {
     return d;
 }
 
-template <int V, int CTAS>
-__global__ void __launch_bounds__(RK_THREADS, CTAS)
+// ---- bulk (TMA) copy of a tree group: one thread issues it, everybody waits on the mbarrier ----
+__device__ __forceinline__ void rk_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rk_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rk_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RK_DONE;\n"
+        "bra RK_WAIT;\n"
+        "RK_DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rk_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int V, int CTAS, int THREADS>
+__global__ void __launch_bounds__(THREADS, CTAS)
 forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, RankedView rv,
                      double* __restrict__ out, int cap_words) {
     extern __shared__ __align__(16) unsigned rk_smem[];
     __shared__ int s_base[RK_MAX_GROUP];
     __shared__ u8 s_rootleaf[RK_MAX_GROUP];
-    constexpr int N = V * RK_THREADS;
+    __shared__ int s_t1;
+    __shared__ __align__(8) unsigned long long s_bar;
+    constexpr int N = V * THREADS;
     const int F = src.F;
-    unsigned* const ranks = rk_smem;                 // [F][N], rank << (2 + fbits)
+    unsigned* const ranks = rk_smem;                 // [F][N], feature | rank (node word fields)
     unsigned* const trees = rk_smem + (size_t)F * N; // [cap_words]
-    const int rshift = 2 + rv.fbits;
-    const unsigned fmask4 = ((1u << rv.fbits) - 1u) << 2;
-    const unsigned rmask = ((1u << rv.rbits) - 1u) << rshift;
-    const int oshift = rshift + rv.rbits;
+    const int fshift = 32 - rv.fbits;                // feature field: top fbits bits
+    const int rshift = fshift - rv.rbits;            // rank field below it
+    const unsigned fmul = 1u << rv.fbits;            // umulhi(word, fmul) = feature
+    const unsigned omask4 = (1u << rshift) - 4u;     // word offset field << 2 = byte offset
     // 32-bit shared addresses: this thread's column of the rank table, the tree buffer
     const unsigned my_sa = (unsigned)__cvta_generic_to_shared(ranks + threadIdx.x);
     const unsigned trees_sa = (unsigned)__cvta_generic_to_shared(trees);
+    const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(&s_bar);
+    unsigned parity = 0u;
+    if (threadIdx.x == 0) {
+        rk_mbar_init(bar_sa, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const i64 nb = *n_band;
     const i64 nchunks = (nb + N - 1) / N;
     for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -355,7 +394,7 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
         unsigned valid = 0u;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const int slot = v * RK_THREADS + threadIdx.x;
+            const int slot = v * THREADS + threadIdx.x;
             const i64 b = chunk * N + slot;
             if (b < nb) {
                 valid |= 1u << v;
@@ -364,7 +403,7 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
                     const float x = __double2float_rn(scaled(src, b, vr, f, sc));
                     const unsigned r = rank_of(rv.thr_tab, __ldg(rv.thr_off + f),
                                                __ldg(rv.thr_off + f + 1), x);
-                    ranks[f * N + slot] = r << rshift;
+                    ranks[f * N + slot] = ((unsigned)f << fshift) | (r << rshift);
                 }
             }
         }
@@ -373,23 +412,38 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
         for (int v = 0; v < V; ++v) acc[v] = 0.0;
         int t0 = 0;
         while (t0 < rv.n_trees) {
-            // group [t0, t1): as many whole trees as the buffer holds
+            // group [t0, t1): as many whole trees as the buffer holds (warp 0 looks 32 trees
+            // ahead per step; tree_start is increasing, so the fitting trees are a prefix)
             const int gbase = __ldg(rv.tree_start + t0);
-            int t1 = t0 + 1;
-            while (t1 < rv.n_trees && t1 - t0 < RK_MAX_GROUP &&
-                   __ldg(rv.tree_start + t1 + 1) - gbase <= cap_words) ++t1;
-            const int gwords = __ldg(rv.tree_start + t1) - gbase;
-            __syncthreads();                         // the previous group's walks / the ranks are done
-            {
-                const uint4* gsrc = reinterpret_cast<const uint4*>(rv.words + gbase);
-                uint4* gdst = reinterpret_cast<uint4*>(trees);
-                for (int i = threadIdx.x; i < (gwords >> 2); i += RK_THREADS) gdst[i] = __ldg(gsrc + i);
-                for (int t = t0 + threadIdx.x; t < t1; t += RK_THREADS) {
-                    s_base[t - t0] = (__ldg(rv.tree_start + t) - gbase) * 4;      // bytes
-                    s_rootleaf[t - t0] = __ldg(rv.root_is_leaf + t);
+            if (threadIdx.x < 32) {
+                int t1w = t0 + 1;
+                for (;;) {
+                    const int t = t1w + (int)threadIdx.x;
+                    const bool ok = t < rv.n_trees && t - t0 < RK_MAX_GROUP &&
+                                    __ldg(rv.tree_start + t + 1) - gbase <= cap_words;
+                    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                    if (bal != 0xffffffffu) { t1w += __ffs((int)~bal) - 1; break; }
+                    t1w += 32;
                 }
+                if (threadIdx.x == 0) s_t1 = t1w;
             }
-            __syncthreads();
+            __syncthreads();                         // the previous group's walks / the ranks are done
+            const int t1 = s_t1;
+            const int gwords = __ldg(rv.tree_start + t1) - gbase;
+            if (threadIdx.x == 0) {
+                // the buffer was read through the generic proxy until the barrier above; the bulk
+                // copy writes it through the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                rk_mbar_expect_tx(bar_sa, (unsigned)gwords * 4u);
+                rk_bulk_g2s(trees_sa, rv.words + gbase, (unsigned)gwords * 4u, bar_sa);
+            }
+            for (int t = t0 + threadIdx.x; t < t1; t += THREADS) {
+                s_base[t - t0] = (__ldg(rv.tree_start + t) - gbase) * 4;          // bytes
+                s_rootleaf[t - t0] = __ldg(rv.root_is_leaf + t);
+            }
+            rk_mbar_wait(bar_sa, parity);            // the group has landed
+            parity ^= 1u;
+            __syncthreads();                         // ... and s_base / s_rootleaf are written
             for (int t = 0; t < t1 - t0; ++t) {
                 const unsigned root = trees_sa + (unsigned)s_base[t];
                 if (V == 1) {
@@ -397,12 +451,10 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
                     bool live = (valid & 1u) && !s_rootleaf[t];
                     while (live) {
                         const unsigned n = lds32(ia);
-                        // row `feature` of the rank table: (feature * 4) * N bytes
-                        const unsigned w = lds32(mad32(n & fmask4, N, my_sa));
-                        const bool right = w > (n & rmask);
-                        unsigned nx = ia + 4u;                         // left child: next word
-                        if (right) nx = ia + ((n >> oshift) << 2);
-                        ia = nx;
+                        // row `feature` of the rank table (N * 4 bytes per row)
+                        const unsigned w = lds32(mad32(__umulhi(n, fmul), N * 4, my_sa));
+                        const bool right = w > n;
+                        if (right) ia += n & omask4; else ia += 4u;    // left child: next word
                         live = !(n & (right ? 2u : 1u));
                     }
                     // (a dead slot reads two node words as a value that is never stored)
@@ -421,11 +473,11 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
                         for (int v = 0; v < V; ++v) n[v] = lds32(ia[v]);
 #pragma unroll
                         for (int v = 0; v < V; ++v)
-                            w[v] = lds32(mad32(n[v] & fmask4, N, my_sa + v * RK_THREADS * 4));
+                            w[v] = lds32(mad32(__umulhi(n[v], fmul), N * 4, my_sa + v * THREADS * 4));
 #pragma unroll
                         for (int v = 0; v < V; ++v) {
-                            const bool right = w[v] > (n[v] & rmask);
-                            const unsigned nx = right ? ia[v] + ((n[v] >> oshift) << 2) : ia[v] + 4u;
+                            const bool right = w[v] > n[v];
+                            const unsigned nx = right ? ia[v] + (n[v] & omask4) : ia[v] + 4u;
                             const bool on = (live >> v) & 1u;
                             const bool ends = (n[v] & (right ? 2u : 1u)) != 0u;
                             if (on && ends) { leaf[v] = nx; live &= ~(1u << v); }
@@ -441,7 +493,7 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const i64 b = chunk * N + v * RK_THREADS + threadIdx.x;
+            const i64 b = chunk * N + v * THREADS + threadIdx.x;
             if (b < nb) out[b] = acc[v] / rv.divisor;
         }
     }
@@ -589,18 +641,18 @@ static int forest_launch(const FeatSrc& src, const i64* n_band, const double* me
     return 0;
 }
 
-template <int V, int CTAS>
+template <int V, int CTAS, int THREADS = RK_THREADS>
 static int ranked_launch_v(const FeatSrc& src, const i64* n_band, const Scaler& sc,
                            const RankedView& rv, double* out, size_t smem, cudaStream_t s) {
     static size_t configured = 0;
     if (smem > configured) {
-        LSML_CUDA(cudaFuncSetAttribute(forest_ranked_kernel<V, CTAS>,
+        LSML_CUDA(cudaFuncSetAttribute(forest_ranked_kernel<V, CTAS, THREADS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const size_t rank_bytes = (size_t)src.F * V * RK_THREADS * sizeof(unsigned);
+    const size_t rank_bytes = (size_t)src.F * V * THREADS * sizeof(unsigned);
     const int cap_words = (int)((smem - rank_bytes) / sizeof(unsigned)) & ~3;
-    forest_ranked_kernel<V, CTAS><<<LSML_SMS * CTAS, RK_THREADS, smem, s>>>(src, n_band, sc, rv, out,
+    forest_ranked_kernel<V, CTAS, THREADS><<<LSML_SMS * CTAS, THREADS, smem, s>>>(src, n_band, sc, rv, out,
                                                                            cap_words);
     LSML_LAUNCH_CHECK("forest_ranked_kernel");
     return 0;
@@ -612,6 +664,7 @@ static int ranked_override() {
     if (v < 0) {
         const char* e = getenv("LSML_FOREST_RK");
         v = (e && e[0] >= '1' && e[0] <= '2' && e[1] >= '1' && e[1] <= '3') ? (e[0] - '0') * 10 + (e[1] - '0') : 0;
+        if (e && e[0] == 't') v = 100 + (e[1] - '0');        // t2 / t1: 1024 threads, 2 / 1 CTAs per SM
     }
     return v;
 }
@@ -619,7 +672,7 @@ static int ranked_override() {
 static int ranked_launch(const FeatSrc& src, const i64* n_band, const double* mean,
                          const double* scale, const RankedArgs& a, double* out, cudaStream_t s) {
     if (a.nfeat != src.F) { set_error("ranked forest: exported for %d features, source has %d", a.nfeat, src.F); return 1; }
-    if (a.n_trees < 1 || a.fbits < 1 || a.rbits < 1 || 2 + a.fbits + a.rbits > 31 ||
+    if (a.n_trees < 1 || a.fbits < 1 || a.rbits < 1 || a.fbits + a.rbits > 28 ||
         src.F > (1 << a.fbits) || a.max_tree_words < 2) {
         set_error("ranked forest: bad layout parameters");
         return 1;
@@ -637,10 +690,18 @@ static int ranked_launch(const FeatSrc& src, const i64* n_band, const double* me
     const size_t three = 74 * 1024, two = RK_SMEM_PER_CTA - 1024, one = 224 * 1024;
     const size_t rank1 = (size_t)src.F * RK_THREADS * sizeof(unsigned);
     const int ov = ranked_override();
+    if (ov == 102 && 2 * rank1 + want_trees <= two) return ranked_launch_v<1, 2, 1024>(src, n_band, sc, rv, out, two, s);
+    if (ov == 101 && 2 * rank1 + tree_bytes <= one) return ranked_launch_v<1, 1, 1024>(src, n_band, sc, rv, out, one, s);
     if (ov == 13 && rank1 + want_trees <= three) return ranked_launch_v<1, 3>(src, n_band, sc, rv, out, three, s);
     if (ov == 23 && 2 * rank1 + want_trees <= three) return ranked_launch_v<2, 3>(src, n_band, sc, rv, out, three, s);
     if (ov == 22 && 2 * rank1 + want_trees <= two) return ranked_launch_v<2, 2>(src, n_band, sc, rv, out, two, s);
     if (ov == 21 && 2 * rank1 + tree_bytes <= one) return ranked_launch_v<2, 1>(src, n_band, sc, rv, out, one, s);
+    // default: one CTA of 1024 threads per SM with the whole 224 KB -- the fewest, largest tree
+    // groups (43 trees of the bench's forest at F = 16: 3 groups per chunk instead of 5 with two
+    // 512-thread CTAs; measured 329 vs 344 us on the probe state)
+    const size_t big_trees = tree_bytes > 64 * 1024 ? tree_bytes : 64 * 1024;
+    if (ov == 0 && 2 * rank1 + big_trees <= one)
+        return ranked_launch_v<1, 1, 1024>(src, n_band, sc, rv, out, one, s);
     if (rank1 + want_trees <= two) return ranked_launch_v<1, 2>(src, n_band, sc, rv, out, two, s);
     if (rank1 + tree_bytes <= one) return ranked_launch_v<1, 1>(src, n_band, sc, rv, out, one, s);
     set_error("ranked forest: %d features and trees of %d words do not fit shared memory",

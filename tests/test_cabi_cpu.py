@@ -199,10 +199,12 @@ def _walk_ranked(pk, root_leaf, X32):
             idx, leaf = int(start[t]), bool(root_leaf[t])
             while not leaf:
                 n = int(words[idx])
-                f, j = (n >> 2) & ((1 << fb) - 1), (n >> (2 + fb)) & ((1 << rb) - 1)
-                right = ranks[i, f] > j
+                f = n >> (32 - fb)
+                # the kernel's comparison: the voxel's (feature | rank) word against the node word
+                right = ((f << (32 - fb)) | (int(ranks[i, f]) << (32 - fb - rb))) > n
+                assert right == (ranks[i, f] > ((n >> (32 - fb - rb)) & ((1 << rb) - 1)))
                 leaf = bool(n & (2 if right else 1))
-                idx += (n >> (2 + fb + rb)) if right else 1
+                idx += ((n & ((1 << (32 - fb - rb)) - 4)) >> 2) if right else 1
             out[i] += words[idx:idx + 2].view(np.float64)[0]
     return out
 
@@ -234,7 +236,7 @@ def test_pack_ranked_round_trip():
         pk = pack_ranked(nodes, bases, root, 6)
         assert pk is not None and pk["words"].dtype == np.uint32
         assert (pk["tree_start"] % 4 == 0).all() and pk["tree_start"][-1] == len(pk["words"])
-        assert 2 + pk["fbits"] + pk["rbits"] <= 30
+        assert pk["fbits"] + pk["rbits"] <= 28 and int(np.diff(pk["thr_off"]).max(initial=0)) < (1 << pk["rbits"])
         X32 = Xt.astype(np.float32)
         # values exactly ON thresholds (x <= thr goes left) and just above them
         tab = pk["thr_tab"]
