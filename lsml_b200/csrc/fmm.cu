@@ -825,18 +825,23 @@ __device__ __forceinline__ void publish_change(i64 e, i64 l, const int (&coord)[
         valid |= okk ? 1u << k : 0u;              // (halo copies are neither queued nor claimed)
         s[k] = __ldcg(mask + (okk ? l + j * st[ax] : l));
     }
+    // ... and, in the same round trip, the scheduling records of the stencil
+    uint2 a[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
+        a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + (((valid >> k) & 1u) ? l + j * st[ax] : l)));
+    }
 #pragma unroll
     for (int k = 0; k < NS; ++k)
         if (!((valid >> k) & 1u)) s[k] = 0xff;
-    // phase 2: scheduling records of the candidates; claims of far direct neighbours
-    uint2 a[NS];
+    // phase 2: claims of far direct neighbours (only when x's value has just entered the band)
     unsigned oldw[NS];
     unsigned claims = 0u, won = 0u;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const int ax = 3 - NDIM + k / 4, j = offs[k % 4];
         const i64 n = ((valid >> k) & 1u) ? l + j * st[ax] : l;
-        a[k] = __ldcg(reinterpret_cast<const uint2*>(sc.aux + n));
         oldw[k] = 0xffffffffu;
         if (expose && (j == 1 || j == -1) && s[k] == 0) {        // claim(): state 0 -> candidate
             claims |= 1u << k;
