@@ -493,7 +493,14 @@ def section_c4(ctx, total=C4_TOTAL, chunk=C4_CHUNK, log=None):
                                              % (nb_batch // C4_ITERS),
                    "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                    "algorithmic_bytes_per_launch": 64.0 * nb_batch / C4_ITERS,
-                   "ms": upd_ms / max(1, upd_n), "traffic": None, "peak_source": peak_src}
+                   "ms": upd_ms / max(1, upd_n), "peak_source": peak_src}
+            # DRAM traffic of the pair at this scale: one ncu capture per kernel at iteration ~20 of
+            # a 2048-crop batch (a launch of fewer band voxels than the average: compare the
+            # BYTES PER MICROSECOND, 2.6-2.9 TB/s, not the totals)
+            tu, su = ncu_traffic("c4_band_update_kernel")
+            ta, _ = ncu_traffic("c4_band_apply_kernel")
+            upd["traffic"] = (tu + ta) if (tu is not None and ta is not None) else None
+            upd["traffic_source"] = su
     del eng, raw
     torch.cuda.empty_cache()
     return {"value": tot_units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 1,

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
+#include <mutex>
 #include "lsml_internal.h"
 #include "band_features.cuh"
 #include "../../include/lsml_b200.h"
@@ -47,12 +48,27 @@ namespace {
     abort();
 }
 
-// RAII device buffer for the host-pointer drop-in path
+// Device buffers of the host-pointer drop-in path.  The reference calls these symbols once per
+// evolution iteration on arrays of one size (model.py:390), so the buffers are kept between
+// calls (four slots per device, grown on demand, freed at process exit by the driver): a call
+// costs its copies and its kernel, not four cudaMalloc / cudaFree pairs (~1 ms each at 256^3).
+// One call at a time per process (the mutex): the reference is single-threaded.
 struct DevBuf {
     void* p = nullptr;
-    int alloc(size_t bytes) { return check_cuda(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc"); }
-    ~DevBuf() { if (p) cudaFree(p); }
+    size_t cap = 0;
+    int dev = -1;
+    int alloc(size_t bytes) {
+        int cur = 0;
+        if (check_cuda(cudaGetDevice(&cur), "cudaGetDevice")) return 1;
+        if (p != nullptr && dev == cur && cap >= bytes) return 0;
+        if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
+        if (check_cuda(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) { p = nullptr; return 1; }
+        cap = bytes; dev = cur;
+        return 0;
+    }
 };
+std::mutex g_host_path_mutex;
+DevBuf g_host_buf[4];
 
 // Host-pointer implementation shared by gmag_os{1,2,3}d.  Output buffers are copied IN first
 // so that voxels outside the mask keep whatever the caller had there (the reference only
@@ -62,7 +78,8 @@ int host_gmag_os(int ndim, const int* shape, double* A, bool* mask, double* nu, 
     Geom g;
     if (make_geom(g, ndim, shape, 1, dx)) return 1;
     const size_t n = (size_t)g.voxels, nb = n * sizeof(double);
-    DevBuf dA, dM, dNu, dG;
+    std::lock_guard<std::mutex> lock(g_host_path_mutex);
+    DevBuf &dA = g_host_buf[0], &dM = g_host_buf[1], &dNu = g_host_buf[2], &dG = g_host_buf[3];
     if (dA.alloc(nb) || dM.alloc(n) || dNu.alloc(nb) || dG.alloc(nb)) return 2;
     cudaStream_t s = 0;
     LSML_CUDA(cudaMemcpyAsync(dA.p, A, nb, cudaMemcpyHostToDevice, s));
@@ -82,7 +99,8 @@ int host_gradient_centered(int ndim, const int* shape, double* A, bool* mask, do
     Geom g;
     if (make_geom(g, ndim, shape, 1, dx)) return 1;
     const size_t n = (size_t)g.voxels, nb = n * sizeof(double);
-    DevBuf dA, dM, dD, dG;
+    std::lock_guard<std::mutex> lock(g_host_path_mutex);
+    DevBuf &dA = g_host_buf[0], &dM = g_host_buf[1], &dD = g_host_buf[2], &dG = g_host_buf[3];
     if (dA.alloc(nb) || dM.alloc(n) || dD.alloc(nb * ndim) || dG.alloc(nb)) return 2;
     cudaStream_t s = 0;
     LSML_CUDA(cudaMemcpyAsync(dA.p, A, nb, cudaMemcpyHostToDevice, s));
