@@ -552,6 +552,81 @@ mlp_predict_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, MlpVi
     }
 }
 
+// ------------------------------------------------------------------------- MLP on tensor cores
+// The dense layers as FP64 tensor-core MMAs (`mma.sync.m8n8k4.f64`: DMMA in the SASS).  float64
+// keeps the reference's precision (MLPRegressor.predict is float64; the level sets must agree
+// to 1e-5 after hundreds of iterations), the accumulation is fused multiply-add in k-blocks of
+// four instead of sklearn's BLAS order: same tolerance as the scalar kernel (1e-11 relative).
+// A warp owns a tile of 8 band voxels: its activations live in shared memory as [8][stride]
+// (stride = width rounded up to 16, + 4: the A-fragment reads of a half-warp then hit 16
+// distinct 8-byte banks), ping-pong between layers; per layer and block of 8 outputs the warp
+// runs ceil(nin / 4) MMAs, adds the bias, applies the activation and stores the D fragment as the
+// next layer's input (columns beyond the layer's width are stored as zeros, so the next k-loop can
+// run to a multiple of four).  Weights come through the read-only path as B fragments (a
+// (16 x 100) layer is 12.8 KB: L1-resident).  Fragment layouts (PTX ISA, m8n8k4 .f64): A[row =
+// lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4], C / D[row = lane / 4][col = 2 * (lane
+// % 4) + {0, 1}].
+constexpr int DM_WARPS = 4;
+constexpr int DM_THREADS = DM_WARPS * 32;
+
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(DM_THREADS)
+mlp_dmma_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, MlpView mv, int stride,
+                double* __restrict__ out) {
+    extern __shared__ double dm_act[];   // [warp][2][8][stride]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = lane >> 2, col = lane & 3;
+    double* cur = dm_act + (size_t)warp * 2 * 8 * stride;
+    double* nxt = cur + 8 * stride;
+    const i64 nb = *n_band;
+    const i64 ntiles = (nb + 7) / 8;
+    const int F = mv.sizes[0];
+    for (i64 tile = (i64)blockIdx.x * DM_WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * DM_WARPS) {
+        const i64 b = tile * 8 + row;
+        const bool live = b < nb;
+        // inputs: the four lanes of a voxel's row gather its features k = col, col + 4, ...;
+        // the row is zero-padded to a multiple of four
+        {
+            VoxelRef v = row_ref(src, live ? b : 0);
+            const int fpad = (F + 3) & ~3;
+            for (int f = col; f < fpad; f += 4)
+                cur[row * stride + f] = (live && f < F) ? scaled(src, b, v, f, sc) : 0.0;
+        }
+        __syncwarp();
+        double* a_in = cur; double* a_out = nxt;
+        for (int l = 0; l < mv.n_layers; ++l) {
+            const int nin = mv.sizes[l], nout = mv.sizes[l + 1];
+            const double* __restrict__ W = mv.W[l];
+            const double* __restrict__ B = mv.b[l];
+            const bool last = l + 1 == mv.n_layers;
+            for (int n0 = 0; n0 < nout; n0 += 8) {
+                double d0 = 0.0, d1 = 0.0;
+                const int bn = n0 + row;                       // this lane's B column
+                for (int k0 = 0; k0 < nin; k0 += 4) {
+                    const double a = a_in[row * stride + k0 + col];
+                    const int bk = k0 + col;
+                    const double w = (bk < nin && bn < nout) ? __ldg(W + (i64)bk * nout + bn) : 0.0;
+                    dmma_8x8x4(d0, d1, a, w);
+                }
+                const int c0 = n0 + 2 * col, c1 = c0 + 1;
+                double y0 = 0.0, y1 = 0.0;
+                if (c0 < nout) { y0 = d0 + __ldg(B + c0); if (!last) y0 = mlp_act(y0, mv.act); }
+                if (c1 < nout) { y1 = d1 + __ldg(B + c1); if (!last) y1 = mlp_act(y1, mv.act); }
+                a_out[row * stride + c0] = y0;
+                a_out[row * stride + c1] = y1;
+            }
+            __syncwarp();
+            double* t = a_in; a_in = a_out; a_out = t;
+        }
+        if (live && col == 0) out[b] = a_in[row * stride];
+        __syncwarp();
+    }
+}
+
 // --------------------------------------------------------------------------------- launchers
 static FeatSrc matrix_source(const double* X, int F) {
     FeatSrc src;
@@ -722,6 +797,21 @@ static int mlp_launch(const FeatSrc& src, const i64* n_band, const double* mean,
         if (sizes[l] > mv.max_width) mv.max_width = sizes[l];
     }
     for (int l = 0; l < n_layers; ++l) { mv.W[l] = W[l]; mv.b[l] = b[l]; }
+    // tensor-core path (LSML_MLP_VARIANT=scalar selects the one-thread-per-voxel kernel below)
+    static const bool scalar_only = [] { const char* e = getenv("LSML_MLP_VARIANT"); return e && e[0] == 's'; }();
+    const int stride = ((mv.max_width + 15) & ~15) + 4;
+    const size_t dsmem = (size_t)DM_WARPS * 2 * 8 * stride * sizeof(double);
+    if (!scalar_only && dsmem <= 200 * 1024) {
+        static size_t configured = 0;
+        if (dsmem > 48 * 1024 && dsmem > configured) {
+            LSML_CUDA(cudaFuncSetAttribute(mlp_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)dsmem));
+            configured = dsmem;
+        }
+        mlp_dmma_kernel<<<LSML_SMS * 8, DM_THREADS, dsmem, s>>>(src, n_band, sc, mv, stride, out);
+        LSML_LAUNCH_CHECK("mlp_dmma_kernel");
+        return 0;
+    }
     const size_t smem = 2 * (size_t)mv.max_width * MLP_THREADS * sizeof(double);
     if (smem > 200 * 1024) { set_error("mlp: layer width %d too large", mv.max_width); return 1; }
     if (smem > 48 * 1024)

@@ -202,6 +202,30 @@ def test_regressors_against_sklearn(variant, monkeypatch):
                 (name, np.abs(got - want).max())
 
 
+def test_mlp_tensor_core_kernel_against_sklearn():
+    """The FP64 tensor-core (DMMA) MLP kernel: widths that are not multiples of 4 / 8, two hidden
+    layers, every activation, a batch that is not a multiple of the 8-voxel tile."""
+    import torch
+    from sklearn.neural_network import MLPRegressor
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from lsml_b200.core.regressors import export_regressor
+    rs = np.random.RandomState(3)
+    for F, hidden, act in ((16, (100,), "relu"), (13, (37, 9), "tanh"), (5, (10,), "logistic"),
+                           (22, (64, 33, 7), "identity")):
+        X = rs.randn(600, F) * (1 + 3 * rs.rand(F)) + rs.randn(F)
+        y = np.tanh(X[:, 0]) + 0.3 * X[:, F - 1] + 0.05 * rs.randn(600)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = Pipeline([("s", StandardScaler()),
+                          ("r", MLPRegressor(hidden_layer_sizes=hidden, activation=act, max_iter=30,
+                                             random_state=0))]).fit(X, y)
+        Xt = rs.randn(1003, F) * 2
+        got = export_regressor(m).predict(torch.from_numpy(Xt).cuda()).cpu().numpy()
+        want = m.predict(Xt)
+        assert np.allclose(got, want, rtol=1e-11, atol=1e-12), (F, hidden, act, np.abs(got - want).max())
+
+
 def test_ranked_forest_shapes():
     """The shared-memory forest kernel at its corners: more trees than one staged group holds,
     64 features (one CTA per SM), a batch that is not a multiple of the chunk, NaN features."""
