@@ -366,6 +366,8 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
     __shared__ u8 s_rootleaf[RK_MAX_GROUP];
     __shared__ int s_t1;
     __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned char s_itemf[64];            // the per-ITEM columns of the feature program
+    __shared__ int s_nitemf;
     constexpr int N = V * THREADS;
     const int F = src.F;
     unsigned* const ranks = rk_smem;                 // [F][N], feature | rank (node word fields)
@@ -382,8 +384,18 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
     if (threadIdx.x == 0) {
         rk_mbar_init(bar_sa, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // columns that have ONE value per item (band mean / std, size, moments, ...): a warp whose
+        // 32 voxels belong to one item ranks each of them once, on one lane
+        int cnt = 0;
+        if (src.X == nullptr)
+            for (int f = 0; f < src.F; ++f) {
+                const int kind = src.bf.prog.kind[f];
+                if (kind != FK_PLANE && kind != FK_DIST_COM && kind != FK_COM_RAY) s_itemf[cnt++] = (unsigned char)f;
+            }
+        s_nitemf = cnt;
     }
     __syncthreads();
+    const int n_itemf = s_nitemf;
     const i64 nb = *n_band;
     const i64 nchunks = (nb + N - 1) / N;
     for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -396,14 +408,42 @@ forest_ranked_kernel(FeatSrc src, const i64* __restrict__ n_band, Scaler sc, Ran
         for (int v = 0; v < V; ++v) {
             const int slot = v * THREADS + threadIdx.x;
             const i64 b = chunk * N + slot;
-            if (b < nb) {
+            const bool live = b < nb;
+            const VoxelRef vr = row_ref(src, live ? b : 0);
+            int same = 0;                            // all 32 voxels of the warp live, in one item
+            if (n_itemf > 0) __match_all_sync(0xffffffffu, live ? vr.item : (i64)-1 - (threadIdx.x & 31), &same);
+            if (live) {
                 valid |= 1u << v;
-                const VoxelRef vr = row_ref(src, b);
                 for (int f = 0; f < F; ++f) {
+                    if (same) {
+                        const int kind = src.bf.prog.kind[f];
+                        if (kind != FK_PLANE && kind != FK_DIST_COM && kind != FK_COM_RAY) continue;
+                    }
                     const float x = __double2float_rn(scaled(src, b, vr, f, sc));
                     const unsigned r = rank_of(rv.thr_tab, __ldg(rv.thr_off + f),
                                                __ldg(rv.thr_off + f + 1), x);
                     ranks[f * N + slot] = ((unsigned)f << fshift) | (r << rshift);
+                }
+            }
+            if (same) {
+                // lane i ranks the i-th per-item column (all searches side by side instead of
+                // one after the other on every lane), then the words are handed round
+                const int lane = threadIdx.x & 31;
+                for (int base = 0; base < n_itemf; base += 32) {
+                    const int cnt = min(32, n_itemf - base);
+                    unsigned word = 0u, fcol = 0u;
+                    if (lane < cnt) {
+                        fcol = s_itemf[base + lane];
+                        const float x = __double2float_rn(scaled(src, b, vr, (int)fcol, sc));
+                        const unsigned r = rank_of(rv.thr_tab, __ldg(rv.thr_off + fcol),
+                                                   __ldg(rv.thr_off + fcol + 1), x);
+                        word = (fcol << fshift) | (r << rshift);
+                    }
+                    for (int j = 0; j < cnt; ++j) {
+                        const unsigned w = __shfl_sync(0xffffffffu, word, j);
+                        const unsigned fj = __shfl_sync(0xffffffffu, fcol, j);
+                        ranks[fj * N + slot] = w;
+                    }
                 }
             }
         }
