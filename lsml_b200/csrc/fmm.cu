@@ -113,6 +113,8 @@ struct FmmCounters {      // device-resident
     i64 live[4];          // {sweep, rix, begin, end} published by thread 0 before every grid-wide
                           // step: readable from another stream while a march is running (hang
                           // diagnosis, tools/c4_probe.py)
+    i64 hint_slack;       // s > 0: hints are written as depth + (depth >> s) (batches, see
+                          // process_candidate); 0: the depth itself
     i64 phase[8];         // -DFMM_PHASE_CLOCKS: SM cycles one lane spent per phase of the small
                           // grid-wide sweeps {loop top -> entry, replay, record, publish, fence,
                           // barrier, -, number of sweeps sampled} (diagnostic, tools/fmm_probe.py)
@@ -220,7 +222,7 @@ fmm_clear_kernel(double* __restrict__ T, Aux* __restrict__ aux, u8* __restrict__
 // Start of a rebuild (one CTA of 256 threads): reset the per-rebuild counters, advance the hint
 // generation, turn last rebuild's hint histogram into parking-bucket offsets.
 __global__ void __launch_bounds__(256)
-fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap) {
+fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap, int hint_slack) {
     __shared__ i64 scan[256];
     const int t = threadIdx.x;
     if (t == 0) {
@@ -229,6 +231,7 @@ fmm_prepare_kernel(FmmCounters* ctr, int allow_hints, i64 park_cap) {
         ctr->resume_sweep = 1; ctr->resume_rix = 1; ctr->resume_begin = 0;
         ctr->overflow[0] = 0; ctr->overflow[1] = 0; ctr->overflow[2] = 0;
         ctr->last_bucket = 0;
+        ctr->hint_slack = hint_slack;
         ctr->gen = ctr->gen + 1;
     }
     __syncthreads();
@@ -420,6 +423,7 @@ struct Sched {
     int tslot;           // its counter: tail3[tslot]
     unsigned hint_tag;   // (tag of the previous rebuild) << 8, or ~0 when hints are off
     int ovf_slot;
+    unsigned slack;      // FmmCounters::hint_slack (0 when not given: off)
 };
 
 // sweep a voxel with hint word `lvl` should be queued for: the next one, or later if last
@@ -947,6 +951,10 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     // the hint is the SWEEP the voxel should be evaluated at next time: its depth, plus
     // (-DFMM_HINT_SLACK_SHIFT=n) depth >> n sweeps of slack that absorb small shifts of the
     // dependency structure upstream instead of cascading them into re-evaluations downstream
+    // On BATCHES (thousands of items per rebuild: throughput-bound, a sweep costs what its entries
+    // cost) the slack pays: -12 % replays for +20 % sweeps at depth / 4, C4 rebuild -4 %.  On one
+    // volume (latency-bound: every sweep costs its 13.5 us floor) it costs +8..12 %, so it is
+    // off there (fmm_rebuild: batch >= 16).
 #if defined(FMM_HINT_SLACK_SHIFT)
     const unsigned hint = level + (level >> FMM_HINT_SLACK_SHIFT);
 #elif defined(FMM_HINT_EARLY)
@@ -955,7 +963,7 @@ __device__ __forceinline__ void process_candidate(i64 e, const double* __restric
     // adds sweeps; an early one only costs a replay)
     const unsigned hint = level > FMM_HINT_EARLY ? level - FMM_HINT_EARLY : 1u;
 #else
-    const unsigned hint = level;
+    const unsigned hint = sc.slack ? level + (level >> sc.slack) : level;
 #endif
     if (lvl != (gen_tag | hint)) {
         if ((lvl & 0xff00u) == gen_tag) warp_agg_add(hist, lvl & 0xffu, -1);
@@ -1002,6 +1010,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
     const bool hints = ctr->use_hints != 0;
     const unsigned gen_tag = hint_tag_of(ctr->gen);
     const unsigned hint_tag = hints ? hint_tag_of(ctr->gen - 1) : 0xffffffffu;
+    const unsigned slack = (unsigned)ctr->hint_slack;
     i64* const hist_cur = ctr->hist[ctr->gen & 1];
     // (a rebuild is one launch on a single GPU; a slab-decomposed rebuild launches again after
     // every halo exchange and continues where the previous launch stopped)
@@ -1063,7 +1072,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                     if (work > FMM_TAIL_MAX) break;
                     if (threadIdx.x == 0 && inner > 0) vtail[(rix + 2u) % 3u] = 0;
                     const Sched sc{aux, ring, park, ctr, b, e, sweep + 1u, (int)((rix + 1u) % 3u),
-                                   hint_tag, slot};
+                                   hint_tag, slot, slack};
                     const i64 pbase = nbk ? ctr->offs[sweep] : 0;
                     for (i64 k = threadIdx.x; k < work; k += FMM_THREADS) {
                         const i64 ent = k < e - b ? ring.slots[(b + k) & (ring.cap - 1)]
@@ -1100,7 +1109,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
         }
         if (!scan) {
             const Sched sc{aux, ring, park, ctr, begin, end, sweep + 1u, (int)((rix + 1u) % 3u),
-                           hint_tag, slot};
+                           hint_tag, slot, slack};
             const i64 work = end - begin + nbk;
             const i64 pbase = nbk ? ctr->offs[sweep] : 0;
             // The work set is dealt to the warps in CHUNKS of G consecutive entries (entries
@@ -1164,7 +1173,7 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
             // ---- fallback: scan the candidate list; a warp collects its queued entries in
             // shared memory and evaluates them 32 at a time
             const Sched sc{aux, ring, park, ctr, end, end, sweep + 1u, (int)((rix + 1u) % 3u),
-                           hint_tag, slot};
+                           hint_tag, slot, slack};
             const i64 nc = *reinterpret_cast<volatile i64*>(&ctr->n_cand);
             int qn = 0;
             for (i64 base = gwarp * 32; base < nc; base += nwarps * 32) {
@@ -1435,8 +1444,9 @@ static int begin_nd(const Geom& g, const FmmGeom& fg, const double* u, const u64
     static const bool no_hints = getenv("LSML_FMM_NO_HINTS") != nullptr;      // A/B switch (probes)
     fmm_clear_kernel<<<LSML_SMS * 8, 256, 0, s>>>(w.T, w.aux, mask, w.list, total, fg, w.ctr, total);
     LSML_LAUNCH_CHECK("fmm_clear_kernel");
+    static const bool no_slack = getenv("LSML_FMM_NO_SLACK") != nullptr;      // A/B switch (probes)
     fmm_prepare_kernel<<<1, 256, 0, s>>>(w.ctr, (prev_band_idx != nullptr && !no_hints) ? 1 : 0,
-                                         w.ring.cap);
+                                         w.ring.cap, (g.batch >= 16 && !no_slack) ? 2 : 0);
     LSML_LAUNCH_CHECK("fmm_prepare_kernel");
     dim3 grid, block;
     if (prev_band_idx != nullptr) {

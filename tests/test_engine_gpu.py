@@ -66,6 +66,24 @@ def test_image_planes_bit_exact(oracle, shape, dx):
             assert np.array_equal(got[b], want), (what, sigma, np.abs(got[b] - want).max())
 
 
+@pytest.mark.parametrize("shape,dx", [((5, 40, 48), (1.0, 1.0, 1.0)), ((70, 33, 64), (1.0, 0.5, 1.0)),
+                                      ((3, 130), (1.0, 1.0))])
+def test_image_planes_bit_exact_marched_axes(oracle, shape, dx):
+    """The register-march Gaussian (strided axes, features.cu: gauss1d_march_kernel) at its
+    corners: a column shorter than the filter radius (several reflections), a column longer than
+    one ring length, radii 4 / 8 / 16 and the fall-back beyond 16, both marched axes of a volume."""
+    specs = [("image_sample", 1), ("image_sample", 2), ("image_sample", 4), ("image_edge", 2),
+             ("image_edge", 4.4)]
+    eng, imgs, us = build_engine(shape, 2, dx, specs, normalize=False)
+    dxa = np.asarray(dx)
+    for p, (what, sigma) in enumerate(eng.program.planes):
+        got = eng.planes[p].cpu().numpy()
+        for b in range(2):
+            want = (oracle.image_sample_plane(imgs[b], sigma, dxa) if what == "sample"
+                    else oracle.image_edge_plane(imgs[b], sigma, dxa))
+            assert np.array_equal(got[b], want), (what, sigma, np.abs(got[b] - want).max())
+
+
 def test_normalize_matches_numpy(oracle):
     eng, imgs, us = build_engine((33, 45), 3, (1, 1), [("image_sample", 0)], normalize=True)
     got = eng.img.cpu().numpy()
