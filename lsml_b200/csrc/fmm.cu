@@ -793,7 +793,15 @@ constexpr int FMM_WARPS = FMM_THREADS / 32;
 #ifndef FMM_MIN_BLOCKS
 #define FMM_MIN_BLOCKS 4
 #endif
-constexpr int FMM_TAIL_MAX = 2 * FMM_THREADS;   // dirty sets this small are swept by ONE CTA
+// Dirty sets this small are swept by ONE CTA with block barriers (two entries per warp at most:
+// a sweep then costs one replay + publish, ~8 us, instead of the grid-wide floor of 13.5 us).
+// Up to 256 entries, as first built, the tail COST time: 32 unrelated entries share a warp as
+// divergent lanes, ~20 us per sweep -- 1072 / 1252 / 1311 us per 256^3 rebuild against 1036 /
+// 1195 / 1203 us with 8 (and 1026 / 1166 / 1195 us with the tail switched off altogether).
+#ifndef FMM_TAIL_MAX_ENTRIES
+#define FMM_TAIL_MAX_ENTRIES 8
+#endif
+constexpr int FMM_TAIL_MAX = FMM_TAIL_MAX_ENTRIES;
 
 // x (entry e, index l) changed from magnitude q_old to q_new during sweep `cur`: queue, for the
 // next sweep, every candidate whose stencil contains x and whose result can depend on it.
@@ -1074,7 +1082,9 @@ fmm_march_kernel(const double* __restrict__ u, double* T, Aux* aux, u8* mask, i6
                     const Sched sc{aux, ring, park, ctr, b, e, sweep + 1u, (int)((rix + 1u) % 3u),
                                    hint_tag, slot, slack};
                     const i64 pbase = nbk ? ctr->offs[sweep] : 0;
-                    for (i64 k = threadIdx.x; k < work; k += FMM_THREADS) {
+                    // (entry k to warp k % 4, lane k / 4: the few entries of a tail sweep each get
+                    // a warp of their own instead of sharing one as divergent lanes)
+                    for (i64 k = (i64)lane * FMM_WARPS + warp; k < work; k += FMM_THREADS) {
                         const i64 ent = k < e - b ? ring.slots[(b + k) & (ring.cap - 1)]
                                                   : park[pbase + k - (e - b)];
                         process_candidate<NDIM>(ent, u, T, mask, list, cap, g, band, sc, gen_tag, hist_cur);
