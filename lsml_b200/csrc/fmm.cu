@@ -790,8 +790,12 @@ constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s a
 constexpr unsigned FMM_SWEEP_LIMIT = 1u << 16;
 constexpr int FMM_THREADS = 128;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
+// CTAs per SM the kernel is compiled for.  3 (166 registers per thread: no local-memory traffic
+// for the replay's state) beats 4 (128 registers) on one volume -- 1011 / 1113 us against 1036 /
+// 1195 us per 256^3 rebuild: a sweep is bound by the latency of ONE lane's replay, not by the
+// number of warps -- and ties on batches (1583 vs 1587 ms per C4 engine batch); 5 (96) loses.
 #ifndef FMM_MIN_BLOCKS
-#define FMM_MIN_BLOCKS 4
+#define FMM_MIN_BLOCKS 3
 #endif
 // Dirty sets this small are swept by ONE CTA with block barriers (two entries per warp at most:
 // a sweep then costs one replay + publish, ~8 us, instead of the grid-wide floor of 13.5 us).
