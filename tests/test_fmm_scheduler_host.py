@@ -58,6 +58,10 @@ class HostScheduler:
     def set_gen(self, gen):
         self.lib.hs_set_gen(self.h, ctypes.c_longlong(gen))
 
+    def set_slack(self, slack):
+        """Hint slack of batch rebuilds: hints are written as depth + (depth >> slack), 0 = off."""
+        self.lib.hs_set_slack(self.h, ctypes.c_longlong(slack))
+
     def set_order(self, order):
         """Evaluation order inside a sweep: 0 as queued, 1 reversed, 2 shuffled."""
         self.lib.hs_set_order(self.h, ctypes.c_int(order))
@@ -109,6 +113,7 @@ def test_scheduler_source_reproduces_marcher_on_evolving_batches(oracle, sched_l
         hs = HostScheduler(sched_lib, shape, batch, dx)
         hs.set_gen(int(rs.choice([0, 14, 120, 124, 250, 252, 380, 507])))     # tag wrap / wipes
         hs.set_order(case % 3)              # the result may not depend on the order within a sweep
+        hs.set_slack(2 if case >= 3 else 0)  # ... nor on the hint slack batch rebuilds run with
         us = _items(rs, shape, batch)
         if batch > 1 and case % 3 == 0:
             us[-1] = -1.0                           # an item without a contour stays untouched
