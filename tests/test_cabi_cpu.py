@@ -34,6 +34,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.lsml_version() >= 100
 
 
+def test_sass_carries_the_blackwell_instructions_the_design_claims():
+    """DESIGN.md names three hardware paths; the built library must contain them: TMA tensor loads
+    (dense stencils), a bulk global->shared copy completing on an mbarrier (tree groups of the
+    ranked forest kernel) and FP64 tensor-core MMAs (MLP layers).  Needs cuobjdump (CUDA toolkit)."""
+    import shutil, subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from lsml_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper() or "EF_CUDA_SM100" in sass
+    for mnemonic, where in (("UTMALDG", "gmag_os_tma_kernel"), ("UBLKCP", "forest_ranked_kernel"),
+                            ("SYNCS", "mbarrier waits"), ("DMMA", "mlp_dmma_kernel")):
+        assert mnemonic in sass, "%s (%s) missing from the SASS of %s" % (mnemonic, where, _lib.LIB_PATH)
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
