@@ -788,7 +788,12 @@ constexpr int FMM_MAX_SWEEPS = 1 << 16;   // grid-wide sweeps per launch; ~1 s a
 // contributor rule of DESIGN.md 4.6 is what rules it out) and ends with `converged` = 0 after a
 // fraction of a second instead of never.
 constexpr unsigned FMM_SWEEP_LIMIT = 1u << 16;
-constexpr int FMM_THREADS = 128;
+// (the same 12 warps per SM as 2 CTAs of 192 or 1 CTA of 384 threads -- fewer participants in the
+// grid barrier -- measured 992 / 1131 and 1031 / 1144 us per 256^3 rebuild against 1004 / 1132)
+#ifndef FMM_THREADS_PER_CTA
+#define FMM_THREADS_PER_CTA 128
+#endif
+constexpr int FMM_THREADS = FMM_THREADS_PER_CTA;
 constexpr int FMM_WARPS = FMM_THREADS / 32;
 // CTAs per SM the kernel is compiled for.  3 (166 registers per thread: no local-memory traffic
 // for the replay's state) beats 4 (128 registers) on one volume -- 1011 / 1113 us against 1036 /
